@@ -1,0 +1,66 @@
+// device_ctx.h -- device-resident tables of one CKKS parameter set + launch helpers shared by kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "params.h"
+
+namespace flk {
+
+#define FLK_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__));                   \
+    } while (0)
+
+constexpr int kMaxLimbSel = 160;
+constexpr int kRadix1Log = 4;   // stages done by the register-only column pass (strides N/2 .. N/16)
+
+// Passed by value to kernels.
+struct DevTables {
+    const u64* q;        // [T]
+    const u64* mu_lo;    // [T] floor(2^128/q) low / high words
+    const u64* mu_hi;
+    const u64* tw;       // [T][N] psi^bitrev(i)
+    const u64* tw_sh;
+    const u64* itw;      // [T][N] psi^-bitrev(i)
+    const u64* itw_sh;
+    const u64* ninv;     // [T]
+    const u64* ninv_sh;
+    int logN, N, L, K;
+};
+
+// modulus index of every limb of a buffer (limb-major [n][N])
+struct LimbSel {
+    int n;
+    uint8_t m[kMaxLimbSel];     // modulus index
+    uint8_t pos[kMaxLimbSel];   // limb slot inside the buffer (NTT kernels only; identity elsewhere)
+};
+
+inline LimbSel sel_range(int first_mod, int count) {
+    LimbSel s; s.n = count;
+    for (int i = 0; i < count; ++i) { s.m[i] = (uint8_t)(first_mod + i); s.pos[i] = (uint8_t)i; }
+    return s;
+}
+// Q limbs 0..l-1 followed by the K P limbs
+inline LimbSel sel_ext(int l, int L, int K) {
+    LimbSel s; s.n = l + K;
+    for (int i = 0; i < l; ++i) { s.m[i] = (uint8_t)i; s.pos[i] = (uint8_t)i; }
+    for (int k = 0; k < K; ++k) { s.m[l + k] = (uint8_t)(L + k); s.pos[l + k] = (uint8_t)(l + k); }
+    return s;
+}
+
+// ---- kernel launchers (definitions in the .cu files) ----
+// In-place negacyclic NTT of `batch` buffers of sel.n limbs each (buffers batch_stride words apart).
+void launch_ntt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, cudaStream_t s);
+// Inverse; multiplies by post[m] (Shoup pair post_sh[m]), indexed by modulus, instead of N^-1 when post != nullptr.
+void launch_intt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, const u64* post,
+                 const u64* post_sh, cudaStream_t s);
+
+}  // namespace flk

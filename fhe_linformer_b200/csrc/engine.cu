@@ -1,0 +1,248 @@
+// engine.cu -- device engine: table upload and the hybrid key-switch / rescale / rotate pipelines.
+// Reference call sites replaced: context->EvalRotate (FHEController.cpp:435,833,843), the relinearisation
+// inside context->EvalMult(ct,ct) (:431) and the implicit FLEXIBLEAUTO rescale (:18); algorithms per
+// SURVEY.md Appendix A.5-A.7.
+#include "engine.h"
+
+#include <cstring>
+
+namespace flk {
+
+template <class V>
+V* Engine::to_device(const std::vector<V>& h) {
+    V* d = nullptr;
+    FLK_CUDA(cudaMalloc(&d, std::max<size_t>(1, h.size()) * sizeof(V)));
+    FLK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+    owned_.push_back(d);
+    return d;
+}
+
+Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw std::runtime_error("fhe_linformer_b200: no CUDA device available (this engine has no CPU fallback)");
+    if (device >= 0) FLK_CUDA(cudaSetDevice(device));
+    FLK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int dev = 0;
+    FLK_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    FLK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;
+    FLK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+
+    const int Tn = P.T, N = P.N;
+    std::vector<u64> tw((size_t)Tn * N), tws(tw.size()), itw(tw.size()), itws(tw.size());
+    for (int m = 0; m < Tn; ++m)
+        P.twiddles(m, &tw[(size_t)m * N], &tws[(size_t)m * N], &itw[(size_t)m * N], &itws[(size_t)m * N]);
+    T.q = to_device(P.q); T.mu_lo = to_device(P.mu_lo); T.mu_hi = to_device(P.mu_hi);
+    T.tw = to_device(tw); T.tw_sh = to_device(tws); T.itw = to_device(itw); T.itw_sh = to_device(itws);
+    T.ninv = to_device(P.ninv); T.ninv_sh = to_device(P.ninv_sh);
+    T.logN = P.logN; T.N = N; T.L = P.L; T.K = P.K;
+
+    // ModDown constants (A.6)
+    {
+        std::vector<int> sm(P.K);
+        for (int k = 0; k < P.K; ++k) sm[k] = P.L + k;
+        std::vector<u64> hatinv(P.K), post(Tn, 0), post_sh(Tn, 0), phm((size_t)P.K * P.L), pinv(P.L), pinv_sh(P.L);
+        P.conv_hatinv(sm.data(), P.K, hatinv.data());
+        for (int k = 0; k < P.K; ++k) {
+            u64 qq = P.q[P.L + k];
+            post[P.L + k] = nt::mulmod(P.ninv[P.L + k], hatinv[k], qq);
+            post_sh[P.L + k] = nt::shoup(post[P.L + k], qq);
+            for (int i = 0; i < P.L; ++i) phm[(size_t)k * P.L + i] = P.conv_hat_mod(sm.data(), P.K, k, P.q[i]);
+        }
+        for (int i = 0; i < P.L; ++i) {
+            pinv[i] = nt::invmod(P.P_mod(P.q[i]), P.q[i]);
+            pinv_sh[i] = nt::shoup(pinv[i], P.q[i]);
+        }
+        md_.post = to_device(post); md_.post_sh = to_device(post_sh); md_.phm = to_device(phm);
+        md_.pinv = to_device(pinv); md_.pinv_sh = to_device(pinv_sh);
+    }
+    // rescale constants (A.7)
+    {
+        std::vector<u64> inv((size_t)P.L * P.L, 0), inv_sh(inv.size(), 0);
+        for (int r = 0; r < P.L; ++r)
+            for (int i = 0; i < r; ++i) {
+                inv[(size_t)r * P.L + i] = nt::invmod(P.q[r] % P.q[i], P.q[i]);
+                inv_sh[(size_t)r * P.L + i] = nt::shoup(inv[(size_t)r * P.L + i], P.q[i]);
+            }
+        rs_.qlinv = to_device(inv); rs_.qlinv_sh = to_device(inv_sh);
+    }
+}
+
+Engine::~Engine() {
+    cudaStreamSynchronize(stream);
+    for (auto& kv : maps_) cudaFree(kv.second);
+    for (void* p : owned_) cudaFree(p);
+    cudaStreamDestroy(stream);
+}
+
+u64* Engine::alloc(size_t words) {
+    u64* p = nullptr;
+    FLK_CUDA(cudaMallocAsync(&p, std::max<size_t>(words, 1) * 8, stream));
+    return p;
+}
+void Engine::release(u64* p) { if (p) FLK_CUDA(cudaFreeAsync(p, stream)); }
+void Engine::upload(u64* dst, const u64* src, size_t words) { FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyHostToDevice, stream)); }
+void Engine::download(u64* dst, const u64* src, size_t words) {
+    FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyDeviceToHost, stream));
+    FLK_CUDA(cudaStreamSynchronize(stream));
+}
+void Engine::copy(u64* dst, const u64* src, size_t words) { FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyDeviceToDevice, stream)); }
+void Engine::sync() { FLK_CUDA(cudaStreamSynchronize(stream)); }
+
+void Engine::ntt(u64* data, const LimbSel& sel, int batch, size_t bs) { launch_ntt(T, data, sel, batch, bs, stream); }
+void Engine::intt(u64* data, const LimbSel& sel, int batch, size_t bs) { launch_intt(T, data, sel, batch, bs, nullptr, nullptr, stream); }
+
+void Engine::ew(EwOp op, u64* out, const u64* a, const u64* b, int l, int polys, bool broadcast_b) {
+    launch_ew(T, op, out, a, b, sel_range(0, l), polys, 1, 0, 0, broadcast_b ? 0 : (size_t)l * P.N, stream);
+}
+void Engine::ew_sel(EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel) {
+    launch_ew(T, op, out, a, b, sel, 1, 1, 0, 0, 0, stream);
+}
+
+const uint32_t* Engine::automorph_map(uint32_t g) {
+    auto it = maps_.find(g);
+    if (it != maps_.end()) return it->second;
+    std::vector<uint32_t> h(P.N);
+    P.automorph_map(g, h.data());
+    uint32_t* d = nullptr;
+    FLK_CUDA(cudaMalloc(&d, (size_t)P.N * 4));
+    FLK_CUDA(cudaMemcpy(d, h.data(), (size_t)P.N * 4, cudaMemcpyHostToDevice));
+    maps_[g] = d;
+    return d;
+}
+
+void Engine::automorph(u64* out, const u64* in, uint32_t g, int limbs) { launch_automorph(out, in, automorph_map(g), P.N, limbs, stream); }
+
+const KsLevel& Engine::ks_level(int l) {
+    auto it = ks_.find(l);
+    if (it != ks_.end()) return it->second;
+    if (l < 1 || l > P.L) throw std::invalid_argument("key switch: limb count out of range");
+    const int beta = P.beta(l), ext = l + P.K, a = P.alpha;
+    std::vector<u64> post(P.T, 0), post_sh(P.T, 0), hm((size_t)beta * a * ext, 0);
+    for (int d = 0; d < beta; ++d) {
+        const int lo = d * a, hi = std::min(lo + a, l), ns = hi - lo;
+        std::vector<int> sm(ns);
+        for (int i = 0; i < ns; ++i) sm[i] = lo + i;
+        std::vector<u64> hatinv(ns);
+        P.conv_hatinv(sm.data(), ns, hatinv.data());
+        for (int i = 0; i < ns; ++i) {
+            const int m = lo + i;
+            post[m] = nt::mulmod(P.ninv[m], hatinv[i], P.q[m]);
+            post_sh[m] = nt::shoup(post[m], P.q[m]);
+            for (int t = 0; t < ext; ++t)
+                hm[((size_t)d * a + i) * ext + t] = P.conv_hat_mod(sm.data(), ns, i, P.q[P.mod_index_ext(l, t)]);
+        }
+    }
+    KsLevel k;
+    k.post = to_device(post); k.post_sh = to_device(post_sh); k.hm = to_device(hm);
+    k.l = l; k.beta = beta; k.alpha = a;
+    return ks_.emplace(l, k).first->second;
+}
+
+void Engine::rescale(u64* out, const u64* in, int l, int polys) {
+    if (l < 2) throw std::invalid_argument("rescale: no limb left to drop");
+    const int N = P.N;
+    u64* xlast = alloc((size_t)polys * N);
+    for (int p = 0; p < polys; ++p) copy(xlast + (size_t)p * N, in + ((size_t)p * l + (l - 1)) * N, N);
+    LimbSel s1; s1.n = polys;
+    for (int p = 0; p < polys; ++p) { s1.m[p] = (uint8_t)(l - 1); s1.pos[p] = (uint8_t)p; }
+    intt(xlast, s1);
+    u64* tq = alloc((size_t)polys * (l - 1) * N);
+    launch_rescale_conv(T, tq, xlast, l, polys, stream);
+    LimbSel s2; s2.n = polys * (l - 1);
+    for (int p = 0; p < polys; ++p)
+        for (int i = 0; i < l - 1; ++i) { s2.m[p * (l - 1) + i] = (uint8_t)i; s2.pos[p * (l - 1) + i] = (uint8_t)(p * (l - 1) + i); }
+    ntt(tq, s2);
+    launch_rescale_finish(T, rs_, out, in, tq, l, polys, stream);
+    release(xlast); release(tq);
+    if (ledger_on) ledger.add("rescale", l, (double)polys / 2 * (32.0 * l - 16.0) * N);
+}
+
+void Engine::keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g) {
+    const KsLevel& ks = ks_level(l);
+    const int N = P.N, K = P.K, ext = l + K, beta = ks.beta;
+    // 1. digits to coefficient form, pre-scaled by (Q_d/q_i)^-1
+    u64* dco = alloc((size_t)l * N);
+    copy(dco, c, (size_t)l * N);
+    launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
+    // 2. ModUp: basis-extend every digit to the limbs outside it, back to evaluation form
+    u64* up = alloc((size_t)beta * ext * N);
+    launch_modup_conv(T, ks, up, dco, stream);
+    LimbSel su; su.n = 0;
+    for (int d = 0; d < beta; ++d) {
+        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
+        for (int t = 0; t < ext; ++t) {
+            if (t >= lo && t < hi) continue;
+            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+        }
+    }
+    ntt(up, su);
+    // 3. inner product with the evaluation key over Q_l u P
+    u64* acc = alloc((size_t)2 * ext * N);
+    launch_inner_product(T, ks, acc, acc + (size_t)ext * N, up, c, evk, stream);
+    // 4. ModDown both accumulators
+    LimbSel sp; sp.n = 2 * K;
+    for (int p = 0; p < 2; ++p)
+        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+    launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
+    u64* tq = alloc((size_t)2 * l * N);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, stream);
+    LimbSel sq; sq.n = 2 * l;
+    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    ntt(tq, sq);
+    launch_moddown_finish(T, md_, out, acc, (size_t)ext * N, tq, add0, add1, g ? automorph_map(g) : nullptr, l, 2, stream);
+    release(dco); release(up); release(acc); release(tq);
+}
+
+void Engine::rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) {
+    keyswitch(out, ct + (size_t)l * P.N, evk, l, ct, nullptr, g);
+    if (ledger_on) ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
+}
+
+void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) {
+    const size_t pl = (size_t)l * P.N;
+    u64* d = alloc(3 * pl);
+    launch_tensor(T, d, d + pl, d + 2 * pl, a, b, l, stream);
+    keyswitch(out, d + 2 * pl, evk, l, d, d + pl, 0);
+    release(d);
+    if (ledger_on) ledger.add("mul_relin", l, (6.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
+}
+
+void Engine::modup(u64* out_ext, const u64* c_eval, int l, int digit) {
+    const KsLevel& ks = ks_level(l);
+    const int N = P.N, ext = l + P.K;
+    u64* dco = alloc((size_t)l * N);
+    copy(dco, c_eval, (size_t)l * N);
+    launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
+    u64* up = alloc((size_t)ks.beta * ext * N);
+    launch_modup_conv(T, ks, up, dco, stream);
+    const int lo = digit * ks.alpha, hi = std::min(lo + ks.alpha, l);
+    LimbSel su; su.n = 0;
+    for (int t = 0; t < ext; ++t) {
+        if (t >= lo && t < hi) continue;
+        su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(digit * ext + t); su.n++;
+    }
+    ntt(up, su);
+    copy(out_ext, up + (size_t)digit * ext * N, (size_t)ext * N);
+    copy(out_ext + (size_t)lo * N, c_eval + (size_t)lo * N, (size_t)(hi - lo) * N);
+    release(dco); release(up);
+}
+
+void Engine::moddown(u64* out, const u64* in_ext, int l) {
+    const int N = P.N, K = P.K, ext = l + K;
+    u64* acc = alloc((size_t)ext * N);
+    copy(acc, in_ext, (size_t)ext * N);
+    LimbSel sp; sp.n = K;
+    for (int k = 0; k < K; ++k) { sp.m[k] = (uint8_t)(P.L + k); sp.pos[k] = (uint8_t)(l + k); }
+    launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
+    u64* tq = alloc((size_t)l * N);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 1, stream);
+    ntt(tq, sel_range(0, l));
+    launch_moddown_finish(T, md_, out, acc, (size_t)ext * N, tq, nullptr, nullptr, nullptr, l, 1, stream);
+    release(acc); release(tq);
+}
+
+}  // namespace flk

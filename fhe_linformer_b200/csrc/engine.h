@@ -1,0 +1,74 @@
+// engine.h -- device engine: owns the parameter tables in HBM, the stream, and the primitive
+// operations on raw limb-major device buffers.  The CKKS scheme layer (scheme.h) and the C-ABI sit on top.
+#pragma once
+#include <map>
+#include <memory>
+#include <unordered_map>
+#include <vector>
+
+#include "device_ctx.h"
+#include "kernels.cuh"
+
+namespace flk {
+
+struct OpLedger {   // algorithmic-byte accounting per SURVEY.md section 8(d)
+    struct Row { long count = 0; double bytes = 0; };
+    std::map<std::string, Row> rows;
+    void add(const std::string& op, int l, double bytes) {
+        Row& r = rows[op + "@" + std::to_string(l)];
+        r.count++; r.bytes += bytes;
+    }
+    void reset() { rows.clear(); }
+};
+
+class Engine {
+public:
+    explicit Engine(const ParamSpec& spec, int device = -1);
+    ~Engine();
+    Engine(const Engine&) = delete;
+
+    const Params P;
+    DevTables T{};
+    cudaStream_t stream = nullptr;
+    OpLedger ledger;
+    bool ledger_on = false;
+
+    // memory (stream-ordered pool)
+    u64* alloc(size_t words);
+    void release(u64* p);
+    void upload(u64* dst, const u64* src, size_t words);
+    void download(u64* dst, const u64* src, size_t words);
+    void copy(u64* dst, const u64* src, size_t words);
+    void sync();
+
+    // --- primitives on device buffers (all asynchronous on `stream`) ---
+    void ntt(u64* data, const LimbSel& sel, int batch = 1, size_t batch_stride = 0);
+    void intt(u64* data, const LimbSel& sel, int batch = 1, size_t batch_stride = 0);
+    void ew(EwOp op, u64* out, const u64* a, const u64* b, int l, int polys, bool broadcast_b);
+    void ew_sel(EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel);
+    void automorph(u64* out, const u64* in, uint32_t g, int limbs);
+    void rescale(u64* out, const u64* in, int l, int polys);
+    // out[2][l][N] = KeySwitch(c) (+add0 / +add1), optionally permuted by the automorphism map of g (0 = none)
+    void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
+    void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
+    void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
+    // pieces exposed for parity tests
+    void modup(u64* out_ext, const u64* c_eval, int l, int digit);     // out: (l+K) limbs eval
+    void moddown(u64* out, const u64* in_ext, int l);                  // in: (l+K) limbs eval
+
+    const uint32_t* automorph_map(uint32_t g);
+    const KsLevel& ks_level(int l);
+    const MdConst& md() const { return md_; }
+    const RsConst& rs() const { return rs_; }
+    size_t evk_words() const { return (size_t)P.dnum * 2 * P.T * P.N; }
+
+private:
+    std::vector<void*> owned_;
+    template <class V> V* to_device(const std::vector<V>& h);
+    std::unordered_map<int, KsLevel> ks_;
+    std::unordered_map<uint32_t, uint32_t*> maps_;
+    MdConst md_{};
+    RsConst rs_{};
+};
+
+}  // namespace flk

@@ -1,0 +1,295 @@
+// kernels.cu -- element-wise, automorphism, base-conversion, inner-product, ModDown and rescale kernels
+// (K2-K7 of SURVEY.md 2.1) for sm_100a.  All are HBM-streaming integer kernels: limb-major layout,
+// adjacent threads on adjacent coefficients, 128-bit accumulators reduced once.
+#include "kernels.cuh"
+#include "modarith.cuh"
+
+namespace flk {
+namespace {
+using namespace dev;
+
+constexpr int kThreads = 256;
+constexpr int kAlphaMax = 8;
+
+// ---------------- element-wise ----------------
+template <int OP>
+__global__ void __launch_bounds__(kThreads) ew_kernel(u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b, DevTables T,
+                                                      LimbSel sel, int polys, size_t a_bs, size_t b_bs, size_t b_ps) {
+    const size_t per_poly = (size_t)sel.n * T.N;
+    const size_t e = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 2;
+    if (e >= per_poly * polys) return;
+    const int p = (int)(e / per_poly);
+    const size_t r = e - (size_t)p * per_poly;
+    const int limb = (int)(r >> T.logN), m = sel.m[limb];
+    const u64 q = T.q[m];
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + blockIdx.y * a_bs + e);
+    const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(b + blockIdx.y * b_bs + (size_t)p * b_ps + r);
+    ulonglong2 z;
+    if (OP == 0) { z.x = addmod(x.x, y.x, q); z.y = addmod(x.y, y.y, q); }
+    else if (OP == 1) { z.x = submod(x.x, y.x, q); z.y = submod(x.y, y.y, q); }
+    else { const u64 ml = T.mu_lo[m], mh = T.mu_hi[m]; z.x = mulmod(x.x, y.x, q, ml, mh); z.y = mulmod(x.y, y.y, q, ml, mh); }
+    *reinterpret_cast<ulonglong2*>(out + blockIdx.y * a_bs + e) = z;
+}
+
+__global__ void __launch_bounds__(kThreads) mul_scalar_kernel(u64* __restrict__ out, const u64* __restrict__ a, DevTables T, LimbSel sel,
+                                                              ScalarSet sc, int polys) {
+    const size_t per_poly = (size_t)sel.n * T.N;
+    const size_t e = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 2;
+    if (e >= per_poly * polys) return;
+    const size_t r = e % per_poly;
+    const int limb = (int)(r >> T.logN);
+    const u64 q = T.q[sel.m[limb]], c = sc.c[limb], cs = sc.c_sh[limb];
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + e);
+    ulonglong2 z; z.x = mul_shoup(x.x, c, cs, q); z.y = mul_shoup(x.y, c, cs, q);
+    *reinterpret_cast<ulonglong2*>(out + e) = z;
+}
+
+__global__ void __launch_bounds__(kThreads) add_scalar_kernel(u64* __restrict__ out, const u64* __restrict__ a, DevTables T, LimbSel sel,
+                                                              ScalarSet sc) {
+    const size_t e = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 2;
+    if (e >= (size_t)sel.n * T.N) return;
+    const int limb = (int)(e >> T.logN);
+    const u64 q = T.q[sel.m[limb]], c = sc.c[limb];
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + e);
+    ulonglong2 z; z.x = addmod(x.x, c, q); z.y = addmod(x.y, c, q);
+    *reinterpret_cast<ulonglong2*>(out + e) = z;
+}
+
+__global__ void __launch_bounds__(kThreads) automorph_kernel(u64* __restrict__ out, const u64* __restrict__ in, const uint32_t* __restrict__ map,
+                                                             int N) {
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= N) return;
+    const size_t o = (size_t)blockIdx.y * N;
+    out[o + j] = in[o + map[j]];
+}
+
+__global__ void __launch_bounds__(kThreads) tensor_kernel(u64* __restrict__ d0, u64* __restrict__ d1, u64* __restrict__ d2,
+                                                          const u64* __restrict__ a, const u64* __restrict__ b, DevTables T, int l) {
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x, pl = (size_t)l * T.N;
+    if (e >= pl) return;
+    const int m = (int)(e >> T.logN);
+    const u64 q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
+    const u64 a0 = a[e], a1 = a[pl + e], b0 = b[e], b1 = b[pl + e];
+    d0[e] = mulmod(a0, b0, q, ml, mh);
+    U128 x{0, 0}; mad128(x, a0, b1); mad128(x, a1, b0);
+    d1[e] = barrett128(x, q, ml, mh);
+    d2[e] = mulmod(a1, b1, q, ml, mh);
+}
+
+// ---------------- fast basis conversion (ModUp / ModDown) ----------------
+// One thread per coefficient: the ns source residues stay in registers while it walks its strip of targets.
+// hm[i * tstride + t] = (S/s_i) mod target_t, staged in shared memory.
+__global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ up, const u64* __restrict__ dcoef, DevTables T, KsLevel ks) {
+    extern __shared__ u64 shm[];
+    const int d = blockIdx.z, l = ks.l, ext = l + T.K;
+    const int lo = d * ks.alpha, hi = min(lo + ks.alpha, l), ns = hi - lo;
+    for (int i = threadIdx.x; i < ks.alpha * ext; i += kThreads) shm[i] = ks.hm[(size_t)d * ks.alpha * ext + i];
+    __syncthreads();
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    u64 y[kAlphaMax];
+#pragma unroll
+    for (int i = 0; i < kAlphaMax; ++i) y[i] = i < ns ? dcoef[(size_t)(lo + i) * T.N + j] : 0;
+    const int tg = gridDim.y, per = (ext + tg - 1) / tg;
+    const int t0 = blockIdx.y * per, t1 = min(t0 + per, ext);
+    for (int t = t0; t < t1; ++t) {
+        if (t >= lo && t < hi) continue;
+        const int m = t < l ? t : T.L + (t - l);
+        U128 acc{0, 0};
+#pragma unroll
+        for (int i = 0; i < kAlphaMax; ++i)
+            if (i < ns) mad128(acc, y[i], shm[i * ext + t]);
+        up[((size_t)d * ext + t) * T.N + j] = barrett128(acc, T.q[m], T.mu_lo[m], T.mu_hi[m]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc0, u64* __restrict__ acc1, const u64* __restrict__ up,
+                                                                 const u64* __restrict__ c_eval, const u64* __restrict__ evk, DevTables T,
+                                                                 KsLevel ks) {
+    const int t = blockIdx.y, l = ks.l, ext = l + T.K;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const int m = t < l ? t : T.L + (t - l);
+    const size_t kpoly = (size_t)(T.L + T.K) * T.N;
+    U128 s0{0, 0}, s1{0, 0};
+    for (int d = 0; d < ks.beta; ++d) {
+        const bool own = t >= d * ks.alpha && t < min((d + 1) * ks.alpha, l);
+        const u64 u = own ? c_eval[(size_t)t * T.N + j] : up[((size_t)d * ext + t) * T.N + j];
+        const u64* kb = evk + (size_t)d * 2 * kpoly + (size_t)m * T.N + j;
+        mad128(s0, u, kb[0]);
+        mad128(s1, u, kb[kpoly]);
+    }
+    const u64 q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
+    acc0[(size_t)t * T.N + j] = barrett128(s0, q, ml, mh);
+    acc1[(size_t)t * T.N + j] = barrett128(s1, q, ml, mh);
+}
+
+__global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
+                                                                MdConst md, int l) {
+    extern __shared__ u64 shm[];
+    const int K = T.K, p = blockIdx.z;
+    for (int i = threadIdx.x; i < K * l; i += kThreads) shm[i] = md.phm[(size_t)(i / l) * T.L + (i % l)];
+    __syncthreads();
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    u64 y[kAlphaMax];
+#pragma unroll
+    for (int k = 0; k < kAlphaMax; ++k) y[k] = k < K ? pcoef[(size_t)p * pstride + (size_t)k * T.N + j] : 0;
+    const int tg = gridDim.y, per = (l + tg - 1) / tg;
+    const int t0 = blockIdx.y * per, t1 = min(t0 + per, l);
+    for (int t = t0; t < t1; ++t) {
+        U128 acc{0, 0};
+#pragma unroll
+        for (int k = 0; k < kAlphaMax; ++k)
+            if (k < K) mad128(acc, y[k], shm[k * l + t]);
+        tq[((size_t)p * l + t) * T.N + j] = barrett128(acc, T.q[t], T.mu_lo[t], T.mu_hi[t]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restrict__ out, const u64* __restrict__ acc, size_t acc_ps,
+                                                                  const u64* __restrict__ tq, const u64* __restrict__ add0,
+                                                                  const u64* __restrict__ add1, const uint32_t* __restrict__ map, DevTables T,
+                                                                  MdConst md, int l) {
+    const int i = blockIdx.y, p = blockIdx.z;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const int src = map ? map[j] : j;
+    const u64 q = T.q[i];
+    const size_t o = (size_t)i * T.N + src;
+    u64 v = submod(acc[(size_t)p * acc_ps + o], tq[(size_t)p * l * T.N + o], q);
+    v = mul_shoup(v, md.pinv[i], md.pinv_sh[i], q);
+    const u64* add = p == 0 ? add0 : add1;
+    if (add) v = addmod(v, add[o], q);
+    out[((size_t)p * l + i) * T.N + j] = v;
+}
+
+// ---------------- rescale ----------------
+__global__ void __launch_bounds__(kThreads) rescale_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ xlast, DevTables T, int l) {
+    const int p = blockIdx.z, i = blockIdx.y;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const u64 ql = T.q[l - 1], half = ql >> 1, q = T.q[i], ml = T.mu_lo[i], mh = T.mu_hi[i];
+    const u64 x = xlast[(size_t)p * T.N + j];
+    u64 v = barrett128(U128{x, 0}, q, ml, mh);
+    if (x > half) v = submod(v, barrett128(U128{ql, 0}, q, ml, mh), q);
+    tq[((size_t)p * (l - 1) + i) * T.N + j] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) rescale_finish_kernel(u64* __restrict__ out, const u64* __restrict__ in, const u64* __restrict__ tq,
+                                                                  DevTables T, RsConst rs, int l) {
+    const int p = blockIdx.z, i = blockIdx.y;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const u64 q = T.q[i];
+    const size_t oi = ((size_t)p * l + i) * T.N + j, oo = ((size_t)p * (l - 1) + i) * T.N + j;
+    const u64 w = rs.qlinv[(size_t)(l - 1) * T.L + i], ws = rs.qlinv_sh[(size_t)(l - 1) * T.L + i];
+    out[oo] = mul_shoup(submod(in[oi], tq[oo], q), w, ws, q);
+}
+
+// ---------------- integer coefficients -> residues ----------------
+__global__ void __launch_bounds__(kThreads) reduce_i64_kernel(u64* __restrict__ out, const int64_t* __restrict__ coef, DevTables T, LimbSel sel) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
+    if (j >= T.N) return;
+    const int m = sel.m[limb];
+    const u64 q = T.q[m];
+    const int64_t v = coef[j];
+    const u64 a = v < 0 ? (u64)(-(v + 1)) + 1 : (u64)v;
+    u64 r = barrett128(U128{a, 0}, q, T.mu_lo[m], T.mu_hi[m]);
+    if (v < 0 && r) r = q - r;
+    out[(size_t)limb * T.N + j] = r;
+}
+__global__ void __launch_bounds__(kThreads) reduce_i128_kernel(u64* __restrict__ out, const int64_t* __restrict__ coef, DevTables T, LimbSel sel) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
+    if (j >= T.N) return;
+    const int m = sel.m[limb];
+    const u64 q = T.q[m];
+    u64 lo = (u64)coef[2 * j];
+    int64_t hi = coef[2 * j + 1];
+    const bool neg = hi < 0;
+    if (neg) { lo = ~lo + 1; hi = ~hi + (lo == 0); }
+    u64 r = barrett128(U128{lo, (u64)hi}, q, T.mu_lo[m], T.mu_hi[m]);
+    if (neg && r) r = q - r;
+    out[(size_t)limb * T.N + j] = r;
+}
+__global__ void __launch_bounds__(kThreads) reduce_i8_kernel(u64* __restrict__ out, const int8_t* __restrict__ coef, DevTables T, LimbSel sel) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
+    if (j >= T.N) return;
+    const u64 q = T.q[sel.m[limb]];
+    const int v = coef[j];
+    out[(size_t)limb * T.N + j] = v >= 0 ? (u64)v : q - (u64)(-v);
+}
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+void launch_ew(const DevTables& t, EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel, int polys, int batch, size_t a_bs,
+               size_t b_bs, size_t b_ps, cudaStream_t s) {
+    dim3 grid(cdiv((size_t)polys * sel.n * t.N / 2, kThreads), batch);
+    switch (op) {
+        case EwOp::Add: ew_kernel<0><<<grid, kThreads, 0, s>>>(out, a, b, t, sel, polys, a_bs, b_bs, b_ps); break;
+        case EwOp::Sub: ew_kernel<1><<<grid, kThreads, 0, s>>>(out, a, b, t, sel, polys, a_bs, b_bs, b_ps); break;
+        case EwOp::Mul: ew_kernel<2><<<grid, kThreads, 0, s>>>(out, a, b, t, sel, polys, a_bs, b_bs, b_ps); break;
+    }
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_mul_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s) {
+    mul_scalar_kernel<<<cdiv((size_t)polys * sel.n * t.N / 2, kThreads), kThreads, 0, s>>>(out, a, t, sel, sc, polys);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, cudaStream_t s) {
+    add_scalar_kernel<<<cdiv((size_t)sel.n * t.N / 2, kThreads), kThreads, 0, s>>>(out, a, t, sel, sc);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_automorph(u64* out, const u64* in, const uint32_t* map, int N, int limbs, cudaStream_t s) {
+    automorph_kernel<<<dim3(cdiv(N, kThreads), limbs), kThreads, 0, s>>>(out, in, map, N);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, cudaStream_t s) {
+    tensor_kernel<<<cdiv((size_t)l * t.N, kThreads), kThreads, 0, s>>>(d0, d1, d2, a, b, t, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, cudaStream_t s) {
+    if (ks.alpha > kAlphaMax) throw std::invalid_argument("digit size above 8 limbs is not supported");
+    const int ext = ks.l + t.K, tg = ext >= 16 ? 4 : 1;
+    modup_conv_kernel<<<dim3(cdiv(t.N, kThreads), tg, ks.beta), kThreads, (size_t)ks.alpha * ext * 8, s>>>(up, dcoef, t, ks);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc0, u64* acc1, const u64* up, const u64* c_eval, const u64* evk,
+                          cudaStream_t s) {
+    inner_product_kernel<<<dim3(cdiv(t.N, kThreads), ks.l + t.K), kThreads, 0, s>>>(acc0, acc1, up, c_eval, evk, t, ks);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, cudaStream_t s) {
+    if (t.K > kAlphaMax) throw std::invalid_argument("more than 8 P limbs is not supported");
+    const int tg = l >= 16 ? 4 : 1;
+    moddown_conv_kernel<<<dim3(cdiv(t.N, kThreads), tg, polys), kThreads, (size_t)t.K * l * 8, s>>>(tq, pcoef, pstride, t, md, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_moddown_finish(const DevTables& t, const MdConst& md, u64* out, const u64* acc, size_t acc_ps, const u64* tq, const u64* add0,
+                           const u64* add1, const uint32_t* map, int l, int polys, cudaStream_t s) {
+    moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), l, polys), kThreads, 0, s>>>(out, acc, acc_ps, tq, add0, add1, map, t, md, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {
+    rescale_conv_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(tq, xlast, t, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s) {
+    rescale_finish_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(out, in, tq, t, rs, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_reduce_i64(const DevTables& t, u64* out, const int64_t* coef, const LimbSel& sel, cudaStream_t s) {
+    reduce_i64_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(out, coef, t, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_reduce_i128(const DevTables& t, u64* out, const int64_t* coef, const LimbSel& sel, cudaStream_t s) {
+    reduce_i128_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(out, coef, t, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_reduce_i8(const DevTables& t, u64* out, const int8_t* coef, const LimbSel& sel, cudaStream_t s) {
+    reduce_i8_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(out, coef, t, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+
+}  // namespace flk

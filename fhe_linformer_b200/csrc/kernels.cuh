@@ -1,0 +1,73 @@
+// kernels.cuh -- launchers for the non-NTT kernels of the CKKS hot path (K2-K7 of SURVEY.md 2.1).
+#pragma once
+#include "device_ctx.h"
+
+namespace flk {
+
+enum class EwOp : int { Add = 0, Sub = 1, Mul = 2 };
+
+// out = a (op) b, limb-wise.  b_poly_stride = 0 broadcasts one polynomial b over `polys` polynomials of a
+// (ct x pt).  Buffers are [batch][polys][l][N]; limb i of every polynomial uses modulus sel.m[i].
+void launch_ew(const DevTables& t, EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel, int polys, int batch,
+               size_t a_batch_stride, size_t b_batch_stride, size_t b_poly_stride, cudaStream_t s);
+
+struct ScalarSet {   // per-limb multiplier with Shoup companion
+    u64 c[64];
+    u64 c_sh[64];
+};
+// out = a * c[limb]  (polys polynomials of sel.n limbs)
+void launch_mul_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s);
+// out = a + c[limb] broadcast to every slot of the evaluation representation
+void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, cudaStream_t s);
+
+// out[limb][j] = in[limb][map[j]]
+void launch_automorph(u64* out, const u64* in, const uint32_t* map, int N, int limbs, cudaStream_t s);
+
+// tensor product of two 2-component ciphertexts: d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1
+void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, cudaStream_t s);
+
+// ---- hybrid key switch pieces ----
+struct KsLevel {          // device constants for key switching at l active limbs
+    const u64* post;      // [T] by modulus: N^-1 * (Q_d/q_m)^-1 mod q_m   (INTT post-scale)
+    const u64* post_sh;
+    const u64* hm;        // [beta][alpha][l+K]: (Q_d/q_{d*alpha+i}) mod q_ext(t)
+    int l, beta, alpha;
+};
+struct MdConst {          // ModDown constants (level independent)
+    const u64* post;      // [T] by modulus (P limbs): N^-1 * (P/p_k)^-1 mod p_k
+    const u64* post_sh;
+    const u64* phm;       // [K][L]: (P/p_k) mod q_i
+    const u64* pinv;      // [L] P^-1 mod q_i
+    const u64* pinv_sh;
+};
+
+// up[d][t][N] (coefficient form) for all digits d and all extended limbs t outside digit d.
+// dcoef = INTT(c) already scaled by KsLevel::post, [l][N].
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, cudaStream_t s);
+// acc{0,1}[t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[t] inside digit d else up[d][t]
+void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc0, u64* acc1, const u64* up, const u64* c_eval,
+                          const u64* evk, cudaStream_t s);
+// tq[p][i][N] (coefficient form), i < l, from the scaled INTT of the P part of `polys` accumulators.
+// pcoef = [polys][K][N] with poly stride pstride; tq = [polys][l][N]
+void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, cudaStream_t s);
+// out[p][i][j] = ((acc[p][i] - tq[p][i]) * P^-1 + (p == 0 && add0 ? add0[i] : (p == 1 && add1 ? add1[i]: 0)))[map ? map[j] : j]
+void launch_moddown_finish(const DevTables& t, const MdConst& md, u64* out, const u64* acc, size_t acc_pstride, const u64* tq, const u64* add0,
+                           const u64* add1, const uint32_t* map, int l, int polys, cudaStream_t s);
+
+// ---- rescale ----
+struct RsConst {
+    const u64* qlinv;     // [L][L]: q_r^-1 mod q_i
+    const u64* qlinv_sh;
+};
+// tq[p][i][j] = centred switch of xlast[p][j] (coefficient form of limb l-1) to modulus q_i, i < l-1
+void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s);
+// out[p][i] = (in[p][i] - tq[p][i]) * q_{l-1}^-1 ; in has l limbs per poly, out has l-1
+void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s);
+
+// coefficients (signed, as int64 or int128 lo/hi) -> residues, [l][N] for moduli sel
+void launch_reduce_i64(const DevTables& t, u64* out, const int64_t* coef, const LimbSel& sel, cudaStream_t s);
+void launch_reduce_i128(const DevTables& t, u64* out, const int64_t* coef_lohi, const LimbSel& sel, cudaStream_t s);
+// small signed int8 coefficients -> residues
+void launch_reduce_i8(const DevTables& t, u64* out, const int8_t* coef, const LimbSel& sel, cudaStream_t s);
+
+}  // namespace flk

@@ -1,0 +1,84 @@
+/*
+ * fl_ckks.h -- C-ABI of the B200-native CKKS evaluation engine that stands behind the reference's
+ * FHEController (drop-in boundary of SURVEY.md section 8(b)).
+ *
+ * Every entry point replaces one OpenFHE call the reference makes through
+ * `CryptoContext<DCRTPoly> context` (/root/reference/src/FHEController.h:23); the call site is cited
+ * next to each declaration (F.cpp = /root/reference/src/FHEController.cpp, M = src/main.cpp).
+ * The reference-side binding (a re-backed FHEController.cpp) is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a non-zero
+ * status otherwise, with the message available from fl_last_error() (thread-local).  There is NO CPU
+ * fallback: fl_ctx_create fails when no CUDA device is present.
+ *
+ * Data layout: a polynomial with l limbs is uint64_t[l][N], limb-major, residues in [0, q_i),
+ * EVALUATION format in OpenFHE's bit-reversed order.  A ciphertext is
+ * uint64_t[2][l][N] (c0 then c1).  An evaluation key is uint64_t[dnum][2][L+K][N] (b then a per digit).
+ */
+#ifndef FL_CKKS_H
+#define FL_CKKS_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fl_ctx fl_ctx;
+
+/* CCParams<CryptoContextCKKSRNS> as set at F.cpp:4-35 */
+typedef struct fl_params {
+    int logN;        /* SetRingDim(1<<15)            F.cpp:13 (1<<16 variant F.cpp:12) */
+    int L;           /* SetMultiplicativeDepth(27)+1 F.cpp:35 */
+    int dnum;        /* SetNumLargeDigits(4)         F.cpp:11 */
+    int first_bits;  /* SetFirstModSize(55)          F.cpp:25 */
+    int scale_bits;  /* SetScalingModSize(52)        F.cpp:23 */
+    int aux_bits;    /* OpenFHE default 60-bit P primes */
+    int sparse_h;    /* SPARSE_TERNARY weight        F.cpp:8  (0 = uniform ternary) */
+} fl_params;
+
+const char* fl_last_error(void);
+
+/* ---- context: GenCryptoContext F.cpp:37 ---- */
+int fl_ctx_create(const fl_params* p, int device, fl_ctx** out);
+void fl_ctx_destroy(fl_ctx* c);
+/* info[0..4] = logN, L, K, alpha, dnum */
+int fl_ctx_info(fl_ctx* c, int* info);
+int fl_ctx_moduli(fl_ctx* c, uint64_t* out /* L+K */);
+int fl_ctx_roots(fl_ctx* c, uint64_t* out /* L+K */);
+int fl_ctx_scale_factors(fl_ctx* c, double* out /* L */);
+uint32_t fl_galois_for_rotation(fl_ctx* c, int k);   /* FindAutomorphismIndex2nComplex inside EvalRotate F.cpp:435 */
+uint32_t fl_galois_conj(fl_ctx* c);
+void* fl_ctx_stream(fl_ctx* c);                       /* cudaStream_t the engine launches on */
+int fl_sync(fl_ctx* c);
+
+/* ---- device buffers (HBM-resident operands) ---- */
+int fl_dev_alloc(fl_ctx* c, size_t words, uint64_t** out);
+int fl_dev_free(fl_ctx* c, uint64_t* p);
+int fl_dev_upload(fl_ctx* c, uint64_t* dst, const uint64_t* src_host, size_t words);
+int fl_dev_download(fl_ctx* c, uint64_t* dst_host, const uint64_t* src, size_t words);
+
+/* ---- raw primitives on device buffers (asynchronous on the engine stream) ----
+ * midx[i] = modulus index of limb i (0..L-1 Q limbs, L..L+K-1 P limbs) */
+int fl_raw_ntt(fl_ctx* c, uint64_t* d, const int* midx, int nl);    /* DCRTPoly::SwitchFormat -> EVALUATION */
+int fl_raw_intt(fl_ctx* c, uint64_t* d, const int* midx, int nl);   /* DCRTPoly::SwitchFormat -> COEFFICIENT */
+int fl_raw_add(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);   /* EvalAdd F.cpp:410 */
+int fl_raw_sub(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);
+int fl_raw_mul(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);
+int fl_raw_automorph(fl_ctx* c, uint64_t* out, const uint64_t* in, int nl, uint32_t g);                    /* AutomorphismTransform */
+int fl_raw_rescale(fl_ctx* c, uint64_t* out, const uint64_t* in, int l, int polys);   /* ModReduceInternal (FLEXIBLEAUTO, F.cpp:18) */
+int fl_raw_modup(fl_ctx* c, uint64_t* out_ext, const uint64_t* c_eval, int l, int digit);   /* ApproxModUp */
+int fl_raw_moddown(fl_ctx* c, uint64_t* out, const uint64_t* in_ext, int l);                /* ApproxModDown */
+int fl_raw_keyswitch(fl_ctx* c, uint64_t* out2 /* [2][l][N] */, const uint64_t* poly, const uint64_t* evk, int l);   /* KeySwitch (HYBRID) */
+int fl_raw_rotate(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uint32_t g, const uint64_t* evk);   /* EvalRotate F.cpp:435,833,843 */
+int fl_raw_mul_relin(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, int l, const uint64_t* evk);   /* EvalMult(ct,ct) F.cpp:431 */
+int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_t* pt, int l);   /* EvalMult(ct,pt) F.cpp:427 */
+
+/* ---- the same operations with HOST buffers: H2D copy, kernels, D2H copy (what a host-resident caller pays) ---- */
+int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse);
+int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev);
+int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
