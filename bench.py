@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json config[1]: CKKS primitive bench, EvalRotate at N=2^16 over the full RNS chain
+(28 Q limbs + 7 P limbs, dnum=4), rotations/s; one step = one pass of EvalRotate over a batch of B
+independent ciphertexts (ciphertext-parallel across ranks, no data-path collective).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "EvalRotate throughput, N=2^16, full chain (L=28 Q limbs + 7 P limbs, dnum=4)"
+UNIT = "rotations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--logN", type=int, default=16)
+    ap.add_argument("--limbs", type=int, default=28, help="active Q limbs of the operands (28 = full chain)")
+    ap.add_argument("--batch", type=int, default=16, help="ciphertexts per step per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=20, help="rotations timed on the host for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def algorithmic_bytes_rotate(N, l, K, alpha):
+    beta = (l + alpha - 1) // alpha
+    return (4 * l + 2 * beta * (l + K)) * 8 * N
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_rotations(o, l, count, seed=0, warm=True):
+    """Oracle EvalRotate on the host (all OpenMP threads): returns seconds per rotation."""
+    rng = np.random.default_rng(seed)
+    ct = np.stack([np.stack([rng.integers(0, int(o.moduli[m]), o.N, dtype=np.uint64) for m in range(l)]) for _ in range(2)])
+    evk = rng.integers(0, 1 << 50, (o.dnum, 2, o.L + o.K, o.N), dtype=np.uint64)
+    g = o.galois(1)
+    if warm:
+        o.rotate(ct, g, evk)   # warm-up (page faults, twiddles into cache)
+    t0 = time.perf_counter()
+    for _ in range(count):
+        o.rotate(ct, g, evk)
+    return (time.perf_counter() - t0) / count
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU path.  OpenFHE cannot be built here, so this arm
+    times the oracle port (oracle/ckks_oracle.c, OpenMP over all host cores) on the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle, lib
+    o = Oracle(logN=a.logN, L=28, dnum=4)
+    cores = int(lib().orc_num_threads())
+    per_step = max(1, min(a.batch, 4))                   # bounded sample of the step's batch
+    for _ in range(a.warmup):
+        cpu_rotations(o, a.limbs, 1, warm=False)
+    secs = [cpu_rotations(o, a.limbs, per_step, seed=100 + s, warm=False) for s in range(a.steps)]
+    per_rot = float(np.mean(secs))
+    val = 1.0 / per_rot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": per_rot * per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": {"workload": f"EvalRotate N=2^{a.logN} l={a.limbs} dnum=4 (BASELINE.json configs[1])", "sample_per_step": per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} rotations per step x {a.steps} steps, oracle/ckks_oracle.c with OpenMP ({cores} threads); "
+                                   "OpenFHE-equivalent CPU restatement, not OpenFHE"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from fhe_linformer_b200 import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    e = Engine(device=local, logN=a.logN)
+    N, l, B = e.N, a.limbs, a.batch
+    rng = np.random.default_rng(1234 + rank)
+    q = e.moduli
+
+    def rand_limbs(midx):
+        return np.stack([rng.integers(0, int(q[m]), N, dtype=np.uint64) for m in midx])
+
+    # evaluation keys: uniformly random residues (timing does not need a valid key); 2 keys alternate
+    nkeys = 2
+    evks = [e.to_dev(np.stack([rand_limbs(range(e.L + e.K)) for _ in range(e.dnum * 2)]).reshape(e.dnum, 2, e.L + e.K, N)) for _ in range(nkeys)]
+    g = e.galois(1)
+    base = np.stack([rand_limbs(range(l)), rand_limbs(range(l))])
+    ins, outs = [], []
+    for i in range(B):
+        ins.append(e.to_dev(np.roll(base, i + 1, axis=2)))    # distinct contents, cheap to generate
+        outs.append(e.buf((2, l, N)))
+    stream = torch.cuda.ExternalStream(e.stream(), device=torch.device("cuda", local))
+
+    def step():
+        for i in range(B):
+            e.rotate(ins[i], g, evks[i % nkeys], out=outs[i])
+
+    def barrier():
+        e.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(a.steps):
+        step()
+    ev1.record(stream)
+    e.sync()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * a.steps / (ms * 1e-3)
+
+    # ---- dominant kernel family: the NTT pass pair (column + chunk), timed alone over the same buffers ----
+    midx2 = np.concatenate([np.arange(l), np.arange(l)]).astype(np.int32)
+    scratch = [e.to_dev(np.roll(base, 7 * i + 3, axis=2)) for i in range(B)]      # 2*l limbs each, > L2 in total
+    for i in range(B):
+        e.ntt(scratch[i], midx2)
+    e.sync()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    n0.record(stream)
+    for _ in range(reps):
+        for i in range(B):
+            e.ntt(scratch[i], midx2)
+    n1.record(stream)
+    e.sync()
+    ntt_ms = n0.elapsed_time(n1) / (reps * B)
+    ntt_bytes = 16 * N * 2 * l
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9
+    rot_bytes = algorithmic_bytes_rotate(N, l, e.K, e.alpha)
+    rot_gbs = rot_bytes * value / world / 1e9
+    for s in scratch:
+        s.free()
+
+    # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region) ----
+    pin_in = [torch.empty((2, l, N), dtype=torch.int64).pin_memory() for _ in range(B)]
+    pin_out = [torch.empty((2, l, N), dtype=torch.int64).pin_memory() for _ in range(B)]
+    h_in = [p.numpy().view(np.uint64) for p in pin_in]
+    h_out = [p.numpy().view(np.uint64) for p in pin_out]
+    for i in range(B):
+        h_in[i][...] = np.roll(base, i + 1, axis=2)
+    e2e_steps = max(2, min(a.steps, 5))
+    for i in range(min(B, 4)):
+        e.host_rotate(h_in[i], g, evks[i % nkeys], out=h_out[i])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for i in range(B):
+            e.host_rotate(h_in[i], g, evks[i % nkeys], out=h_out[i])
+    e.sync()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(te.item())
+    ok = bool((h_out[0] == outs[0].download()).all())      # e2e result equals the device-resident result
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle.oracle import Oracle, lib
+        o = Oracle(logN=a.logN, L=28, dnum=4)
+        per = cpu_rotations(o, l, a.cpu_sample)
+        cores = int(lib().orc_num_threads())
+        cpu = {"value": 1.0 / per, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_sample} EvalRotate at N=2^{a.logN}, l={l}, oracle/ckks_oracle.c OpenMP {cores} threads "
+                         "(OpenFHE-equivalent CPU restatement, not OpenFHE)"}
+
+    if rank == 0:
+        launches_per_rotation = 13      # 4 NTT pass pairs (8) + modup/inner/moddown conv/finish (4) + 1 D2D copy
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"EvalRotate N=2^{a.logN} l={l} K={e.K} dnum={e.dnum} (BASELINE.json configs[1])", "batch_per_gpu": B,
+                       "parallelism": f"ciphertext-parallel x{world}", "l2": f"inputs larger than L2 ({B * 2 * 2 * l * N * 8 / 1e6:.0f} MB touched per step)"},
+            "roofline": {"bound": "hbm", "kernel": "ntt pass pair (ntt_column_kernel + ntt_chunk_kernel)", "achieved": ntt_gbs, "peak": peak,
+                         "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ntt_bytes, "avg_launch_ms": ntt_ms},
+            "rotate_roofline": {"algorithmic_bytes_per_rotation": rot_bytes, "achieved": rot_gbs, "unit": "GB/s", "frac": rot_gbs / peak},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 2 * l * N * 8, "d2h_bytes_per_step": B * 2 * l * N * 8,
+                    "steps": e2e_steps, "matches_device_path": ok},
+            "gpu_launches": launches_per_rotation * B * a.steps,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,10 +27,8 @@ struct DevTables {
     const u64* q;        // [T]
     const u64* mu_lo;    // [T] floor(2^128/q) low / high words
     const u64* mu_hi;
-    const u64* tw;       // [T][N] psi^bitrev(i)
-    const u64* tw_sh;
-    const u64* itw;      // [T][N] psi^-bitrev(i)
-    const u64* itw_sh;
+    const ulonglong2* tw2;    // [T][N] {psi^bitrev(i), its Shoup companion}
+    const ulonglong2* itw2;   // [T][N] {psi^-bitrev(i), Shoup companion}
     const u64* ninv;     // [T]
     const u64* ninv_sh;
     int logN, N, L, K;

@@ -12,7 +12,10 @@ template <class V>
 V* Engine::to_device(const std::vector<V>& h) {
     V* d = nullptr;
     FLK_CUDA(cudaMalloc(&d, std::max<size_t>(1, h.size()) * sizeof(V)));
-    FLK_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice));
+    // pageable H2D copies may still be in flight on the legacy stream when cudaMemcpy returns; the engine stream is
+    // non-blocking, so copy on it and wait.
+    FLK_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(V), cudaMemcpyHostToDevice, stream));
+    FLK_CUDA(cudaStreamSynchronize(stream));
     owned_.push_back(d);
     return d;
 }
@@ -32,11 +35,19 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     FLK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 
     const int Tn = P.T, N = P.N;
-    std::vector<u64> tw((size_t)Tn * N), tws(tw.size()), itw(tw.size()), itws(tw.size());
-    for (int m = 0; m < Tn; ++m)
-        P.twiddles(m, &tw[(size_t)m * N], &tws[(size_t)m * N], &itw[(size_t)m * N], &itws[(size_t)m * N]);
+    {   // twiddles interleaved with their Shoup companions so one 16-byte load fetches both
+        std::vector<u64> tw(N), tws(N), itw(N), itws(N);
+        std::vector<ulonglong2> f((size_t)Tn * N), b((size_t)Tn * N);
+        for (int m = 0; m < Tn; ++m) {
+            P.twiddles(m, tw.data(), tws.data(), itw.data(), itws.data());
+            for (int i = 0; i < N; ++i) {
+                f[(size_t)m * N + i] = make_ulonglong2(tw[i], tws[i]);
+                b[(size_t)m * N + i] = make_ulonglong2(itw[i], itws[i]);
+            }
+        }
+        T.tw2 = to_device(f); T.itw2 = to_device(b);
+    }
     T.q = to_device(P.q); T.mu_lo = to_device(P.mu_lo); T.mu_hi = to_device(P.mu_hi);
-    T.tw = to_device(tw); T.tw_sh = to_device(tws); T.itw = to_device(itw); T.itw_sh = to_device(itws);
     T.ninv = to_device(P.ninv); T.ninv_sh = to_device(P.ninv_sh);
     T.logN = P.logN; T.N = N; T.L = P.L; T.K = P.K;
 
@@ -109,7 +120,8 @@ const uint32_t* Engine::automorph_map(uint32_t g) {
     P.automorph_map(g, h.data());
     uint32_t* d = nullptr;
     FLK_CUDA(cudaMalloc(&d, (size_t)P.N * 4));
-    FLK_CUDA(cudaMemcpy(d, h.data(), (size_t)P.N * 4, cudaMemcpyHostToDevice));
+    FLK_CUDA(cudaMemcpyAsync(d, h.data(), (size_t)P.N * 4, cudaMemcpyHostToDevice, stream));
+    FLK_CUDA(cudaStreamSynchronize(stream));
     maps_[g] = d;
     return d;
 }

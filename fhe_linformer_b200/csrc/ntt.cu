@@ -9,8 +9,11 @@
 //   column pass : the 4 widest-stride stages, radix-16 entirely in registers, one column per thread,
 //                 adjacent threads on adjacent columns (fully coalesced, no shared memory);
 //   chunk pass  : the remaining logN-4 stages on contiguous chunks of 2^(logN-4) words, one CTA per
-//                 chunk, radix-8 register blocks exchanged through XOR-swizzled shared memory.
-// Butterflies are Harvey lazy (values < 4q forward, < 2q inverse) with Shoup twiddles.
+//                 chunk, radix-8 register blocks exchanged through XOR-swizzled shared memory, the
+//                 next round's twiddles prefetched (16-byte {w, w'} loads) across the barrier.
+// Butterflies are Harvey lazy with Shoup twiddles.  Forward values grow by 2q per stage; for moduli
+// below 2^56 (every Q limb) 33q < 2^64, so the forward transform carries NO conditional subtraction
+// until one Barrett-style reduction at the very end; the 60-bit P limbs keep values below 4q.
 #include "device_ctx.h"
 #include "modarith.cuh"
 
@@ -19,32 +22,61 @@ namespace {
 
 using namespace dev;
 
-// forward radix-2^LOG block over e[0..2^LOG): twiddle index of group g at sub-stage s is (J<<s)+g
+__device__ __forceinline__ bool is_wide(u64 q) { return (q >> 56) != 0; }
+
+// a*w - floor(a*ws/2^64)*q, written as two fused multiply-adds with nq = -q
+__device__ __forceinline__ u64 shoup_nq(u64 a, u64 w, u64 ws, u64 nq) { return a * w + __umul64hi(a, ws) * nq; }
+
+template <bool WIDE>
+__device__ __forceinline__ void ct_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q2) {
+    u64 u = x;
+    if (WIDE) u = csub(u, q2);
+    const u64 v = shoup_nq(y, t.x, t.y, nq);
+    x = u + v;
+    y = u - v + q2;
+}
+__device__ __forceinline__ void gs_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q2) {
+    const u64 s = csub(x + y, q2);
+    const u64 d = x - y + q2;
+    x = s;
+    y = shoup_nq(d, t.x, t.y, nq);
+}
+
+// twiddles of one radix-2^LOG block: entry (1<<s)-1+g is table index (J<<s)+g
 template <int LOG>
-__device__ __forceinline__ void ct_block(u64* e, const u64* __restrict__ tw, const u64* __restrict__ tws, u32 J, u64 q) {
+__device__ __forceinline__ void load_tw(ulonglong2* t, const ulonglong2* __restrict__ tab, u32 J) {
+#pragma unroll
+    for (int s = 0; s < LOG; ++s)
+#pragma unroll
+        for (int g = 0; g < (1 << s); ++g) t[(1 << s) - 1 + g] = __ldg(tab + ((J << s) + g));
+}
+template <int LOG, bool WIDE>
+__device__ __forceinline__ void ct_block(u64* e, const ulonglong2* t, u64 nq, u64 q2) {
 #pragma unroll
     for (int s = 0; s < LOG; ++s) {
         const int half = (1 << LOG) >> (s + 1);
 #pragma unroll
-        for (int g = 0; g < (1 << s); ++g) {
-            const u64 w = __ldg(tw + ((J << s) + g)), ws = __ldg(tws + ((J << s) + g));
+        for (int g = 0; g < (1 << s); ++g)
 #pragma unroll
-            for (int j = 0; j < half; ++j) ct_bfly(e[g * 2 * half + j], e[g * 2 * half + half + j], w, ws, q);
-        }
+            for (int j = 0; j < half; ++j) ct_bf<WIDE>(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q2);
     }
 }
 template <int LOG>
-__device__ __forceinline__ void gs_block(u64* e, const u64* __restrict__ tw, const u64* __restrict__ tws, u32 J, u64 q) {
+__device__ __forceinline__ void gs_block(u64* e, const ulonglong2* t, u64 nq, u64 q2) {
 #pragma unroll
     for (int s = LOG - 1; s >= 0; --s) {
         const int half = (1 << LOG) >> (s + 1);
 #pragma unroll
-        for (int g = 0; g < (1 << s); ++g) {
-            const u64 w = __ldg(tw + ((J << s) + g)), ws = __ldg(tws + ((J << s) + g));
+        for (int g = 0; g < (1 << s); ++g)
 #pragma unroll
-            for (int j = 0; j < half; ++j) gs_bfly(e[g * 2 * half + j], e[g * 2 * half + half + j], w, ws, q);
-        }
+            for (int j = 0; j < half; ++j) gs_bf(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q2);
     }
+}
+// canonical residue of a lazily accumulated forward value
+template <bool WIDE>
+__device__ __forceinline__ u64 final_reduce(u64 v, u64 q, u64 q2, u64 nq, u64 qinv64) {
+    if (WIDE) return csub(csub(v, q2), q);          // v < 4q
+    return csub(v + __umul64hi(v, qinv64) * nq, q);  // v < 33q: one Barrett step with floor(2^64/q)
 }
 
 // ---------------- column pass (register radix-16) ----------------
@@ -58,16 +90,18 @@ __global__ void __launch_bounds__(256) ntt_column_kernel(u64* __restrict__ data,
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + c;
-    const u64 q = T.q[m];
+    const u64 q = T.q[m], nq = 0 - q, q2 = q << 1;
     u64 e[R1];
 #pragma unroll
     for (int k = 0; k < R1; ++k) e[k] = a[(size_t)k * cols];
+    ulonglong2 t[R1 - 1];
+    load_tw<kRadix1Log>(t, (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N, 1);
     if (FWD) {
-        ct_block<kRadix1Log>(e, T.tw + (size_t)m * T.N, T.tw_sh + (size_t)m * T.N, 1, q);
+        if (is_wide(q)) ct_block<kRadix1Log, true>(e, t, nq, q2); else ct_block<kRadix1Log, false>(e, t, nq, q2);
 #pragma unroll
-        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy, < 4q
+        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 4q (wide) or < 9q (narrow)
     } else {
-        gs_block<kRadix1Log>(e, T.itw + (size_t)m * T.N, T.itw_sh + (size_t)m * T.N, 1, q);
+        gs_block<kRadix1Log>(e, t, nq, q2);
         const u64 w = post ? post[m] : T.ninv[m], ws = post ? post_sh[m] : T.ninv_sh[m];
 #pragma unroll
         for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = mul_shoup(e[k], w, ws, q);
@@ -75,71 +109,156 @@ __global__ void __launch_bounds__(256) ntt_column_kernel(u64* __restrict__ data,
 }
 
 // ---------------- chunk pass (shared-memory radix-8 rounds) ----------------
-// swizzled shared-memory position: conflict-free for the stride patterns of every round
-__device__ __forceinline__ int spos(int idx) { return (idx ^ ((idx >> 3) & 7)) + ((idx >> 6) << 3); }
+// Shared-memory position of logical index idx: spos(idx) = (idx ^ ((idx>>3)&7)) + ((idx>>6)<<3).
+// Conflict-free for every round's stride pattern.  For idx = base | (k<<ULOG) with disjoint bit
+// fields this splits into a per-thread part and compile-time constants:
+struct SBase {
+    int px, d0;   // px = base ^ ((base>>3)&7), d0 = (base>>6)<<3
+    __device__ __forceinline__ explicit SBase(int base) : px(base ^ ((base >> 3) & 7)), d0((base >> 6) << 3) {}
+    template <int KC>
+    __device__ __forceinline__ int at() const { return (px ^ (KC ^ ((KC >> 3) & 7))) + d0 + ((KC >> 6) << 3); }
+};
 
 template <int S2>
 struct Sched {
     static constexpr int C = 1 << S2;
-    static constexpr int NT = C / 8 < 1 ? 1 : C / 8;
+    static constexpr int NT = C / 8;
     static constexpr int NR = (S2 + 2) / 3;
     static constexpr int last_log = S2 - 3 * (NR - 1);
+    static constexpr int MINB = NT >= 512 ? 2 : (NT >= 256 ? 4 : 1);
     __host__ __device__ static constexpr int log_of(int r) { return r < NR - 1 ? 3 : last_log; }
     __host__ __device__ static constexpr int ulog_of(int r) { return r < NR - 1 ? S2 - 3 * (r + 1) : 0; }
 };
 
-// one round: each thread owns 8 elements = G groups of E = 2^LOG; element k of group (hi,lo) is at hi*E*u + lo + k*u
-template <int LOG, int ULOG, bool FWD, bool FINAL>
-__device__ __forceinline__ void chunk_round(u64* sm, int tid, u32 chunk, int logN, int S2, const u64* tw, const u64* tws, u64 q) {
-    constexpr int E = 1 << LOG, G = 8 / E, U = 1 << ULOG;
-#pragma unroll
-    for (int h = 0; h < G; ++h) {
+// Geometry of round (LOG, ULOG): a thread owns G = 8>>LOG groups of E = 2^LOG elements; element k of group
+// gid = tid*G + h sits at logical index hi*E*U + lo + k*U  (lo = gid mod U, hi = gid / U).
+template <int LOG, int ULOG>
+struct Geo {
+    static constexpr int E = 1 << LOG, G = 8 / E, U = 1 << ULOG, TW = E - 1;
+    __device__ static __forceinline__ int base(int tid, int h) {
         const int gid = tid * G + h;
-        const int lo = gid & (U - 1), hi = gid >> ULOG;
-        const int base = hi * (E * U) + lo;
-        u64 e[E];
-#pragma unroll
-        for (int k = 0; k < E; ++k) e[k] = sm[spos(base + k * U)];
-        const u32 J = (1u << (logN - LOG - ULOG)) + (chunk << (S2 - LOG - ULOG)) + hi;
-        if (FWD) ct_block<LOG>(e, tw, tws, J, q); else gs_block<LOG>(e, tw, tws, J, q);
-#pragma unroll
-        for (int k = 0; k < E; ++k) {
-            u64 v = e[k];
-            if (FINAL) { v = csub(v, q << 1); v = csub(v, q); }
-            sm[spos(base + k * U)] = v;
-        }
+        return (gid >> ULOG) * (E * U) + (gid & (U - 1));
+    }
+    __device__ static __forceinline__ u32 J(int tid, int h, u32 chunk, int logN, int S2) {
+        const int gid = tid * G + h;
+        return (1u << (logN - LOG - ULOG)) + (chunk << (S2 - LOG - ULOG)) + (u32)(gid >> ULOG);
+    }
+};
+
+template <int LOG, int ULOG, int K>
+__device__ __forceinline__ void lds_group(u64* e, const u64* sm, const SBase& b) {
+    if constexpr (K < (1 << LOG)) {
+        e[K] = sm[b.at<(K << ULOG)>()];
+        lds_group<LOG, ULOG, K + 1>(e, sm, b);
+    }
+}
+template <int LOG, int ULOG, int K>
+__device__ __forceinline__ void sts_group(const u64* e, u64* sm, const SBase& b) {
+    if constexpr (K < (1 << LOG)) {
+        sm[b.at<(K << ULOG)>()] = e[K];
+        sts_group<LOG, ULOG, K + 1>(e, sm, b);
     }
 }
 
 template <int S2, bool FWD, int R>
 struct Rounds {
     using S = Sched<S2>;
-    __device__ static __forceinline__ void run(u64* sm, int tid, u32 chunk, int logN, const u64* tw, const u64* tws, u64 q) {
-        // forward visits rounds 0..NR-1 (wide strides first); inverse visits NR-1..0
-        constexpr int r = FWD ? R : S::NR - 1 - R;
-        chunk_round<S::log_of(r), S::ulog_of(r), FWD, FWD && (R == S::NR - 1)>(sm, tid, chunk, logN, S2, tw, tws, q);
-        __syncthreads();
-        if constexpr (R + 1 < S::NR) Rounds<S2, FWD, R + 1>::run(sm, tid, chunk, logN, tw, tws, q);
+    static constexpr int r = FWD ? R : S::NR - 1 - R;     // forward: wide strides first; inverse: narrow first
+    static constexpr int LOG = S::log_of(r), ULOG = S::ulog_of(r);
+    using G = Geo<LOG, ULOG>;
+    static constexpr bool FIRST = R == 0, LAST = R == S::NR - 1;
+
+    __device__ static __forceinline__ void load_twiddles(ulonglong2* t, const ulonglong2* tab, int tid, u32 chunk, int logN) {
+#pragma unroll
+        for (int h = 0; h < G::G; ++h) load_tw<LOG>(t + h * G::TW, tab, G::J(tid, h, chunk, logN, S2));
+    }
+
+    // tw: this round's twiddles (already in flight / loaded).  Data: forward round 0 reads global memory directly,
+    // inverse last round writes global memory directly; everything else goes through swizzled shared memory.
+    __device__ static __forceinline__ void run(u64* __restrict__ a, u64* sm, int tid, u32 chunk, int logN, const ulonglong2* tab,
+                                               ulonglong2* tw, u64 q, u64 nq, u64 q2, u64 qinv64, bool wide) {
+        u64 e[8];
+        if constexpr (FWD && FIRST) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = a[tid + k * S::NT];
+        } else {
+#pragma unroll
+            for (int h = 0; h < G::G; ++h) lds_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
+        }
+#pragma unroll
+        for (int h = 0; h < G::G; ++h) {
+            if (FWD) {
+                if (wide) ct_block<LOG, true>(e + h * G::E, tw + h * G::TW, nq, q2);
+                else ct_block<LOG, false>(e + h * G::E, tw + h * G::TW, nq, q2);
+            } else {
+                gs_block<LOG>(e + h * G::E, tw + h * G::TW, nq, q2);
+            }
+        }
+        if constexpr (FWD && LAST) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = wide ? final_reduce<true>(e[k], q, q2, nq, qinv64) : final_reduce<false>(e[k], q, q2, nq, qinv64);
+        }
+        if constexpr (!LAST) {
+            // prefetch the next round's twiddles so their L2 latency overlaps the exchange and the barrier
+            Rounds<S2, FWD, R + 1>::load_twiddles(tw, tab, tid, chunk, logN);
+        }
+        if constexpr (!FWD && LAST) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[tid + k * S::NT] = e[k];    // lazy < 2q, consumed by the column pass
+        } else {
+#pragma unroll
+            for (int h = 0; h < G::G; ++h) sts_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
+            __syncthreads();
+        }
+        if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q2, qinv64, wide);
     }
 };
 
+template <int S2, int K>
+__device__ __forceinline__ void copy_in(u64* sm, const u64* __restrict__ a, int tid, const SBase& b) {
+    if constexpr (K < 8) {
+        sm[b.at<(K << (S2 - 3))>()] = a[tid + K * Sched<S2>::NT];
+        copy_in<S2, K + 1>(sm, a, tid, b);
+    }
+}
+template <int S2, int K>
+__device__ __forceinline__ void copy_out(u64* __restrict__ a, const u64* sm, int tid, const SBase& b) {
+    if constexpr (K < 8) {
+        a[tid + K * Sched<S2>::NT] = sm[b.at<(K << (S2 - 3))>()];
+        copy_out<S2, K + 1>(a, sm, tid, b);
+    }
+}
+
 template <int S2, bool FWD>
-__global__ void __launch_bounds__(Sched<S2>::NT) ntt_chunk_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride) {
+__global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kernel(u64* __restrict__ data, DevTables T, LimbSel sel,
+                                                                                    size_t batch_stride) {
     using S = Sched<S2>;
-    constexpr int C = S::C, NT = S::NT;
-    __shared__ u64 sm[C + C / 8 + 8];
+    constexpr int C = S::C;
+    __shared__ u64 sm[C + C / 8];
     const int limb = blockIdx.y, m = sel.m[limb], tid = threadIdx.x;
     const u32 chunk = blockIdx.x;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + (size_t)chunk * C;
-    const u64 q = T.q[m];
-    const u64* tw = (FWD ? T.tw : T.itw) + (size_t)m * T.N;
-    const u64* tws = (FWD ? T.tw_sh : T.itw_sh) + (size_t)m * T.N;
-#pragma unroll
-    for (int k = 0; k < C / NT; ++k) sm[spos(tid + k * NT)] = a[tid + k * NT];
-    __syncthreads();
-    Rounds<S2, FWD, 0>::run(sm, tid, chunk, T.logN, tw, tws, q);
-#pragma unroll
-    for (int k = 0; k < C / NT; ++k) a[tid + k * NT] = sm[spos(tid + k * NT)];
+    const u64 q = T.q[m], nq = 0 - q, q2 = q << 1, qinv64 = T.mu_hi[m];
+    const bool wide = is_wide(q);
+    const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
+    ulonglong2 tw[7];
+    Rounds<S2, FWD, 0>::load_twiddles(tw, tab, tid, chunk, T.logN);
+    if constexpr (!FWD) {
+        copy_in<S2, 0>(sm, a, tid, SBase(tid));
+        __syncthreads();
+    }
+    Rounds<S2, FWD, 0>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q2, qinv64, wide);
+    if constexpr (FWD) copy_out<S2, 0>(a, sm, tid, SBase(tid));
+}
+
+template <int S2, bool FWD>
+void launch_chunk_s(const DevTables& t, u64* data, const LimbSel& sel, dim3 grid, size_t bs, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(ntt_chunk_kernel<S2, FWD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    ntt_chunk_kernel<S2, FWD><<<grid, Sched<S2>::NT, 0, s>>>(data, t, sel, bs);
 }
 
 template <bool FWD>
@@ -147,7 +266,7 @@ void launch_chunk(const DevTables& t, u64* data, const LimbSel& sel, int batch, 
     const int S2 = t.logN - kRadix1Log;
     dim3 grid(1u << kRadix1Log, sel.n, batch);
     switch (S2) {
-#define FLK_CASE(X) case X: ntt_chunk_kernel<X, FWD><<<grid, Sched<X>::NT, 0, s>>>(data, t, sel, bs); break;
+#define FLK_CASE(X) case X: launch_chunk_s<X, FWD>(t, data, sel, grid, bs, s); break;
         FLK_CASE(6) FLK_CASE(7) FLK_CASE(8) FLK_CASE(9) FLK_CASE(10) FLK_CASE(11) FLK_CASE(12)
 #undef FLK_CASE
         default: throw std::invalid_argument("unsupported ring dimension (logN must be 10..16)");
