@@ -5,3 +5,4 @@ sm_100a.  This Python package is only a ctypes front-end used by tests and bench
 fallback -- importing `capi` raises if the library has not been built.
 """
 from .capi import Engine, DevBuf, load_library, LIB_PATH, ReferenceParams  # noqa: F401
+from .ckks import CKKS, Elem  # noqa: F401

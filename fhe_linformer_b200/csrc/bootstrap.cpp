@@ -1,0 +1,335 @@
+// bootstrap.cpp -- CKKS bootstrapping (EvalBootstrapSetup / EvalBootstrapKeyGen / EvalBootstrap, reference
+// FHEController.cpp:238-239,280,445): ModRaise -> CoeffsToSlots -> EvalMod -> SlotsToCoeffs, full packing
+// (slots = N/2, the reference's configuration: N = 2^15, 2^14 slots), level budget {cts, stc}.
+//
+//   * CoeffsToSlots / SlotsToCoeffs: the special-FFT butterfly factors of the encoding matrix (Appendix A.9/A.11),
+//     merged into `budget` sparse-diagonal matrices each, evaluated with baby-step/giant-step rotations; all scalar
+//     factors (1/(K q0), q0/2pi, the pre-scaling correction) are folded into the plaintext diagonals.
+//   * EvalMod: Chebyshev interpolant of cos(2 pi (K x - 1/4) / 2^R) followed by R double-angle steps
+//     (sparse-secret range K = 28; R = 4, degree 31: 9 levels).  Total depth 3 + 9 + 3 = 15 incl. the pending rescale.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <map>
+
+#include "scheme.h"
+
+namespace flk {
+
+namespace {
+
+using Diag = std::map<int, std::vector<cplx>>;   // shift -> diagonal; (M v)[p] = sum_d diag_d[p] * v[(p + d) mod n]
+
+int norm_shift(int d, int n) {
+    d %= n;
+    if (d < 0) d += n;
+    return d;
+}
+std::vector<cplx> rot_vec(const std::vector<cplx>& v, int k) {
+    const int n = (int)v.size();
+    std::vector<cplx> r(n);
+    for (int p = 0; p < n; ++p) r[p] = v[norm_shift(p + k, n)];
+    return r;
+}
+// (A after B): A (B v)
+Diag compose(const Diag& A, const Diag& B, int n) {
+    Diag C;
+    for (auto& a : A)
+        for (auto& b : B) {
+            const int s = norm_shift(a.first + b.first, n);
+            auto& dst = C[s];
+            if (dst.empty()) dst.assign(n, cplx(0, 0));
+            const std::vector<cplx> br = rot_vec(b.second, a.first);
+            for (int p = 0; p < n; ++p) dst[p] += a.second[p] * br[p];
+        }
+    return C;
+}
+
+// butterfly stage of the special FFT with block length len (A.9); inverse = its matrix inverse
+Diag butterfly(int n, int len, bool inverse) {
+    const int lenh = len >> 1, lenq = len << 2, m = 4 * n;
+    std::vector<uint32_t> rot(n);
+    uint32_t pw = 1;
+    for (int i = 0; i < n; ++i) { rot[i] = pw; pw = (uint32_t)(((u64)pw * 5) % (uint32_t)m); }
+    std::vector<cplx> d0(n), dp(n, cplx(0, 0)), dm(n, cplx(0, 0));
+    for (int p = 0; p < n; ++p) {
+        const int r = p % len;
+        const bool first = r < lenh;
+        const int j = first ? r : r - lenh;
+        const uint32_t idx = (rot[j] % (uint32_t)lenq) * (uint32_t)(m / lenq);
+        const double ang = 2.0 * M_PI * (double)idx / (double)m;
+        const cplx w(std::cos(ang), std::sin(ang));
+        if (!inverse) {
+            if (first) { d0[p] = 1.0; dp[p] = w; } else { d0[p] = -w; dm[p] = 1.0; }
+        } else {
+            if (first) { d0[p] = 0.5; dp[p] = 0.5; } else { d0[p] = -0.5 / w; dm[p] = 0.5 / w; }
+        }
+    }
+    Diag D;
+    D[0] = d0;
+    auto addto = [&](int s, const std::vector<cplx>& v) {
+        s = norm_shift(s, n);
+        auto& dst = D[s];
+        if (dst.empty()) dst = v;
+        else for (int p = 0; p < n; ++p) dst[p] += v[p];
+    };
+    addto(lenh, dp);
+    addto(-lenh, dm);
+    return D;
+}
+
+}  // namespace
+
+struct LinStage {
+    int g = 1, n1 = 1, n2 = 1, off = 0, cnt = 0, level = 0;
+    std::vector<int> giant_rot;                    // rotation amount of giant step j (may be 0)
+    std::vector<std::vector<Elem>> pt;             // [j][b], invalid Elem = zero diagonal
+    std::vector<std::vector<std::vector<cplx>>> host;   // pre-rotated diagonals (kept for re-encoding at another level)
+};
+
+struct BootPrecomp {
+    int slots = 0, K = 28, R = 4, cheb_deg = 31, corr = 0;
+    std::vector<LinStage> cts, stc;
+    std::vector<double> cheb;
+    ScalarSet zeta;       // psi^(N/2) per Q limb (multiplication by i)
+};
+
+namespace {
+
+// split the merged matrix into the BSGS plan and pre-rotate its diagonals
+LinStage plan_stage(const Diag& M, int n, int g) {
+    LinStage st;
+    st.g = g;
+    int lo = 0, hi = 0;
+    std::map<int, const std::vector<cplx>*> byidx;
+    for (auto& kv : M) {
+        int d = kv.first;
+        if (d > n / 2) d -= n;                       // signed shift in (-n/2, n/2]
+        if (d % g) throw std::runtime_error("bootstrap: unexpected diagonal stride");
+        const int i = d / g;
+        lo = std::min(lo, i); hi = std::max(hi, i);
+        byidx[i] = &kv.second;
+    }
+    st.off = -lo;
+    st.cnt = hi - lo + 1;
+    st.n1 = 1;
+    while (st.n1 * st.n1 < st.cnt) st.n1 <<= 1;
+    st.n2 = (st.cnt + st.n1 - 1) / st.n1;
+    st.giant_rot.resize(st.n2);
+    st.host.assign(st.n2, std::vector<std::vector<cplx>>(st.n1));
+    for (int j = 0; j < st.n2; ++j) {
+        const int gr = g * (st.n1 * j - st.off);
+        st.giant_rot[j] = gr;
+        for (int b = 0; b < st.n1; ++b) {
+            auto it = byidx.find(st.n1 * j + b - st.off);
+            if (it == byidx.end()) continue;
+            st.host[j][b] = rot_vec(*it->second, -gr);      // P_{j,b} = Rot_{-giant}(D_i)
+        }
+    }
+    return st;
+}
+
+}  // namespace
+
+void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
+    const int n = P.N / 2;
+    if (slots != n) throw std::invalid_argument("EvalBootstrapSetup: only full packing (slots = N/2) is implemented");
+    if (boot_.count(slots)) return;
+    auto bp = std::make_shared<BootPrecomp>();
+    bp->slots = slots;
+    int logn = 0;
+    while ((1 << logn) < n) ++logn;
+    // correction factor rule of OpenFHE's EvalBootstrapSetup for FLEXIBLEAUTO (A.11), clamped to [7,13]
+    {
+        int cf = (int)std::lround(-0.265 * (2.0 * std::log2((double)P.N) + std::log2((double)slots)) + 19.1);
+        cf = std::min(13, std::max(7, cf));
+        const int deg = (int)std::lround(std::log2((double)P.q[0] / P.sf[0]));
+        bp->corr = std::max(0, cf - deg);
+        // OpenFHE's rule gives 4 here.  With our degree-31 / R = 4 EvalMod the interpolation error (amplified by
+        // q0 2^corr / 2 pi sf0 and by SlotsToCoeffs) balances the sine's cubic term at corr = 2 (measured:
+        // 1.1e-6 max slot error at N = 2^15 against 4.2e-6 at corr = 4), so cap it there.
+        bp->corr = std::min(bp->corr, 2);
+        if (const char* e = std::getenv("FLK_BOOT_CORR")) bp->corr = std::atoi(e);
+    }
+    const double q0 = (double)P.q[0];
+    // EvalMod polynomial
+    {
+        struct Ctx { int K, R; } cx{bp->K, bp->R};
+        auto f = [](double x, void* u) {
+            auto* c = (Ctx*)u;
+            return std::cos(2.0 * M_PI * (c->K * x - 0.25) / std::ldexp(1.0, c->R));
+        };
+        bp->cheb = chebyshev_coefficients(f, &cx, -1.0, 1.0, bp->cheb_deg);
+    }
+    // level flow: CtS stages at levels 0..b-1; EvalMod: Chebyshev depth D then R squarings; StC after that
+    int D = 0;
+    while ((1 << D) < bp->cheb_deg + 1) ++D;
+    const int stc_level0 = budget_cts + D + 1 + bp->R;   // Chebyshev: D levels + 1 for the scalar coefficients
+    auto build = [&](bool to_slots, int budget, double total_const, int level0) {
+        std::vector<LinStage> out;
+        // application order: CtS applies B_logn^-1 first ... B_1^-1 last; StC applies B_1 first ... B_logn last
+        std::vector<int> order;
+        for (int s = 1; s <= logn; ++s) order.push_back(s);
+        if (to_slots) std::reverse(order.begin(), order.end());
+        const double per_stage = std::pow(total_const, 1.0 / budget);
+        int pos = 0;
+        for (int b = 0; b < budget; ++b) {
+            const int cntf = (logn - pos + (budget - b) - 1) / (budget - b);
+            Diag M;
+            int smin = 1 << 30;
+            for (int t = 0; t < cntf; ++t) {
+                const int s = order[pos + t];
+                smin = std::min(smin, s);
+                Diag Bf = butterfly(n, 1 << s, to_slots);
+                M = M.empty() ? Bf : compose(Bf, M, n);
+            }
+            pos += cntf;
+            for (auto& kv : M) for (auto& v : kv.second) v *= per_stage;
+            LinStage st = plan_stage(M, n, 1 << (smin - 1));
+            st.level = level0 + b;
+            out.push_back(std::move(st));
+        }
+        return out;
+    };
+    // CtS: U0^-1 z = (t_lo + i t_hi)/sf0; want (t_lo + i t_hi)/(K q0), halved because re/im are taken as ct +- conj(ct)
+    bp->cts = build(true, budget_cts, 0.5 * P.sf[0] / (q0 * bp->K), 0);
+    // StC: sin(2 pi t/q0) ~ 2 pi m'/q0 with m' = sf0 2^-corr enc(v)  =>  multiply by q0 2^corr / (2 pi sf0)
+    bp->stc = build(false, budget_stc, q0 * std::ldexp(1.0, bp->corr) / (2.0 * M_PI * P.sf[0]), stc_level0);
+    for (auto* stages : {&bp->cts, &bp->stc})
+        for (auto& st : *stages) {
+            st.pt.assign(st.n2, std::vector<Elem>(st.n1));
+            for (int j = 0; j < st.n2; ++j)
+                for (int b = 0; b < st.n1; ++b)
+                    if (!st.host[j][b].empty()) st.pt[j][b] = encode(st.host[j][b].data(), n, st.level, n, 1);
+        }
+    for (int i = 0; i < P.L; ++i) {
+        const u64 z = nt::powmod(P.psi[i], (u64)P.N / 2, P.q[i]);
+        bp->zeta.c[i] = z; bp->zeta.c_sh[i] = nt::shoup(z, P.q[i]);
+    }
+    boot_[slots] = bp;
+}
+
+std::vector<int> Scheme::bootstrap_rotations(int slots) {
+    auto it = boot_.find(slots);
+    if (it == boot_.end()) throw std::runtime_error("EvalBootstrapKeyGen: call EvalBootstrapSetup first");
+    std::vector<int> r;
+    for (auto* stages : {&it->second->cts, &it->second->stc})
+        for (auto& st : *stages) {
+            for (int b = 1; b < st.n1; ++b) r.push_back(st.g * b);
+            for (int gr : st.giant_rot) if (gr) r.push_back(gr);
+        }
+    std::sort(r.begin(), r.end());
+    r.erase(std::unique(r.begin(), r.end()), r.end());
+    return r;
+}
+
+void Scheme::bootstrap_keygen(int slots) {
+    for (int k : bootstrap_rotations(slots)) gen_rotation_key(k);
+    gen_galois_key(P.galois_conj());
+    if (!mk_) gen_mult_key();
+}
+
+namespace {
+Elem apply_stage(Scheme& s, LinStage& st, const Elem& in_ct, int n) {
+    Elem ct = in_ct;
+    if (ct.deg == 2) s.rescale_inplace(ct);
+    const int lvl = s.level_of(ct);
+    if (lvl != st.level) {       // re-encode the diagonals at the level the ciphertext actually has
+        for (int j = 0; j < st.n2; ++j)
+            for (int b = 0; b < st.n1; ++b)
+                if (!st.host[j][b].empty()) st.pt[j][b] = s.encode(st.host[j][b].data(), n, lvl, n, 1);
+        st.level = lvl;
+    }
+    std::vector<Elem> baby(st.n1);
+    baby[0] = ct;
+    for (int b = 1; b < st.n1; ++b) {
+        bool needed = false;
+        for (int j = 0; j < st.n2; ++j) needed |= st.pt[j][b].valid();
+        if (needed) baby[b] = s.rotate(ct, st.g * b);
+    }
+    Elem acc;
+    for (int j = 0; j < st.n2; ++j) {
+        Elem inner;
+        for (int b = 0; b < st.n1; ++b) {
+            if (!st.pt[j][b].valid()) continue;
+            Elem t = s.mult(baby[b], st.pt[j][b]);
+            inner = inner.valid() ? s.add(inner, t) : t;
+        }
+        if (!inner.valid()) continue;
+        if (st.giant_rot[j]) inner = s.rotate(inner, st.giant_rot[j]);
+        acc = acc.valid() ? s.add(acc, inner) : inner;
+    }
+    return acc;
+}
+}  // namespace
+
+Elem Scheme::bootstrap(const Elem& in) {
+    if (in.ncomp != 2) throw std::invalid_argument("EvalBootstrap: ciphertext expected");
+    auto it = boot_.find(in.slots);
+    if (it == boot_.end()) throw std::runtime_error("EvalBootstrap: EvalBootstrapSetup was not called for this slot count");
+    BootPrecomp& bp = *it->second;
+    const int N = P.N, n = N / 2, L = P.L;
+    Elem ct = in;
+    if (ct.deg == 2) {
+        if (ct.l < 2) throw std::runtime_error("EvalBootstrap: degree-2 ciphertext at the last level");
+        rescale_inplace(ct);
+    }
+    // ---- pre-scaling (OpenFHE AdjustCiphertext): message polynomial becomes sf0 2^-corr enc(v), one limb left
+    double post_fix = 1.0;
+    if (ct.l >= 2) {
+        drop_to(ct, 2);
+        const double kd = (double)P.q[1] * P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));
+        mult_int_inplace(ct, (i128)std::rint(kd));
+        Elem r = make(2, 1, 1, P.sf[0], ct.slots);
+        eng.rescale(r.data(), ct.data(), 2, 2);
+        ct = r;
+    } else {
+        post_fix = P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));   // no limb to spend: fix the scale after StC
+    }
+    // ---- ModRaise: centred coefficients mod q0 -> all L limbs
+    Elem raised = make(2, L, 1, P.sf[0], ct.slots);
+    {
+        u64* x = eng.alloc((size_t)2 * N);
+        eng.copy(x, ct.data(), (size_t)2 * N);
+        LimbSel s0; s0.n = 2; s0.m[0] = s0.m[1] = 0; s0.pos[0] = 0; s0.pos[1] = 1;
+        eng.intt(x, s0);
+        launch_mod_switch(eng.T, raised.data(), x, 0, sel_range(0, L), 2, eng.stream);
+        LimbSel sa; sa.n = 2 * L;
+        for (int i = 0; i < 2 * L; ++i) { sa.m[i] = (uint8_t)(i % L); sa.pos[i] = (uint8_t)i; }
+        eng.ntt(raised.data(), sa);
+        eng.release(x);
+    }
+    // ---- CoeffsToSlots
+    Elem c = raised;
+    for (auto& st : bp.cts) c = apply_stage(*this, st, c, n);
+    // real / imaginary coefficient halves: x_lo = c + conj(c), x_hi = -i (c - conj(c))   (the 1/2 is folded into CtS)
+    Elem cc = conjugate(c);
+    Elem xlo = add(c, cc);
+    Elem dif = sub(c, cc);
+    auto times_i = [&](const Elem& a, bool negate) {
+        Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
+        launch_mul_i(eng.T, r.data(), a.data(), bp.zeta, sel_range(0, a.l), a.ncomp, eng.stream);
+        if (negate) mult_int_inplace(r, -1);
+        return r;
+    };
+    Elem xhi = times_i(dif, true);
+    // ---- EvalMod on both halves
+    auto eval_mod = [&](const Elem& x) {
+        std::vector<double> cf = bp.cheb;
+        cf[0] *= 0.5;
+        Elem y = cheby_ps(x, cf);
+        for (int r = 0; r < bp.R; ++r) {
+            Elem sq = square(y);
+            y = add_const(add(sq, sq), -1.0);
+        }
+        return y;
+    };
+    Elem ylo = eval_mod(xlo), yhi = eval_mod(xhi);
+    Elem y = add(ylo, times_i(yhi, false));
+    // ---- SlotsToCoeffs
+    for (auto& st : bp.stc) y = apply_stage(*this, st, y, n);
+    if (post_fix != 1.0) y = mult_const(y, post_fix);
+    return y;
+}
+
+}  // namespace flk

@@ -4,12 +4,19 @@
 #include <cstring>
 #include <string>
 
-#include "engine.h"
+#include <cstdio>
+#include <vector>
+
+#include "scheme.h"
 
 using namespace flk;
 
 struct fl_ctx {
-    Engine* eng;
+    Scheme* sch;
+    Engine* eng;   // = &sch->eng
+};
+struct fl_elem {
+    Elem e;
 };
 
 static thread_local std::string g_err;
@@ -42,14 +49,15 @@ int fl_ctx_create(const fl_params* p, int device, fl_ctx** out) {
         ParamSpec s;
         s.logN = p->logN; s.L = p->L; s.dnum = p->dnum; s.first_bits = p->first_bits; s.scale_bits = p->scale_bits;
         s.aux_bits = p->aux_bits; s.sparse_h = p->sparse_h;
-        fl_ctx* c = new fl_ctx{nullptr};
-        try { c->eng = new Engine(s, device); } catch (...) { delete c; throw; }
+        fl_ctx* c = new fl_ctx{nullptr, nullptr};
+        try { c->sch = new Scheme(s, device); } catch (...) { delete c; throw; }
+        c->eng = &c->sch->eng;
         *out = c;
     })
 }
 void fl_ctx_destroy(fl_ctx* c) {
     if (!c) return;
-    delete c->eng;
+    delete c->sch;
     delete c;
 }
 int fl_ctx_info(fl_ctx* c, int* info) {
@@ -127,6 +135,101 @@ int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, con
         e.mul_relin(out, a, b, l, evk_dev);
         e.download(out_host, out, w);
         e.release(a); e.release(b); e.release(out);
+    })
+}
+
+
+// ======================= scheme level =======================
+static fl_elem* wrap(Elem&& e) { return new fl_elem{std::move(e)}; }
+
+int fl_keygen(fl_ctx* c, uint64_t seed) { FL_TRY(c->sch->keygen(seed)) }
+int fl_gen_mult_key(fl_ctx* c) { FL_TRY(c->sch->gen_mult_key()) }
+int fl_gen_rot_keys(fl_ctx* c, const int* idx, int n) { FL_TRY(for (int i = 0; i < n; ++i) c->sch->gen_rotation_key(idx[i])) }
+int fl_gen_conj_key(fl_ctx* c) { FL_TRY(c->sch->gen_galois_key(c->sch->P.galois_conj())) }
+int fl_keys_clear(fl_ctx* c, int kind) { FL_TRY(if (kind == 0) c->sch->clear_rotation_keys(); else c->sch->clear_mult_key()) }
+int fl_num_rot_keys(fl_ctx* c) { return (int)c->sch->num_galois_keys(); }
+int fl_export_sk(fl_ctx* c, uint64_t* out) { FL_TRY(c->sch->export_sk(out)) }
+int fl_export_pk(fl_ctx* c, uint64_t* out) { FL_TRY(c->sch->export_pk(out)) }
+int fl_export_evk(fl_ctx* c, uint32_t g, uint64_t* out) { FL_TRY(c->sch->export_evk(g, out)) }
+int fl_import_keys(fl_ctx* c, const uint64_t* sk, const uint64_t* pk) { FL_TRY(c->sch->import_keys(sk, pk)) }
+int fl_import_evk(fl_ctx* c, uint32_t g, const uint64_t* evk) { FL_TRY(c->sch->import_evk(g, evk)) }
+int fl_keys_save(fl_ctx* c, const char* path) { FL_TRY(c->sch->save_keys(path)) }
+int fl_keys_load(fl_ctx* c, const char* path) { FL_TRY(c->sch->load_keys(path)) }
+
+int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out) {
+    FL_TRY({
+        std::vector<cplx> v(n);
+        for (int i = 0; i < n; ++i) v[i] = cplx(re[i], im ? im[i] : 0.0);
+        *out = wrap(c->sch->encode(v.data(), n, level, slots, 1));
+    })
+}
+int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out) { FL_TRY(*out = wrap(c->sch->encrypt(p->e))) }
+int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out) { FL_TRY(*out = wrap(c->sch->encrypt_seeded(p->e, seed))) }
+static void split(const std::vector<cplx>& v, double* re, double* im) {
+    for (size_t i = 0; i < v.size(); ++i) { re[i] = v[i].real(); if (im) im[i] = v[i].imag(); }
+}
+int fl_decrypt(fl_ctx* c, const fl_ct* a, double* re, double* im, int slots) {
+    FL_TRY({ std::vector<cplx> v(slots); c->sch->decrypt(a->e, v.data(), slots); split(v, re, im); })
+}
+int fl_decode(fl_ctx* c, const fl_pt* p, double* re, double* im, int slots) {
+    FL_TRY({ std::vector<cplx> v(slots); c->sch->decode(p->e, v.data(), slots); split(v, re, im); })
+}
+int fl_add(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out) { FL_TRY(*out = wrap(c->sch->add(a->e, b->e))) }
+int fl_sub(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out) { FL_TRY(*out = wrap(c->sch->sub(a->e, b->e))) }
+int fl_add_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out) {
+    FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->add_many(std::move(e))); })
+}
+int fl_add_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->add_const(a->e, k))) }
+int fl_mul(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out) { FL_TRY(*out = wrap(c->sch->mult(a->e, b->e))) }
+int fl_mul_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->mult_const(a->e, k))) }
+int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out) {
+    FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->mult_many(std::move(e))); })
+}
+int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotate(a->e, k))) }
+int fl_conjugate(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->conjugate(a->e))) }
+int fl_rescale(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rescaled(a->e))) }
+int fl_eval_poly(fl_ctx* c, const fl_ct* a, const double* coeffs, int n, fl_ct** out) {
+    FL_TRY(*out = wrap(c->sch->eval_poly(a->e, std::vector<double>(coeffs, coeffs + n))))
+}
+int fl_eval_chebyshev(fl_ctx* c, const fl_ct* x, const double* coeffs, int n, double a, double b, fl_ct** out) {
+    FL_TRY(*out = wrap(c->sch->eval_chebyshev(x->e, std::vector<double>(coeffs, coeffs + n), a, b)))
+}
+int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree, double* out) {
+    FL_TRY({ auto v = Scheme::chebyshev_coefficients(f, user, a, b, degree); std::memcpy(out, v.data(), 8 * v.size()); })
+}
+int fl_bootstrap_setup(fl_ctx* c, int b0, int b1, int slots) { FL_TRY(c->sch->bootstrap_setup(b0, b1, slots)) }
+int fl_bootstrap_keygen(fl_ctx* c, int slots) { FL_TRY(c->sch->bootstrap_keygen(slots)) }
+int fl_bootstrap(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->bootstrap(a->e))) }
+
+int fl_elem_level(const fl_elem* a) { return a->e.valid() ? (int)(a->e.mem->eng->P.L - a->e.l) : -1; }
+int fl_elem_limbs(const fl_elem* a) { return a->e.l; }
+int fl_elem_deg(const fl_elem* a) { return a->e.deg; }
+int fl_elem_slots(const fl_elem* a) { return a->e.slots; }
+int fl_elem_ncomp(const fl_elem* a) { return a->e.ncomp; }
+double fl_elem_scale(const fl_elem* a) { return a->e.scale; }
+int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out) { FL_TRY(*out = wrap(c->sch->clone(a->e))) }
+void fl_elem_free(fl_elem* a) { delete a; }
+int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host) {
+    FL_TRY(c->eng->download(host, a->e.data(), (size_t)a->e.ncomp * a->e.l * c->eng->P.N))
+}
+int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int deg, double scale, int slots, fl_elem** out) {
+    FL_TRY(*out = wrap(c->sch->import_elem(host, ncomp, limbs, deg, scale, slots)))
+}
+int fl_elem_save(fl_ctx* c, const fl_elem* a, const char* path) { FL_TRY(c->sch->save_elem(a->e, path)) }
+int fl_elem_load(fl_ctx* c, const char* path, fl_elem** out) { FL_TRY(*out = wrap(c->sch->load_elem(path))) }
+
+int fl_ledger_enable(fl_ctx* c, int on) { c->eng->ledger_on = on != 0; return 0; }
+int fl_ledger_reset(fl_ctx* c) { c->eng->ledger.reset(); return 0; }
+int fl_ledger_dump(fl_ctx* c, char* buf, size_t cap) {
+    FL_TRY({
+        std::string s;
+        for (auto& kv : c->eng->ledger.rows) {
+            char line[160];
+            std::snprintf(line, sizeof line, "%s %ld %.0f\n", kv.first.c_str(), kv.second.count, kv.second.bytes);
+            s += line;
+        }
+        if (s.size() + 1 > cap) throw std::runtime_error("ledger buffer too small");
+        std::memcpy(buf, s.c_str(), s.size() + 1);
     })
 }
 

@@ -186,6 +186,31 @@ __global__ void __launch_bounds__(kThreads) rescale_finish_kernel(u64* __restric
     out[oo] = mul_shoup(submod(in[oi], tq[oo], q), w, ws, q);
 }
 
+__global__ void __launch_bounds__(kThreads) mod_switch_kernel(u64* __restrict__ out, const u64* __restrict__ x, DevTables T, int src_mod, LimbSel sel) {
+    const int p = blockIdx.z, i = blockIdx.y;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const int m = sel.m[i];
+    const u64 qs = T.q[src_mod], half = qs >> 1, q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
+    const u64 v0 = x[(size_t)p * T.N + j];
+    u64 v = barrett128(U128{v0, 0}, q, ml, mh);
+    if (v0 > half) v = submod(v, barrett128(U128{qs, 0}, q, ml, mh), q);
+    out[((size_t)p * sel.n + i) * T.N + j] = v;
+}
+
+__global__ void __launch_bounds__(kThreads) mul_i_kernel(u64* __restrict__ out, const u64* __restrict__ a, DevTables T, LimbSel sel, ScalarSet sc,
+                                                         int polys) {
+    const size_t per_poly = (size_t)sel.n * T.N;
+    const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= per_poly * polys) return;
+    const size_t r = e % per_poly;
+    const int limb = (int)(r >> T.logN), j = (int)(r & (T.N - 1));
+    const u64 q = T.q[sel.m[limb]];
+    u64 v = mul_shoup(a[e], sc.c[limb], sc.c_sh[limb], q);
+    if (j >= (T.N >> 1) && v) v = q - v;
+    out[e] = v;
+}
+
 // ---------------- integer coefficients -> residues ----------------
 __global__ void __launch_bounds__(kThreads) reduce_i64_kernel(u64* __restrict__ out, const int64_t* __restrict__ coef, DevTables T, LimbSel sel) {
     const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
@@ -277,6 +302,14 @@ void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, i
 }
 void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s) {
     rescale_finish_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(out, in, tq, t, rs, l);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_mod_switch(const DevTables& t, u64* out, const u64* x, int src_mod, const LimbSel& sel, int polys, cudaStream_t s) {
+    mod_switch_kernel<<<dim3(cdiv(t.N, kThreads), sel.n, polys), kThreads, 0, s>>>(out, x, t, src_mod, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_mul_i(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s) {
+    mul_i_kernel<<<cdiv((size_t)polys * sel.n * t.N, kThreads), kThreads, 0, s>>>(out, a, t, sel, sc, polys);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_reduce_i64(const DevTables& t, u64* out, const int64_t* coef, const LimbSel& sel, cudaStream_t s) {

@@ -64,6 +64,12 @@ void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, i
 // out[p][i] = (in[p][i] - tq[p][i]) * q_{l-1}^-1 ; in has l limbs per poly, out has l-1
 void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s);
 
+// ModRaise / modulus switch: out[p][i][j] = centred(x[p][j] mod q_src) mod q_{sel.m[i]}   (x in coefficient form)
+void launch_mod_switch(const DevTables& t, u64* out, const u64* x, int src_mod, const LimbSel& sel, int polys, cudaStream_t s);
+// multiplication by the monomial X^(N/2) (every slot times i) in evaluation format: first half of each limb times zeta,
+// second half times -zeta, zeta = psi^(N/2); sc holds zeta per limb
+void launch_mul_i(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s);
+
 // coefficients (signed, as int64 or int128 lo/hi) -> residues, [l][N] for moduli sel
 void launch_reduce_i64(const DevTables& t, u64* out, const int64_t* coef, const LimbSel& sel, cudaStream_t s);
 void launch_reduce_i128(const DevTables& t, u64* out, const int64_t* coef_lohi, const LimbSel& sel, cudaStream_t s);

@@ -1,0 +1,559 @@
+// scheme.cpp -- CKKS scheme layer: keys, encoding, encryption and the leveled operations with OpenFHE's
+// FLEXIBLEAUTO bookkeeping, all arithmetic on the device engine.
+#include "scheme.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace flk {
+
+namespace {
+
+// |X| cumulative distribution of the discrete Gaussian, sigma = 3.19, scaled to 2^64 (DESIGN.md "Randomness")
+const u64 kGaussCdt[30] = {
+    0x2003F343659528D0ull, 0x5CF9E7DE0F06D96Bull, 0x9194FD0BB0694AF3ull, 0xBABAA2EF1EEC1101ull, 0xD7E6AB30AA084360ull,
+    0xEAA5B92100F77DABull, 0xF591040AC34992E9ull, 0xFB54CB2CA496FFFAull, 0xFE1702297749D972ull, 0xFF4953F8BD4AE9D1ull,
+    0xFFC1C20EF5DE7233ull, 0xFFECAC7F021E2BA0ull, 0xFFFA892133378B29ull, 0xFFFE9810099A70DBull, 0xFFFFABC31CFFB430ull,
+    0xFFFFEE138CF385DBull, 0xFFFFFC88B8F21ED7ull, 0xFFFFFF641EF54A94ull, 0xFFFFFFE7207A46BAull, 0xFFFFFFFC6560DA3Aull,
+    0xFFFFFFFF86A24B98ull, 0xFFFFFFFFF1822EC9ull, 0xFFFFFFFFFE6DFC66ull, 0xFFFFFFFFFFD877EFull, 0xFFFFFFFFFFFC7916ull,
+    0xFFFFFFFFFFFFB6EAull, 0xFFFFFFFFFFFFFAA2ull, 0xFFFFFFFFFFFFFFA4ull, 0xFFFFFFFFFFFFFFFAull, 0xFFFFFFFFFFFFFFFFull};
+
+std::vector<int8_t> sample_ternary(int N, u64 seed) {
+    SplitMix r(seed);
+    std::vector<int8_t> s(N);
+    for (int j = 0; j < N; ++j) { u64 v = r.next() % 3; s[j] = v == 2 ? -1 : (int8_t)v; }
+    return s;
+}
+std::vector<int8_t> sample_sparse(int N, int h, u64 seed) {
+    SplitMix r(seed);
+    std::vector<int8_t> s(N, 0);
+    for (int placed = 0; placed < h;) {
+        u64 pos = r.next() % N, sg = r.next() & 1;
+        if (!s[pos]) { s[pos] = sg ? -1 : 1; ++placed; }
+    }
+    return s;
+}
+std::vector<int8_t> sample_gauss(int N, u64 seed) {
+    SplitMix r(seed);
+    std::vector<int8_t> s(N);
+    for (int j = 0; j < N; ++j) {
+        u64 u = r.next(), sg = r.next() & 1;
+        int k = 0;
+        while (k < 29 && u >= kGaussCdt[k]) ++k;
+        s[j] = (int8_t)(sg ? -k : k);
+    }
+    return s;
+}
+
+// special FFT of CKKS encoding (A.9), tables cached per slot count
+struct FftTables {
+    std::vector<uint32_t> rot;
+    std::vector<double> cre, cim;
+};
+const FftTables& fft_tables(int n) {
+    static std::map<int, FftTables> cache;
+    auto it = cache.find(n);
+    if (it != cache.end()) return it->second;
+    FftTables t;
+    const uint32_t m = 4u * n;
+    t.rot.resize(n);
+    uint32_t p = 1;
+    for (int i = 0; i < n; ++i) { t.rot[i] = p; p = (uint32_t)(((u64)p * 5) % m); }
+    t.cre.resize(m + 1); t.cim.resize(m + 1);
+    for (uint32_t k = 0; k <= m; ++k) {
+        double a = 2.0 * M_PI * (double)k / (double)m;
+        t.cre[k] = std::cos(a); t.cim[k] = std::sin(a);
+    }
+    return cache.emplace(n, std::move(t)).first->second;
+}
+void bit_reverse(double* re, double* im, int n) {
+    for (int i = 1, j = 0; i < n; ++i) {
+        int bit = n >> 1;
+        for (; j >= bit; bit >>= 1) j -= bit;
+        j += bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+}
+void fft_special_inv(double* re, double* im, int n) {
+    const FftTables& t = fft_tables(n);
+    const uint32_t m = 4u * n;
+    for (int len = n; len >= 2; len >>= 1) {
+        const int lenh = len >> 1;
+        const uint32_t lenq = (uint32_t)len << 2;
+        for (int i = 0; i < n; i += len)
+            for (int j = 0; j < lenh; ++j) {
+                const uint32_t idx = (lenq - (t.rot[j] % lenq)) * (m / lenq);
+                const double ur = re[i + j] + re[i + j + lenh], ui = im[i + j] + im[i + j + lenh];
+                const double wr = re[i + j] - re[i + j + lenh], wi = im[i + j] - im[i + j + lenh];
+                const double kr = t.cre[idx], ki = t.cim[idx];
+                re[i + j] = ur; im[i + j] = ui;
+                re[i + j + lenh] = wr * kr - wi * ki;
+                im[i + j + lenh] = wr * ki + wi * kr;
+            }
+    }
+    bit_reverse(re, im, n);
+    for (int i = 0; i < n; ++i) { re[i] /= n; im[i] /= n; }
+}
+void fft_special(double* re, double* im, int n) {
+    const FftTables& t = fft_tables(n);
+    const uint32_t m = 4u * n;
+    bit_reverse(re, im, n);
+    for (int len = 2; len <= n; len <<= 1) {
+        const int lenh = len >> 1;
+        const uint32_t lenq = (uint32_t)len << 2;
+        for (int i = 0; i < n; i += len)
+            for (int j = 0; j < lenh; ++j) {
+                const uint32_t idx = (t.rot[j] % lenq) * (m / lenq);
+                const double kr = t.cre[idx], ki = t.cim[idx];
+                const double ar = re[i + j], ai = im[i + j], br = re[i + j + lenh], bi = im[i + j + lenh];
+                const double wr = br * kr - bi * ki, wi = br * ki + bi * kr;
+                re[i + j] = ar + wr; im[i + j] = ai + wi;
+                re[i + j + lenh] = ar - wr; im[i + j + lenh] = ai - wi;
+            }
+    }
+}
+
+}  // namespace
+
+Scheme::Scheme(const ParamSpec& spec, int device) : eng(spec, device), P(eng.P) {}
+
+Scheme::~Scheme() {
+    try {
+        eng.sync();
+        boot_.clear();
+        eng.release(sk_); eng.release(pk_); eng.release(mk_);
+        for (auto& kv : gk_) eng.release(kv.second);
+        eng.sync();
+    } catch (...) {}
+}
+
+Elem Scheme::make(int ncomp, int l, int deg, double scale, int slots) {
+    Elem e;
+    e.mem = std::make_shared<DevMem>(&eng, (size_t)ncomp * l * P.N);
+    e.ncomp = ncomp; e.l = l; e.deg = deg; e.scale = scale; e.slots = slots;
+    return e;
+}
+
+// ---------------------------------------------------------------- keys
+void Scheme::sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSel& sel) {
+    int8_t* d8 = (int8_t*)eng.alloc((P.N + 7) / 8);
+    FLK_CUDA(cudaMemcpyAsync(d8, s.data(), P.N, cudaMemcpyHostToDevice, eng.stream));
+    launch_reduce_i8(eng.T, dst, d8, sel, eng.stream);
+    eng.ntt(dst, sel);
+    eng.sync();   // s is a host temporary
+    eng.release((u64*)d8);
+}
+
+void Scheme::uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel) {
+    std::vector<u64> h((size_t)sel.n * P.N);
+    for (int i = 0; i < sel.n; ++i) {
+        SplitMix r(SplitMix::sub(seed, 1000 + sel.m[i]));
+        const u64 q = P.q[sel.m[i]];
+        u64* o = &h[(size_t)i * P.N];
+        for (int j = 0; j < P.N; ++j) o[j] = r.next() % q;
+    }
+    eng.upload(dst, h.data(), h.size());
+    eng.sync();
+}
+
+void Scheme::keygen(u64 seed) {
+    key_seed_ = seed;
+    const int T = P.T, N = P.N;
+    if (!sk_) sk_ = eng.alloc((size_t)T * N);
+    if (!pk_) pk_ = eng.alloc((size_t)2 * P.L * N);
+    auto s = P.spec.sparse_h > 0 ? sample_sparse(N, P.spec.sparse_h, SplitMix::sub(seed, 0)) : sample_ternary(N, SplitMix::sub(seed, 0));
+    sample_to_eval(sk_, s, sel_range(0, T));
+    // pk = (e - a*s, a)
+    const LimbSel q = sel_range(0, P.L);
+    const size_t pl = (size_t)P.L * N;
+    const u64 pseed = seed + 1;
+    uniform_to_dev(pk_ + pl, SplitMix::sub(pseed, 10), q);
+    u64* e = eng.alloc(pl);
+    sample_to_eval(e, sample_gauss(N, SplitMix::sub(pseed, 11)), q);
+    launch_ew(eng.T, EwOp::Mul, pk_, pk_ + pl, sk_, q, 1, 1, 0, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Sub, pk_, e, pk_, q, 1, 1, 0, 0, 0, eng.stream);
+    eng.release(e);
+}
+
+// hybrid key-switching key from s_old to s_new (A.6): per digit d, (b_d, a_d) with
+// b_d = e_d - a_d s_new + [limb in digit d] (P mod q_i) s_old
+void Scheme::keyswitch_gen(const u64* sk_old, const u64* sk_new, u64 seed, u64* evk) {
+    const int T = P.T, N = P.N;
+    const size_t kl = (size_t)T * N;
+    const LimbSel all = sel_range(0, T);
+    u64* e = eng.alloc(kl);
+    u64* tmp = eng.alloc((size_t)P.alpha * N);
+    for (int d = 0; d < P.dnum; ++d) {
+        u64* b = evk + (size_t)d * 2 * kl;
+        u64* a = b + kl;
+        uniform_to_dev(a, SplitMix::sub(seed, 100 + 2 * d), all);
+        sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 101 + 2 * d)), all);
+        launch_ew(eng.T, EwOp::Mul, b, a, sk_new, all, 1, 1, 0, 0, 0, eng.stream);
+        launch_ew(eng.T, EwOp::Sub, b, e, b, all, 1, 1, 0, 0, 0, eng.stream);
+        const int lo = d * P.alpha, hi = std::min(lo + P.alpha, P.L), ns = hi - lo;
+        ScalarSet sc;
+        for (int i = 0; i < ns; ++i) { sc.c[i] = P.P_mod(P.q[lo + i]); sc.c_sh[i] = nt::shoup(sc.c[i], P.q[lo + i]); }
+        const LimbSel ds = sel_range(lo, ns);
+        launch_mul_scalar(eng.T, tmp, sk_old + (size_t)lo * N, sc, ds, 1, eng.stream);
+        launch_ew(eng.T, EwOp::Add, b + (size_t)lo * N, b + (size_t)lo * N, tmp, ds, 1, 1, 0, 0, 0, eng.stream);
+    }
+    eng.release(e); eng.release(tmp);
+}
+
+void Scheme::gen_mult_key() {
+    if (!sk_) throw std::runtime_error("EvalMultKeyGen: no secret key");
+    const size_t kl = (size_t)P.T * P.N;
+    u64* s2 = eng.alloc(kl);
+    launch_ew(eng.T, EwOp::Mul, s2, sk_, sk_, sel_range(0, P.T), 1, 1, 0, 0, 0, eng.stream);
+    if (!mk_) mk_ = eng.alloc(eng.evk_words());
+    keyswitch_gen(s2, sk_, key_seed_ + 2, mk_);
+    eng.release(s2);
+}
+
+void Scheme::gen_galois_key(uint32_t g) {
+    if (!sk_) throw std::runtime_error("EvalAutomorphismKeyGen: no secret key");
+    if (gk_.count(g)) return;
+    // switch from s to sigma_{g^-1}(s); the permutation by g that follows restores s (A.5)
+    uint32_t gi = 1;
+    for (int i = 0; i < 6; ++i) gi = gi * (2 - g * gi);
+    gi &= (uint32_t)(2 * P.N - 1);
+    u64* sp = eng.alloc((size_t)P.T * P.N);
+    eng.automorph(sp, sk_, gi, P.T);
+    u64* evk = eng.alloc(eng.evk_words());
+    keyswitch_gen(sk_, sp, key_seed_ + 1000 + g, evk);
+    eng.release(sp);
+    gk_[g] = evk;
+}
+void Scheme::gen_rotation_key(int k) { gen_galois_key(P.galois_for_rotation(k)); }
+
+void Scheme::clear_rotation_keys() {
+    for (auto& kv : gk_) eng.release(kv.second);
+    gk_.clear();
+}
+void Scheme::clear_mult_key() { eng.release(mk_); mk_ = nullptr; }
+
+void Scheme::export_sk(u64* out) const { const_cast<Engine&>(eng).download(out, sk_, (size_t)P.T * P.N); }
+void Scheme::export_pk(u64* out) const { const_cast<Engine&>(eng).download(out, pk_, (size_t)2 * P.L * P.N); }
+void Scheme::export_evk(uint32_t g, u64* out) const {
+    const u64* src = g == 0 ? mk_ : (gk_.count(g) ? gk_.at(g) : nullptr);
+    if (!src) throw std::runtime_error("export_evk: key not present");
+    const_cast<Engine&>(eng).download(out, src, eng.evk_words());
+}
+void Scheme::import_keys(const u64* sk, const u64* pk) {
+    if (sk) { if (!sk_) sk_ = eng.alloc((size_t)P.T * P.N); eng.upload(sk_, sk, (size_t)P.T * P.N); }
+    if (pk) { if (!pk_) pk_ = eng.alloc((size_t)2 * P.L * P.N); eng.upload(pk_, pk, (size_t)2 * P.L * P.N); }
+    eng.sync();
+}
+void Scheme::import_evk(uint32_t g, const u64* evk) {
+    u64*& dst = g == 0 ? mk_ : gk_[g];
+    if (!dst) dst = eng.alloc(eng.evk_words());
+    eng.upload(dst, evk, eng.evk_words());
+    eng.sync();
+}
+
+// ---------------------------------------------------------------- encode / decode
+void Scheme::encode_coeffs(const cplx* vals, int n, int slots, double scale, std::vector<i128>& co) const {
+    const int N = P.N, Nh = N / 2;
+    if (slots < 1 || slots > Nh || (slots & (slots - 1))) throw std::invalid_argument("encode: slots must be a power of two <= N/2");
+    const int gap = Nh / slots;
+    std::vector<double> re(slots, 0.0), im(slots, 0.0);
+    for (int i = 0; i < std::min(n, slots); ++i) { re[i] = vals[i].real(); im[i] = vals[i].imag(); }
+    fft_special_inv(re.data(), im.data(), slots);
+    co.assign(N, 0);
+    for (int i = 0; i < slots; ++i) {
+        co[(size_t)i * gap] = (i128)std::rint(re[i] * scale);
+        co[(size_t)Nh + (size_t)i * gap] = (i128)std::rint(im[i] * scale);
+    }
+}
+
+void Scheme::coeffs_to_dev(u64* dst, const std::vector<i128>& co, int l) {
+    const int N = P.N;
+    std::vector<int64_t> lohi((size_t)2 * N);
+    for (int j = 0; j < N; ++j) { lohi[2 * j] = (int64_t)(u64)co[j]; lohi[2 * j + 1] = (int64_t)(co[j] >> 64); }
+    int64_t* d = (int64_t*)eng.alloc((size_t)2 * N);
+    FLK_CUDA(cudaMemcpyAsync(d, lohi.data(), (size_t)16 * N, cudaMemcpyHostToDevice, eng.stream));
+    const LimbSel sel = sel_range(0, l);
+    launch_reduce_i128(eng.T, dst, d, sel, eng.stream);
+    eng.ntt(dst, sel);
+    eng.sync();
+    eng.release((u64*)d);
+}
+
+Elem Scheme::encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg) {
+    if (l < 1 || l > P.L) throw std::invalid_argument("encode: level out of range");
+    std::vector<i128> co;
+    encode_coeffs(vals, n, slots, scale, co);
+    Elem e = make(1, l, deg, scale, slots);
+    coeffs_to_dev(e.data(), co, l);
+    return e;
+}
+
+Elem Scheme::encode(const cplx* vals, int n, int level, int slots, int deg) {
+    if (level < 0 || level >= P.L) throw std::invalid_argument("encode: level out of range");
+    double scale = P.sf[level];
+    if (deg == 2) scale *= scale;
+    return encode_at(vals, n, P.L - level, scale, slots, deg);
+}
+
+Elem Scheme::encode_real(const double* vals, int n, int level, int slots) {
+    std::vector<cplx> v(n);
+    for (int i = 0; i < n; ++i) v[i] = cplx(vals[i], 0.0);
+    return encode(v.data(), n, level, slots, 1);
+}
+
+void Scheme::decode(const Elem& pt, cplx* out, int slots) {
+    const int N = P.N, Nh = N / 2;
+    if (slots <= 0) slots = pt.slots;
+    const int gap = Nh / slots;
+    const int nl = pt.l >= 2 ? 2 : 1;
+    u64* d = eng.alloc((size_t)nl * N);
+    eng.copy(d, pt.data(), (size_t)nl * N);
+    eng.intt(d, sel_range(0, nl));
+    std::vector<u64> x((size_t)nl * N);
+    eng.download(x.data(), d, x.size());
+    eng.release(d);
+    std::vector<double> re(slots), im(slots);
+    auto coef = [&](int j) -> double {
+        if (nl == 1) {
+            const u64 q = P.q[0];
+            return x[j] > q / 2 ? -(double)(q - x[j]) : (double)x[j];
+        }
+        const u64 q0 = P.q[0], q1 = P.q[1];
+        static thread_local u64 cq0 = 0, cq1 = 0, inv = 0;
+        if (cq0 != q0 || cq1 != q1) { cq0 = q0; cq1 = q1; inv = nt::invmod(q0 % q1, q1); }
+        const u64 x0 = x[j], x1 = x[(size_t)N + j];
+        const u64 x0m = x0 % q1;
+        const u64 dlt = x1 >= x0m ? x1 - x0m : x1 + q1 - x0m;
+        const u128 v = (u128)x0 + (u128)q0 * nt::mulmod(dlt, inv, q1), Q = (u128)q0 * q1;
+        return v > Q / 2 ? -(double)(Q - v) : (double)v;
+    };
+    for (int i = 0; i < slots; ++i) { re[i] = coef(i * gap) / pt.scale; im[i] = coef(Nh + i * gap) / pt.scale; }
+    fft_special(re.data(), im.data(), slots);
+    for (int i = 0; i < slots; ++i) out[i] = cplx(re[i], im[i]);
+}
+
+// ---------------------------------------------------------------- encrypt / decrypt
+Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) {
+    if (!pk_) throw std::runtime_error("Encrypt: no public key");
+    if (pt.ncomp != 1) throw std::invalid_argument("Encrypt: plaintext expected");
+    const int l = pt.l, N = P.N;
+    const size_t pl = (size_t)l * N, pkl = (size_t)P.L * N;
+    const LimbSel sel = sel_range(0, l);
+    Elem ct = make(2, l, pt.deg, pt.scale, pt.slots);
+    u64* v = eng.alloc(pl);
+    u64* e = eng.alloc(pl);
+    sample_to_eval(v, sample_ternary(N, SplitMix::sub(seed, 1)), sel);
+    sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 2)), sel);
+    u64* c0 = ct.data(); u64* c1 = c0 + pl;
+    launch_ew(eng.T, EwOp::Mul, c0, pk_, v, sel, 1, 1, 0, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, c0, c0, e, sel, 1, 1, 0, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, c0, c0, pt.data(), sel, 1, 1, 0, 0, 0, eng.stream);
+    sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 3)), sel);
+    launch_ew(eng.T, EwOp::Mul, c1, pk_ + pkl, v, sel, 1, 1, 0, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, c1, c1, e, sel, 1, 1, 0, 0, 0, eng.stream);
+    eng.release(v); eng.release(e);
+    return ct;
+}
+Elem Scheme::encrypt(const Elem& pt) { return encrypt_seeded(pt, SplitMix::sub(key_seed_, 0xE0000 + (seed_counter++))); }
+
+void Scheme::decrypt(const Elem& ct_in, cplx* out, int slots) {
+    if (!sk_) throw std::runtime_error("Decrypt: no secret key");
+    Elem ct = ct_in;
+    if (ct.deg >= 2 && ct.l >= 2) rescale_inplace(ct);      // bring the message under two limbs before decoding
+    const int l = ct.l;
+    const size_t pl = (size_t)l * P.N;
+    Elem m = make(1, l, ct.deg, ct.scale, ct.slots);
+    launch_ew(eng.T, EwOp::Mul, m.data(), ct.data() + pl, sk_, sel_range(0, l), 1, 1, 0, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, m.data(), m.data(), ct.data(), sel_range(0, l), 1, 1, 0, 0, 0, eng.stream);
+    decode(m, out, slots > 0 ? slots : ct.slots);
+}
+
+// ---------------------------------------------------------------- level / scale plumbing
+Elem Scheme::clone(const Elem& a) {
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
+    eng.copy(r.data(), a.data(), (size_t)a.ncomp * a.l * P.N);
+    return r;
+}
+
+void Scheme::drop_to(Elem& a, int l) {
+    if (l == a.l) return;
+    if (l > a.l || l < 1) throw std::invalid_argument("LevelReduce: bad target");
+    Elem r = make(a.ncomp, l, a.deg, a.scale, a.slots);
+    for (int c = 0; c < a.ncomp; ++c) eng.copy(r.data() + (size_t)c * l * P.N, a.data() + (size_t)c * a.l * P.N, (size_t)l * P.N);
+    a = r;
+}
+void Scheme::level_reduce_inplace(Elem& a, int levels) { if (levels > 0) drop_to(a, a.l - levels); }
+
+void Scheme::rescale_inplace(Elem& a) {
+    if (a.l < 2) throw std::runtime_error("rescale: ciphertext is at the last level");
+    Elem r = make(a.ncomp, a.l - 1, a.deg - 1, a.scale / (double)P.q[a.l - 1], a.slots);
+    eng.rescale(r.data(), a.data(), a.l, a.ncomp);
+    a = r;
+}
+Elem Scheme::rescaled(const Elem& a) { Elem r = a; rescale_inplace(r); return r; }
+
+ScalarSet Scheme::scalar_set(i128 k, int l) const {
+    ScalarSet sc;
+    for (int i = 0; i < l; ++i) {
+        i128 r = k % (i128)P.q[i];
+        if (r < 0) r += P.q[i];
+        sc.c[i] = (u64)r; sc.c_sh[i] = nt::shoup((u64)r, P.q[i]);
+    }
+    return sc;
+}
+
+void Scheme::mult_int_inplace(Elem& a, i128 k) {
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
+    launch_mul_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), a.ncomp, eng.stream);
+    a = r;
+}
+
+void Scheme::mult_scalar_core(Elem& a, double c) {
+    const double sf = P.sf[level_of(a)];
+    const i128 k = (i128)std::rint(c * sf);
+    mult_int_inplace(a, k);
+    a.deg += 1;
+    a.scale *= sf;
+}
+
+// OpenFHE LeveledSHECKKSRNS::AdjustLevelsAndDepthInPlace (FLEXIBLEAUTO), restated (A.8)
+void Scheme::adjust_pair(Elem& a, Elem& b) {
+    const int la = level_of(a), lb = level_of(b);
+    if (la == lb) {
+        if (a.deg < b.deg) mult_scalar_core(a, 1.0);
+        else if (b.deg < a.deg) mult_scalar_core(b, 1.0);
+        return;
+    }
+    Elem& lo = la < lb ? a : b;          // fewer dropped limbs: must be brought down
+    const Elem& hi = la < lb ? b : a;
+    const int l1 = level_of(lo), l2 = level_of(hi);
+    const double scf = P.sf[l1];
+    const double q1 = (double)P.q[lo.l - 1];
+    if (lo.deg == 2) {
+        if (hi.deg == 2) {
+            mult_scalar_core(lo, hi.scale / lo.scale * q1 / scf);
+            rescale_inplace(lo);
+            if (l1 + 1 < l2) level_reduce_inplace(lo, l2 - l1 - 1);
+            lo.scale = hi.scale; lo.deg = 2;
+        } else {
+            if (l1 + 1 == l2) {
+                rescale_inplace(lo);
+            } else {
+                const double scf2 = P.sf[l2 - 1] * P.sf[l2 - 1];
+                mult_scalar_core(lo, scf2 / lo.scale * q1 / scf);
+                rescale_inplace(lo);
+                if (l1 + 2 < l2) level_reduce_inplace(lo, l2 - l1 - 2);
+                rescale_inplace(lo);
+                lo.scale = hi.scale; lo.deg = 1;
+            }
+        }
+    } else {
+        if (hi.deg == 2) {
+            mult_scalar_core(lo, hi.scale / lo.scale / scf);
+            level_reduce_inplace(lo, l2 - l1);
+            lo.scale = hi.scale; lo.deg = 2;
+        } else {
+            const double scf2 = P.sf[l2 - 1] * P.sf[l2 - 1];
+            mult_scalar_core(lo, scf2 / lo.scale / scf);
+            if (l1 + 1 < l2) level_reduce_inplace(lo, l2 - l1 - 1);
+            rescale_inplace(lo);
+            lo.scale = hi.scale; lo.deg = 1;
+        }
+    }
+}
+
+void Scheme::adjust_pair_to_one(Elem& a, Elem& b) {
+    adjust_pair(a, b);
+    if (a.deg == 2) { rescale_inplace(a); rescale_inplace(b); }
+}
+
+// ---------------------------------------------------------------- leveled operations
+Elem Scheme::binary(const Elem& a_in, const Elem& b_in, bool subtract) {
+    if (a_in.ncomp == 1 && b_in.ncomp == 2 && !subtract) return binary(b_in, a_in, false);
+    if (a_in.ncomp < b_in.ncomp) throw std::invalid_argument("EvalSub(plaintext, ciphertext) is not supported");
+    Elem a = a_in, b = b_in;
+    adjust_pair(a, b);
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
+    const size_t pl = (size_t)a.l * P.N;
+    const LimbSel sel = sel_range(0, a.l);
+    if (b.ncomp == a.ncomp) {
+        launch_ew(eng.T, subtract ? EwOp::Sub : EwOp::Add, r.data(), a.data(), b.data(), sel, a.ncomp, 1, 0, 0, pl, eng.stream);
+    } else {
+        launch_ew(eng.T, subtract ? EwOp::Sub : EwOp::Add, r.data(), a.data(), b.data(), sel, 1, 1, 0, 0, 0, eng.stream);
+        eng.copy(r.data() + pl, a.data() + pl, pl * (a.ncomp - 1));
+    }
+    if (eng.ledger_on) eng.ledger.add("add", a.l, 48.0 * P.N * a.l);
+    return r;
+}
+Elem Scheme::add(const Elem& a, const Elem& b) { return binary(a, b, false); }
+Elem Scheme::sub(const Elem& a, const Elem& b) { return binary(a, b, true); }
+
+Elem Scheme::add_many(std::vector<Elem> v) {
+    if (v.empty()) throw std::invalid_argument("EvalAddMany: empty input");
+    const size_t n = v.size();
+    for (size_t j = 1; j < n; j *= 2)
+        for (size_t i = 0; i + j < n; i += 2 * j) v[i] = add(v[i], v[i + j]);
+    return v[0];
+}
+
+Elem Scheme::add_const(const Elem& a, double c) {
+    // constant polynomial round(c * scale): every evaluation-format entry of c0 receives the same residue
+    const i128 k = (i128)std::rint(c * a.scale);
+    Elem r = clone(a);
+    launch_add_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), eng.stream);
+    return r;
+}
+
+Elem Scheme::mult(const Elem& a_in, const Elem& b_in) {
+    if (a_in.ncomp == 1 && b_in.ncomp == 2) return mult(b_in, a_in);
+    if (a_in.ncomp != 2) throw std::invalid_argument("EvalMult: ciphertext expected");
+    Elem a = a_in, b = b_in;
+    adjust_pair_to_one(a, b);
+    Elem r = make(2, a.l, a.deg + b.deg, a.scale * b.scale, a.slots);
+    if (b.ncomp == 2) {
+        if (!mk_) throw std::runtime_error("EvalMult: relinearisation key missing");
+        eng.mul_relin(r.data(), a.data(), b.data(), a.l, mk_);
+    } else {
+        eng.ew(EwOp::Mul, r.data(), a.data(), b.data(), a.l, 2, true);
+        if (eng.ledger_on) eng.ledger.add("mul_plain", a.l, 40.0 * P.N * a.l);
+    }
+    return r;
+}
+
+Elem Scheme::mult_const(const Elem& a_in, double c) {
+    Elem a = a_in;
+    if (a.deg == 2) rescale_inplace(a);
+    mult_scalar_core(a, c);
+    return a;
+}
+
+Elem Scheme::mult_many(std::vector<Elem> v) {
+    const size_t n = v.size();
+    if (n == 0) throw std::invalid_argument("EvalMultMany: empty input");
+    if (n == 1) return v[0];
+    std::vector<Elem> m(n - 1);
+    size_t ctr = 0;
+    for (size_t i = 0; i < 2 * n - 2; i += 2) {
+        const Elem& x = i < n ? v[i] : m[i - n];
+        const Elem& y = i + 1 < n ? v[i + 1] : m[i + 1 - n];
+        m[ctr++] = mult(x, y);
+    }
+    return m.back();
+}
+
+Elem Scheme::apply_galois(const Elem& a, uint32_t g) {
+    if (a.ncomp != 2) throw std::invalid_argument("EvalAutomorphism: ciphertext expected");
+    auto it = gk_.find(g);
+    if (it == gk_.end()) throw std::runtime_error("EvalAutomorphism: no evaluation key for Galois element " + std::to_string(g));
+    Elem r = make(2, a.l, a.deg, a.scale, a.slots);
+    eng.rotate(r.data(), a.data(), a.l, g, it->second);
+    return r;
+}
+Elem Scheme::rotate(const Elem& a, int k) {
+    if (k == 0) return clone(a);
+    return apply_galois(a, P.galois_for_rotation(k));
+}
+Elem Scheme::conjugate(const Elem& a) { return apply_galois(a, P.galois_conj()); }
+
+}  // namespace flk

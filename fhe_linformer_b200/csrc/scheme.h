@@ -1,0 +1,145 @@
+// scheme.h -- CKKS scheme layer over the device engine: keys, encode/encrypt/decrypt, FLEXIBLEAUTO level and
+// scale management, polynomial evaluation and bootstrapping.  This is what stands behind the reference's
+// `CryptoContext<DCRTPoly> context` (FHEController.h:23); every public method names the OpenFHE call it replaces.
+#pragma once
+#include <complex>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "engine.h"
+
+namespace flk {
+
+using cplx = std::complex<double>;
+
+struct DevMem {   // stream-ordered HBM allocation, returned to the engine pool on destruction
+    Engine* eng;
+    u64* p;
+    size_t words;
+    DevMem(Engine* e, size_t w) : eng(e), p(e->alloc(w)), words(w) {}
+    ~DevMem() { try { eng->release(p); } catch (...) {} }
+    DevMem(const DevMem&) = delete;
+};
+using Mem = std::shared_ptr<DevMem>;
+
+// Ciphertext (ncomp = 2) or plaintext (ncomp = 1): ncomp polynomials of l limbs, evaluation format.
+struct Elem {
+    Mem mem;
+    int ncomp = 0;
+    int l = 0;          // active Q limbs; GetLevel() = L - l
+    int deg = 1;        // noiseScaleDeg
+    double scale = 0;   // scalingFactor
+    int slots = 0;
+    u64* data() const { return mem->p; }
+    bool valid() const { return (bool)mem; }
+};
+
+struct SplitMix {
+    u64 s;
+    explicit SplitMix(u64 seed) : s(seed) {}
+    u64 next() { u64 z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+    static u64 sub(u64 seed, u64 tag) { SplitMix t(seed + tag * 0x9E3779B97F4A7C15ull); return t.next(); }
+};
+
+struct BootPrecomp;   // bootstrap.cpp
+
+class Scheme {
+public:
+    explicit Scheme(const ParamSpec& spec, int device = -1);
+    ~Scheme();
+    Engine eng;
+    const Params& P;
+    int L() const { return P.L; }
+
+    // ---- keys (KeyGen F.cpp:47, EvalMultKeyGen :49, EvalRotateKeyGen :248, EvalBootstrapKeyGen :239) ----
+    void keygen(u64 seed);
+    void gen_mult_key();
+    void gen_rotation_key(int k);
+    void gen_galois_key(uint32_t g);
+    bool has_galois_key(uint32_t g) const { return gk_.count(g) != 0; }
+    void clear_rotation_keys();                       // ClearEvalAutomorphismKeys F.cpp:336
+    void clear_mult_key();                            // ClearEvalMultKeys F.cpp:342
+    size_t num_galois_keys() const { return gk_.size(); }
+    // raw import/export (device <-> host), used by save/load and by the parity tests
+    void export_sk(u64* out) const;                   // (L+K) limbs eval
+    void export_pk(u64* out) const;                   // [2][L][N]
+    void export_evk(uint32_t g, u64* out) const;      // g = 0: mult key
+    void import_keys(const u64* sk, const u64* pk);
+    void import_evk(uint32_t g, const u64* evk);
+
+    // ---- encode / encrypt / decrypt (MakeCKKSPackedPlaintext F.cpp:353, Encrypt :380, Decrypt :389) ----
+    Elem encode(const cplx* vals, int n, int level, int slots, int deg = 1);
+    Elem encode_real(const double* vals, int n, int level, int slots);
+    Elem encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg);   // explicit limb count / scale
+    Elem encrypt(const Elem& pt);
+    Elem encrypt_seeded(const Elem& pt, u64 seed);
+    void decrypt(const Elem& ct, cplx* out, int slots);
+    void decode(const Elem& pt, cplx* out, int slots);
+
+    // ---- leveled ops with FLEXIBLEAUTO bookkeeping ----
+    Elem add(const Elem& a, const Elem& b);           // EvalAdd F.cpp:410,414 (ct+ct, ct+pt)
+    Elem sub(const Elem& a, const Elem& b);
+    Elem add_many(std::vector<Elem> v);               // EvalAddMany F.cpp:418,1067
+    Elem add_const(const Elem& a, double c);
+    Elem mult(const Elem& a, const Elem& b);          // EvalMult F.cpp:427 (ct*pt), :431 (ct*ct + relinearisation)
+    Elem mult_const(const Elem& a, double c);         // EvalMult(ct, double)
+    Elem mult_many(std::vector<Elem> v);              // EvalMultMany F.cpp:1297
+    Elem square(const Elem& a) { return mult(a, a); }
+    Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
+    Elem conjugate(const Elem& a);
+    Elem apply_galois(const Elem& a, uint32_t g);
+    Elem clone(const Elem& a);                        // Ciphertext::Clone M:223
+    Elem rescaled(const Elem& a);                     // ModReduceInternal
+    void rescale_inplace(Elem& a);
+    void level_reduce_inplace(Elem& a, int levels);   // LevelReduceInternal
+    void mult_scalar_core(Elem& a, double c);         // EvalMultCoreInPlace(ct, double): x round(c * sf[level]), deg+1
+    void mult_int_inplace(Elem& a, i128 k);           // multiply by an integer, metadata unchanged
+    void adjust_pair(Elem& a, Elem& b);               // AdjustLevelsAndDepthInPlace
+    void adjust_pair_to_one(Elem& a, Elem& b);        // AdjustLevelsAndDepthToOneInPlace
+    void drop_to(Elem& a, int l);                     // keep the first l limbs
+
+    // ---- polynomial evaluation (EvalPoly F.cpp:1291, EvalChebyshevFunction F.cpp:486,1319-1335) ----
+    Elem eval_poly(const Elem& x, const std::vector<double>& coeffs);
+    Elem eval_chebyshev(const Elem& x, const std::vector<double>& coeffs, double a, double b);
+    static std::vector<double> chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree);
+
+    // ---- bootstrapping (EvalBootstrapSetup F.cpp:238,280; EvalBootstrapKeyGen :239; EvalBootstrap :445) ----
+    void bootstrap_setup(int budget_cts, int budget_stc, int slots);
+    void bootstrap_keygen(int slots);
+    std::vector<int> bootstrap_rotations(int slots);
+    Elem bootstrap(const Elem& ct);
+
+    // ---- serialisation (stands in for Serial::SerializeToFile / DeserializeFromFile, F.cpp:59-89,1360-1394) ----
+    Elem import_elem(const u64* host, int ncomp, int l, int deg, double scale, int slots);
+    void save_elem(const Elem& a, const char* path);
+    Elem load_elem(const char* path);
+    void save_keys(const char* path);
+    void load_keys(const char* path);
+
+    int level_of(const Elem& a) const { return P.L - a.l; }
+    u64 seed_counter = 0x5EEDull;
+
+private:
+    friend struct BootPrecomp;
+    Elem make(int ncomp, int l, int deg, double scale, int slots);
+    void keyswitch_gen(const u64* sk_old_dev, const u64* sk_new_dev, u64 seed, u64* evk_dev);
+    void sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSel& sel);
+    void uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel);
+    void encode_coeffs(const cplx* vals, int n, int slots, double scale, std::vector<i128>& co) const;
+    void coeffs_to_dev(u64* dst, const std::vector<i128>& co, int l);
+    ScalarSet scalar_set(i128 k, int l) const;
+    Elem binary(const Elem& a, const Elem& b, bool subtract);
+    // evaluation helpers
+    Elem cheby_ps(const Elem& x, const std::vector<double>& c);
+    Elem inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto);
+
+    u64 key_seed_ = 1;
+    u64* sk_ = nullptr;      // (L+K) limbs eval
+    u64* pk_ = nullptr;      // [2][L][N]
+    u64* mk_ = nullptr;      // relinearisation key
+    std::map<uint32_t, u64*> gk_;
+    std::map<int, std::shared_ptr<BootPrecomp>> boot_;
+};
+
+}  // namespace flk

@@ -78,6 +78,73 @@ int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse);
 int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev);
 int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev);
 
+/* ================= scheme level: what FHEController's methods call on `context` ================= */
+typedef struct fl_elem fl_elem;   /* ciphertext (2 polynomials) or plaintext (1), with level / noiseScaleDeg / scale / slots */
+typedef fl_elem fl_ct;            /* Ctxt = Ciphertext<DCRTPoly>   FHEController.h:20 */
+typedef fl_elem fl_pt;            /* Ptxt = Plaintext              FHEController.h:19 */
+
+/* keys: KeyGen F.cpp:47, EvalMultKeyGen F.cpp:49, EvalRotateKeyGen F.cpp:248 (seeded; DESIGN.md "Randomness") */
+int fl_keygen(fl_ctx* c, uint64_t seed);
+int fl_gen_mult_key(fl_ctx* c);
+int fl_gen_rot_keys(fl_ctx* c, const int* indices, int n);
+int fl_gen_conj_key(fl_ctx* c);
+int fl_keys_clear(fl_ctx* c, int kind);   /* 0: ClearEvalAutomorphismKeys F.cpp:336, 1: ClearEvalMultKeys F.cpp:342 */
+int fl_num_rot_keys(fl_ctx* c);
+/* raw key material <-> host (Serial::SerializeToFile / DeserializeFromFile of keys, F.cpp:59-89,192-220,251,291) */
+int fl_export_sk(fl_ctx* c, uint64_t* out /* (L+K) N */);
+int fl_export_pk(fl_ctx* c, uint64_t* out /* 2 L N */);
+int fl_export_evk(fl_ctx* c, uint32_t galois /* 0 = mult key */, uint64_t* out);
+int fl_import_keys(fl_ctx* c, const uint64_t* sk_or_null, const uint64_t* pk_or_null);
+int fl_import_evk(fl_ctx* c, uint32_t galois, const uint64_t* evk);
+int fl_keys_save(fl_ctx* c, const char* path);    /* one file: sk, pk, mult key, all automorphism keys */
+int fl_keys_load(fl_ctx* c, const char* path);
+
+/* MakeCKKSPackedPlaintext(vec, 1, level, nullptr, slots) F.cpp:353; im may be NULL */
+int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out);
+int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out);                         /* Encrypt F.cpp:380 */
+int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out);
+int fl_decrypt(fl_ctx* c, const fl_ct* a, double* re, double* im, int slots);   /* Decrypt + GetRealPackedValue F.cpp:389,402 */
+int fl_decode(fl_ctx* c, const fl_pt* p, double* re, double* im, int slots);
+
+int fl_add(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out);         /* EvalAdd F.cpp:410,414 */
+int fl_sub(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out);
+int fl_add_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out);                /* EvalAddMany F.cpp:418,1067 */
+int fl_add_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out);
+int fl_mul(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out);         /* EvalMult F.cpp:427,431 */
+int fl_mul_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out);
+int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out);                /* EvalMultMany F.cpp:1297 */
+int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out);                   /* EvalRotate F.cpp:435,833,843 */
+int fl_conjugate(fl_ctx* c, const fl_ct* a, fl_ct** out);
+int fl_rescale(fl_ctx* c, const fl_ct* a, fl_ct** out);
+int fl_eval_poly(fl_ctx* c, const fl_ct* a, const double* coeffs, int n, fl_ct** out);                       /* EvalPoly F.cpp:1291 */
+/* EvalChebyshevFunction(f, ct, a, b, degree) F.cpp:486,1319-1335: coefficients from fl_chebyshev_coefficients */
+int fl_eval_chebyshev(fl_ctx* c, const fl_ct* x, const double* coeffs, int n, double a, double b, fl_ct** out);
+int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree, double* out /* degree+1 */);
+
+/* EvalBootstrapSetup F.cpp:238,280, EvalBootstrapKeyGen F.cpp:239, EvalBootstrap F.cpp:445 */
+int fl_bootstrap_setup(fl_ctx* c, int budget_cts, int budget_stc, int slots);
+int fl_bootstrap_keygen(fl_ctx* c, int slots);
+int fl_bootstrap(fl_ctx* c, const fl_ct* a, fl_ct** out);
+
+/* Ciphertext / Plaintext accessors: GetLevel (M:231..), GetSlots F.cpp:448, Clone M:223 */
+int fl_elem_level(const fl_elem* a);
+int fl_elem_limbs(const fl_elem* a);
+int fl_elem_deg(const fl_elem* a);
+int fl_elem_slots(const fl_elem* a);
+int fl_elem_ncomp(const fl_elem* a);
+double fl_elem_scale(const fl_elem* a);
+int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out);
+void fl_elem_free(fl_elem* a);
+int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host /* ncomp * limbs * N */);
+int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int deg, double scale, int slots, fl_elem** out);
+int fl_elem_save(fl_ctx* c, const fl_elem* a, const char* path);    /* Serial::SerializeToFile(ct) F.cpp:1361 */
+int fl_elem_load(fl_ctx* c, const char* path, fl_elem** out);       /* Serial::DeserializeFromFile F.cpp:1386 */
+
+/* op ledger: algorithmic bytes per SURVEY.md section 8(d) */
+int fl_ledger_enable(fl_ctx* c, int on);
+int fl_ledger_reset(fl_ctx* c);
+int fl_ledger_dump(fl_ctx* c, char* buf, size_t cap);   /* "op@limbs count bytes\n" lines */
+
 #ifdef __cplusplus
 }
 #endif
