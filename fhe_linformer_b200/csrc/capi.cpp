@@ -153,7 +153,8 @@ int fl_export_pk(fl_ctx* c, uint64_t* out) { FL_TRY(c->sch->export_pk(out)) }
 int fl_export_evk(fl_ctx* c, uint32_t g, uint64_t* out) { FL_TRY(c->sch->export_evk(g, out)) }
 int fl_import_keys(fl_ctx* c, const uint64_t* sk, const uint64_t* pk) { FL_TRY(c->sch->import_keys(sk, pk)) }
 int fl_import_evk(fl_ctx* c, uint32_t g, const uint64_t* evk) { FL_TRY(c->sch->import_evk(g, evk)) }
-int fl_keys_save(fl_ctx* c, const char* path) { FL_TRY(c->sch->save_keys(path)) }
+int fl_keys_save(fl_ctx* c, const char* path) { FL_TRY(c->sch->save_keys(path, 15)) }
+int fl_keys_save_sel(fl_ctx* c, const char* path, int what) { FL_TRY(c->sch->save_keys(path, what)) }
 int fl_keys_load(fl_ctx* c, const char* path) { FL_TRY(c->sch->load_keys(path)) }
 
 int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out) {
@@ -186,6 +187,11 @@ int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out) {
     FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->mult_many(std::move(e))); })
 }
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotate(a->e, k))) }
+int fl_has_rot_key(fl_ctx* c, int k) { return c->sch->has_rotation_key(k) ? 1 : 0; }
+int fl_rotsum(fl_ctx* c, const fl_ct* a, int steps, int stride, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotsum(a->e, steps, stride))) }
+int fl_bootstrap_iter(fl_ctx* c, const fl_ct* a, int iterations, int precision, fl_ct** out) {
+    FL_TRY(*out = wrap(c->sch->bootstrap_iter(a->e, iterations, precision)))
+}
 int fl_conjugate(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->conjugate(a->e))) }
 int fl_rescale(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rescaled(a->e))) }
 int fl_eval_poly(fl_ctx* c, const fl_ct* a, const double* coeffs, int n, fl_ct** out) {

@@ -214,6 +214,15 @@ void Engine::rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) 
     if (ledger_on) ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
 }
 
+void Engine::rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) {
+    keyswitch(out, ct + (size_t)l * P.N, evk, l, ct, nullptr, g);
+    launch_ew(T, EwOp::Add, out, out, ct, sel_range(0, l), 2, 1, 0, 0, (size_t)l * P.N, stream);
+    if (ledger_on) {
+        ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
+        ledger.add("add", l, 48.0 * l * P.N);
+    }
+}
+
 void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) {
     const size_t pl = (size_t)l * P.N;
     u64* d = alloc(3 * pl);

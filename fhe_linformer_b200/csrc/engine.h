@@ -51,6 +51,7 @@ public:
     // out[2][l][N] = KeySwitch(c) (+add0 / +add1), optionally permuted by the automorphism map of g (0 = none)
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
+    void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
     // pieces exposed for parity tests
     void modup(u64* out_ext, const u64* c_eval, int l, int digit);     // out: (l+K) limbs eval

@@ -55,19 +55,25 @@ Elem Scheme::load_elem(const char* path) {
     return import_elem(h.data(), hd.ncomp, hd.l, hd.deg, hd.scale, hd.slots);
 }
 
-void Scheme::save_keys(const char* path) {
-    if (!sk_ || !pk_) throw std::runtime_error("save_keys: no key pair");
+// Key bundle = header + tagged records {tag, galois, words} + payload.  tag: 1 secret key, 2 public key, 3 evaluation key
+// (galois 0 = relinearisation key).  `what` selects what is written: 1 sk | 2 pk | 4 mult key | 8 automorphism keys,
+// mirroring the reference's separate secret-key / public-key / mult-keys / rot_* files (FHEController.cpp:59-89,251).
+void Scheme::save_keys(const char* path, int what) {
     FileHdr hd{};
     std::memcpy(hd.magic, "FLCK", 4);
-    hd.kind = 2; hd.logN = P.logN; hd.L = P.L; hd.K = P.K; hd.nkeys = (int)gk_.size() + (mk_ ? 1 : 0);
+    hd.kind = 2; hd.logN = P.logN; hd.L = P.L; hd.K = P.K;
+    std::vector<uint32_t> evks;
+    if ((what & 4) && mk_) evks.push_back(0);
+    if (what & 8) for (auto& kv : gk_) evks.push_back(kv.first);
+    if ((what & 3) && (!sk_ || !pk_)) throw std::runtime_error("save_keys: no key pair");
+    hd.nkeys = (int)evks.size() + ((what & 1) ? 1 : 0) + ((what & 2) ? 1 : 0);
     File f(path, "wb");
     f.write(&hd, sizeof hd);
     std::vector<u64> buf(std::max((size_t)2 * P.L * P.N, eng.evk_words()));
-    export_sk(buf.data()); f.write(buf.data(), (size_t)P.T * P.N * 8);
-    export_pk(buf.data()); f.write(buf.data(), (size_t)2 * P.L * P.N * 8);
-    auto put = [&](uint32_t g) { export_evk(g, buf.data()); f.write(&g, 4); f.write(buf.data(), eng.evk_words() * 8); };
-    if (mk_) put(0);
-    for (auto& kv : gk_) put(kv.first);
+    auto rec = [&](uint32_t tag, uint32_t g, size_t words) { uint64_t w = words; f.write(&tag, 4); f.write(&g, 4); f.write(&w, 8); f.write(buf.data(), words * 8); };
+    if (what & 1) { export_sk(buf.data()); rec(1, 0, (size_t)P.T * P.N); }
+    if (what & 2) { export_pk(buf.data()); rec(2, 0, (size_t)2 * P.L * P.N); }
+    for (uint32_t g : evks) { export_evk(g, buf.data()); rec(3, g, eng.evk_words()); }
 }
 
 void Scheme::load_keys(const char* path) {
@@ -75,15 +81,17 @@ void Scheme::load_keys(const char* path) {
     FileHdr hd{};
     f.read(&hd, sizeof hd);
     if (std::memcmp(hd.magic, "FLCK", 4) || hd.kind != 2 || hd.logN != P.logN || hd.L != P.L || hd.K != P.K) throw std::runtime_error("not a key file of this context");
-    std::vector<u64> buf(std::max((size_t)2 * P.L * P.N, eng.evk_words())), sk((size_t)P.T * P.N);
-    f.read(sk.data(), sk.size() * 8);
-    f.read(buf.data(), (size_t)2 * P.L * P.N * 8);
-    import_keys(sk.data(), buf.data());
+    std::vector<u64> buf;
     for (int i = 0; i < hd.nkeys; ++i) {
-        uint32_t g;
-        f.read(&g, 4);
-        f.read(buf.data(), eng.evk_words() * 8);
-        import_evk(g, buf.data());
+        uint32_t tag, g; uint64_t words;
+        f.read(&tag, 4); f.read(&g, 4); f.read(&words, 8);
+        if (words > std::max((size_t)2 * P.L * P.N, eng.evk_words())) throw std::runtime_error("corrupt key file");
+        buf.resize(words);
+        f.read(buf.data(), words * 8);
+        if (tag == 1 && words == (size_t)P.T * P.N) import_keys(buf.data(), nullptr);
+        else if (tag == 2 && words == (size_t)2 * P.L * P.N) import_keys(nullptr, buf.data());
+        else if (tag == 3 && words == eng.evk_words()) import_evk(g, buf.data());
+        else throw std::runtime_error("corrupt key record");
     }
 }
 

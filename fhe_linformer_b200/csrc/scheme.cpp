@@ -556,4 +556,32 @@ Elem Scheme::rotate(const Elem& a, int k) {
 }
 Elem Scheme::conjugate(const Elem& a) { return apply_galois(a, P.galois_conj()); }
 
+// r <- r + rot(r, stride 2^i), i = 0 .. steps-1: the rotate-and-add ladders of FHEController::rotsum / repeat
+// (F.cpp:829-867) as one call; the running ciphertext never leaves the device.
+Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
+    if (a.ncomp != 2) throw std::invalid_argument("rotsum: ciphertext expected");
+    Elem r = a;
+    for (int i = 0; i < steps; ++i) {
+        const uint32_t g = P.galois_for_rotation(stride * (1 << i));
+        auto it = gk_.find(g);
+        if (it == gk_.end()) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(stride * (1 << i)));
+        Elem nx = make(2, r.l, r.deg, r.scale, r.slots);
+        eng.rotate_add(nx.data(), r.data(), r.l, g, it->second);
+        r = nx;
+    }
+    return steps == 0 ? clone(a) : r;
+}
+
+// EvalBootstrap(ct, numIterations = 2, precision) (F.cpp:461): bootstrap, then bootstrap the 2^precision-amplified
+// residual error and subtract it
+Elem Scheme::bootstrap_iter(const Elem& ct, int iterations, int precision) {
+    Elem first = bootstrap(ct);
+    if (iterations <= 1) return first;
+    Elem err = sub(ct, first);                      // aligned to ct's (deeper) level by the FLEXIBLEAUTO adjustment
+    mult_int_inplace(err, (i128)1 << precision);    // integer scaling: no level is spent
+    Elem eb = bootstrap(err);
+    Elem fix = mult_const(eb, std::ldexp(1.0, -precision));
+    return add(first, fix);
+}
+
 }  // namespace flk

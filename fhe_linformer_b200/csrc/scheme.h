@@ -88,6 +88,7 @@ public:
     Elem square(const Elem& a) { return mult(a, a); }
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);
+    Elem rotsum(const Elem& a, int steps, int stride);   // FHEController::rotsum / repeat ladders F.cpp:829-867
     Elem apply_galois(const Elem& a, uint32_t g);
     Elem clone(const Elem& a);                        // Ciphertext::Clone M:223
     Elem rescaled(const Elem& a);                     // ModReduceInternal
@@ -109,12 +110,14 @@ public:
     void bootstrap_keygen(int slots);
     std::vector<int> bootstrap_rotations(int slots);
     Elem bootstrap(const Elem& ct);
+    Elem bootstrap_iter(const Elem& ct, int iterations, int precision);   // EvalBootstrap(c, 2, precision) F.cpp:461
+    bool has_rotation_key(int k) const { return k == 0 || gk_.count(P.galois_for_rotation(k)) != 0; }
 
     // ---- serialisation (stands in for Serial::SerializeToFile / DeserializeFromFile, F.cpp:59-89,1360-1394) ----
     Elem import_elem(const u64* host, int ncomp, int l, int deg, double scale, int slots);
     void save_elem(const Elem& a, const char* path);
     Elem load_elem(const char* path);
-    void save_keys(const char* path);
+    void save_keys(const char* path, int what = 15);
     void load_keys(const char* path);
 
     int level_of(const Elem& a) const { return P.L - a.l; }

@@ -146,6 +146,8 @@ public:
     unsigned long long key_seed = 20261018ULL;
     fl_ctx* native() const { return ctx_; }
     Ctxt chebyshev(const std::function<double(double)>& f, const Ctxt& c, double a, double b, int degree);
+    Ctxt ladder(const Ctxt& in, int slots, int stride);   // shared body of rotsum / rotsum_padded / repeat
+    Ctxt adopt(fl_elem* e) const;                          // take ownership of a raw C-ABI handle
 
 private:
     void create(int log_ring, int depth, int digits, int first_bits, int scale_bits);
@@ -153,7 +155,7 @@ private:
     Ctxt wrap(fl_elem* e) const { return std::make_shared<CiphertextImpl<DCRTPoly>>(ctx_, e); }
     Ptxt wrap_pt(fl_elem* e) const { return std::make_shared<PlaintextImpl>(ctx_, e); }
     Ptxt mask_plain(int kind, int a, int b, double value, int level);
-    string key_path(const string& name) const { return "../" + parameters_folder + "/" + name; }
+    string key_path(const string& name) const;
 
     fl_ctx* ctx_ = nullptr;
     fl_params params_{};

@@ -1,0 +1,246 @@
+// linformer.cpp -- encrypted forward pass of the 1-layer Linformer classifier (d = 128, k = 32 projected keys, FFN 512,
+// CLS-only attention) on FHEController.  Restates the circuit of the reference's src/main.cpp:145-475 stage by stage;
+// the line each step follows is cited as M:<line>.  Slot layouts are those of SURVEY.md section 3.3.
+#include "linformer.h"
+
+#include <cmath>
+#include <filesystem>
+
+namespace flh {
+
+namespace fs = std::filesystem;
+
+LinformerForward::LinformerForward(FHEController& controller, LinformerFiles files, bool verbose)
+    : fc_(controller), files_(std::move(files)), verbose_(verbose), t0_(utils::start_time()) {}
+
+double LinformerForward::scalar(const std::string& path) const {
+    std::ifstream in(path);
+    double v;
+    if (!(in >> v)) {   // M:30-38
+        std::cerr << "cannot read a value from " << path << std::endl;
+        std::exit(1);
+    }
+    return v;
+}
+
+void LinformerForward::checkpoint(const std::string& name, const Ctxt& c) {
+    if (sink_) sink_(name, fc_.decrypt_tovector(c, fc_.num_slots), (int)c->GetLevel());
+}
+
+void LinformerForward::lap(const std::string& name) {
+    fl_sync(fc_.native());
+    const double s = std::chrono::duration<double>(utils::clock_type::now() - t0_).count();
+    times_.push_back({name, s});
+    if (verbose_) std::cout << "The evaluation of " << name << " took: " << s << " seconds." << std::endl;
+    t0_ = utils::start_time();
+}
+
+std::vector<Ctxt> LinformerForward::load_expanded(const std::string& dir, const std::string& stem, int count) {
+    std::vector<Ctxt> rows;
+    rows.reserve(count);
+    for (int i = 0; i < count; ++i) rows.push_back(fc_.read_expanded_input(dir + "/" + stem + std::to_string(i) + ".txt"));
+    return rows;
+}
+
+// ---- attention for the CLS query only (M:176-215) -------------------------------------------------------------------------
+// K = X_E W_K, V = X_F W_V on the 32 client-projected rows; scores = softmax-like exp / sum over the 32 keys; context = scores V.
+Ctxt LinformerForward::attend_cls(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf) {
+    const Ptxt wq = fc_.read_plain_input(layer("selfAttn_WQ_weight_T.txt"));            // M:177
+    const Ptxt bq = fc_.read_plain_repeated_input(layer("selfAttn_WQ_bias.txt"));        // M:178
+    const Ptxt wk = fc_.read_plain_input(layer("selfAttn_WK_weight_T.txt"));            // M:179
+    const Ptxt bk = fc_.read_plain_repeated_input(layer("selfAttn_WK_bias.txt"));        // M:180
+
+    // The reference projects every row to a query (M:182) and then uses row 0 only (M:196).
+    const std::vector<Ctxt> queries = fc_.matmulRE(dead_work_ ? rows : std::vector<Ctxt>{rows[0]}, wq, bq);
+    const Ctxt keys = fc_.wrapUpRepeated(fc_.matmulRE(xe, wk, bk));                     // M:183-185
+    checkpoint("query_cls", queries[0]);
+    checkpoint("keys_wrapped", keys);
+
+    Ctxt scores = fc_.matmulScores(queries[0], keys);                                    // M:196
+    checkpoint("scores_raw", scores);
+    scores = fc_.eval_exp(scores, 32);                                                   // M:197
+    checkpoint("scores_exp", scores);
+    const Ctxt total = fc_.rotsum(scores, 32, 128);                                      // M:201
+    const Ctxt inverse = fc_.eval_inverse_naive(total, -1, 128);                         // M:203
+    checkpoint("scores_inverse", inverse);
+    scores = fc_.mult(scores, inverse);                                                  // M:205
+    checkpoint("scores_normalised", scores);
+    const std::vector<Ctxt> weights = fc_.unwrapExpanded(scores, 1);                     // M:207
+
+    const Ptxt wv = fc_.read_plain_input(layer("selfAttn_WV_weight_T.txt"));            // M:209
+    const Ptxt bv = fc_.read_plain_repeated_input(layer("selfAttn_WV_bias.txt"));        // M:210
+    const Ctxt values = fc_.wrapUpRepeated(fc_.matmulRE(xf, wv, bv));                   // M:212-213
+    checkpoint("values_wrapped", values);
+    return fc_.matmulRE(weights, values, 128, 128)[0];                                   // M:215-216
+}
+
+// ---- W_O, bias and residual (M:217-239): only row 0 carries attention output, the other rows are encryptions of zero ------
+std::vector<Ctxt> LinformerForward::self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows) {
+    const int level = (int)cls_context->GetLevel();
+    std::vector<Ctxt> out;
+    out.reserve(rows.size());
+    out.push_back(cls_context);
+    const Ctxt zero = fc_.encrypt_ptxt(fc_.encode(0, level, 0));                         // M:220-221
+    for (size_t i = 1; i < rows.size(); ++i) out.push_back(zero->Clone());               // M:222-224
+    const Ptxt wo = fc_.read_plain_input(layer("selfAttn_WO_weight.txt"), level);        // M:231
+    const Ptxt bo = fc_.read_plain_expanded_input(layer("selfAttn_WO_bias.txt"), level + 1);   // M:232
+    if (dead_work_) {
+        out = fc_.matmulCR(out, wo, nullptr);                                            // M:235
+    } else {
+        // W_O applied to an encryption of zero is an encryption of zero at the product's level: do one and share it
+        std::vector<Ctxt> two = fc_.matmulCR({out[0], out.size() > 1 ? out[1] : out[0]}, wo, nullptr);
+        for (size_t i = 0; i < out.size(); ++i) out[i] = i == 0 ? two[0] : two[1];
+    }
+    out[0] = fc_.add(out[0], bo);                                                        // M:236
+    for (size_t i = 0; i < out.size(); ++i) out[i] = fc_.add(out[i], rows[i]);           // M:237-239
+    return out;
+}
+
+// ---- rows -> two wrapped ciphertexts (first 128 rows, the rest), the affine stand-in for LayerNorm, optional bootstrap ----
+// M:292-320 (affine1 + bootstrap) and M:382-414 (affine2, no bootstrap; the caller adds the residual in between)
+std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh) {
+    if (rows.size() <= 128 || rows.size() > 256) throw std::invalid_argument("the circuit packs rows as 128 + (S - 128): need 129 <= S <= 256");
+    const std::vector<Ctxt> first(rows.begin(), rows.begin() + 128), rest(rows.begin() + 128, rows.end());
+    Ctxt w0 = fc_.wrapUpExpanded(first), w1 = fc_.wrapUpExpanded(rest);                  // M:307-308 / M:392-393
+    if (!refresh) return {w0, w1};
+    const double s = (double)rows.size();
+    const double f = scalar(layer("ffn_" + which + "_c0.txt")) + scalar(layer("ffn_" + which + "_c1.txt")) / std::sqrt(s) +
+                     scalar(layer("ffn_" + which + "_c2.txt")) / s;                      // M:292-297
+    const Ptxt a = fc_.read_plain_repeated_input(layer("ffn_" + which + "_a.txt"), (int)w0->GetLevel(), f);       // M:311
+    const Ptxt b = fc_.read_plain_repeated_input(layer("ffn_" + which + "_b.txt"), (int)w0->GetLevel() + 1, f);   // M:312
+    w0 = fc_.add(fc_.mult(w0, a), b);                                                    // M:314-315
+    w1 = fc_.add(fc_.mult(w1, a), b);                                                    // M:316-317
+    checkpoint(which + "_0", w0);
+    checkpoint(which + "_1", w1);
+    return {fc_.bootstrap(w0), fc_.bootstrap(w1)};                                       // M:319-320
+}
+
+// ---- FFN: 128 -> 512 (scaled by 1/8 so GELU's argument lies in [-1, 1]), GELU, bootstrap, 512 -> 128 (M:325-380) ----------
+std::vector<Ctxt> LinformerForward::feed_forward(const Ctxt& half0, const Ctxt& half1, int rows) {
+    const double gelu_scale = 1.0 / 8.0;                                                 // M:334
+    std::vector<Ctxt> x0 = fc_.unwrapExpanded(half0, 128);                               // M:325
+    std::vector<Ctxt> x1 = fc_.unwrapExpanded(half1, rows - 128);                        // M:326
+    checkpoint("self_output_row0", x0[0]);
+    lap("Self-Output");
+
+    const int level = (int)half0->GetLevel();
+    std::vector<Ptxt> w0;
+    for (int b = 0; b < 4; ++b) w0.push_back(fc_.read_plain_input(w("ffn_W0_transposed_block_" + std::to_string(b) + ".txt"), level, gelu_scale));   // M:338-341
+    const Ptxt b0 = fc_.read_plain_input(layer("ffn_Wffn_0_bias.txt"), level + 1, gelu_scale);   // M:345
+    std::vector<Ctxt> hidden = fc_.matmulRElarge(x0, w0, b0);                            // M:347
+    std::vector<Ctxt> hidden1 = fc_.matmulRElarge(x1, w0, b0);                           // M:348
+    hidden.insert(hidden.end(), hidden1.begin(), hidden1.end());                         // M:351-354
+    checkpoint("hidden_row0", hidden[0]);
+
+    std::vector<Ctxt> containers = fc_.generate_containers(hidden, nullptr);             // M:358
+    for (size_t i = 0; i < containers.size(); ++i) {
+        if (i == 0) checkpoint("container0_pre_gelu", containers[0]);
+        containers[i] = fc_.bootstrap(fc_.eval_gelu_function(containers[i], -1, 1, gelu_scale, 119));   // M:362-363
+    }
+    checkpoint("container0_gelu", containers[0]);
+    std::vector<std::vector<Ctxt>> quads = fc_.unwrapRepeatedLarge(containers, rows);    // M:366
+    lap("Intermediate");
+
+    const int l2 = (int)quads[0][0]->GetLevel();
+    std::vector<Ptxt> w2;
+    for (int b = 0; b < 4; ++b) w2.push_back(fc_.read_plain_input(w("ffn_W2_block_" + std::to_string(b) + ".txt"), l2));   // M:373-376
+    const Ptxt b2 = fc_.read_plain_expanded_input(layer("ffn_Wffn_2_bias.txt"), l2 + 1); // M:378
+    return fc_.matmulCRlarge(quads, w2, b2);                                             // M:380
+}
+
+Ctxt LinformerForward::encoder() {
+    t0_ = utils::start_time();
+    int found = 0;                                                                       // M:147-154: one row per file, plus CLS
+    for (const auto& entry : fs::directory_iterator(files_.tokens))
+        if (entry.path().filename().string().rfind("input_", 0) == 0) ++found;
+    if (token_limit_ > 0 && found > token_limit_) found = token_limit_;
+    tokens_ = found + 1;
+    if (verbose_) std::cout << tokens_ << " inputs found!" << std::endl << std::endl;
+
+    const std::vector<Ctxt> xe = load_expanded(files_.input, "XE_", 32);                 // M:159-162
+    const std::vector<Ctxt> xf = load_expanded(files_.input, "XF_", 32);                 // M:164-167
+    std::vector<Ctxt> rows;
+    rows.push_back(fc_.read_expanded_input(w("cls_token.txt")));                         // M:170
+    const std::vector<Ctxt> embedded = load_expanded(files_.tokens, "input_", found);    // M:171-173
+    rows.insert(rows.end(), embedded.begin(), embedded.end());
+    lap("Encrypt");
+
+    const Ctxt context = attend_cls(rows, xe, xf);
+    checkpoint("attention_cls", context);
+    lap("Self-Attention");
+
+    const std::vector<Ctxt> attended = self_output(context, rows);
+    checkpoint("attended_row0", attended[0]);
+    checkpoint("attended_row1", attended[1]);
+    auto [half0, half1] = affine_and_refresh(attended, "affine1", true);
+    checkpoint("affine1_refreshed_0", half0);
+    const Ctxt residual0 = half0->Clone(), residual1 = half1->Clone();                   // M:322-323
+
+    const std::vector<Ctxt> ffn = feed_forward(half0, half1, tokens_);
+    checkpoint("ffn_row0", ffn[0]);
+    auto [o0, o1] = affine_and_refresh(ffn, "affine2", false);
+    o0 = fc_.add(o0, residual0);                                                         // M:395
+    o1 = fc_.add(o1, residual1);                                                         // M:396
+    const double s = (double)ffn.size();
+    const double f2 = scalar(layer("ffn_affine2_c0.txt")) + scalar(layer("ffn_affine2_c1.txt")) / std::sqrt(s) + scalar(layer("ffn_affine2_c2.txt")) / s;   // M:398-403
+    const Ptxt a2 = fc_.read_plain_repeated_input(layer("ffn_affine2_a.txt"), (int)o0->GetLevel(), f2);       // M:407
+    const Ptxt b2 = fc_.read_plain_repeated_input(layer("ffn_affine2_b.txt"), (int)o1->GetLevel() + 1, f2);   // M:408
+    o0 = fc_.add(fc_.mult(o0, a2), b2);                                                  // M:410,413
+    o1 = fc_.add(fc_.mult(o1, a2), b2);                                                  // M:411,414
+    checkpoint("affine2_0", o0);
+    std::vector<Ctxt> final0 = fc_.unwrapExpanded(o0, dead_work_ ? 128 : 1);             // M:416 (only element 0 is used)
+    if (dead_work_) (void)fc_.unwrapExpanded(o1, tokens_ - 128);                         // M:417
+    checkpoint("encoder_out", final0[0]);
+    lap("Output");
+    return final0[0];                                                                    // M:424 (the caller may save() it, M:422)
+}
+
+Ctxt LinformerForward::pooler(const Ctxt& encoded) {
+    const double tanh_scale = 1.0 / 50;                                                  // M:430
+    const int level = (int)encoded->GetLevel();
+    const Ptxt weight = fc_.read_plain_input(w("pooler_dense_weight_T.txt"), level, tanh_scale);          // M:432
+    const Ptxt bias = fc_.read_plain_repeated_input(w("pooler_dense_bias.txt"), level + 1, tanh_scale);   // M:433
+    Ctxt y = fc_.add(fc_.rotsum(fc_.mult(encoded, weight), 128, 128), bias);             // M:435-439
+    checkpoint("pooler_pre_tanh", y);
+    y = fc_.eval_tanh_function(fc_.bootstrap(y), -1, 1, tanh_scale, 300);                // M:441-445
+    checkpoint("pooler_out", y);
+    lap("Pooler");
+    return y;
+}
+
+Ctxt LinformerForward::classifier(const Ctxt& pooled) {
+    const int level = (int)pooled->GetLevel();
+    const Ptxt weight = fc_.read_plain_input(w("fcLinear_0_weight.txt"), level);         // M:454
+    const Ptxt bias = fc_.read_plain_expanded_input(w("fcLinear_0_bias.txt"), level);    // M:455
+    Ctxt y = fc_.add(fc_.rotsum(fc_.mult(pooled, weight), 128, 1), bias);                // M:457-461
+    std::vector<double> pick((size_t)fc_.num_slots, 0.0);                                // M:463-470: keep slots 128 i, i < 20
+    for (int i = 0; i < 20; ++i) pick[(size_t)i * 128] = 1;
+    y = fc_.mult(y, fc_.encrypt(pick, (int)y->GetLevel()));                              // M:472 (ciphertext mask, as in main.cpp)
+    lap("Classifier");
+    return y;
+}
+
+std::vector<double> LinformerForward::logits(const Ctxt& classified, int classes) {
+    const std::vector<double> slots = fc_.decrypt_tovector(classified, fc_.num_slots);   // M:115
+    std::vector<double> out((size_t)classes);
+    for (int i = 0; i < classes; ++i) out[i] = slots[(size_t)i * 128];                   // M:120-123
+    return out;
+}
+
+std::vector<double> LinformerForward::run(int classes) {
+    times_.clear();
+    return logits(classifier(pooler(encoder())), classes);
+}
+
+int LinformerForward::argmax_softmax(const std::vector<double>& z, std::vector<double>* prob) {
+    const double top = *std::max_element(z.begin(), z.end());
+    std::vector<double> p(z.size());
+    double sum = 0;
+    for (size_t i = 0; i < z.size(); ++i) sum += (p[i] = std::exp(z[i] - top));
+    for (double& v : p) v /= sum;
+    const int best = (int)(std::max_element(p.begin(), p.end()) - p.begin());
+    if (prob) *prob = std::move(p);
+    return best;
+}
+
+}  // namespace flh

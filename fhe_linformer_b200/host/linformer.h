@@ -1,0 +1,72 @@
+// linformer.h -- the encrypted Linformer forward pass (encoder layer -> pooler -> classifier) driven through
+// FHEController, i.e. the circuit of the reference's src/main.cpp:145-475, organised as stages so that tests and the
+// bench can time and checkpoint each of them.  Reads the same text files, in the same layouts, as the reference.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "FHEController.h"
+
+namespace flh {
+
+struct LinformerFiles {
+    std::string weights;   // the reference's ../weights-20NG
+    std::string input;     // ../input          (XE_0..31.txt, XF_0..31.txt: client-side Linformer projections)
+    std::string tokens;    // <input_folder>    (input_0.txt .. input_{S-2}.txt: token embeddings)
+};
+
+struct StageTime {
+    std::string name;
+    double seconds;
+};
+
+class LinformerForward {
+public:
+    LinformerForward(FHEController& controller, LinformerFiles files, bool verbose = false);
+
+    // decrypted slots of named intermediate ciphertexts are handed to `sink` (tests compare them with the slot simulator);
+    // the reference prints a few of the same intermediates (main.cpp:198-199,227,329,369,420,448)
+    void set_checkpoint_sink(std::function<void(const std::string&, const std::vector<double>&, int level)> sink) { sink_ = std::move(sink); }
+    void set_token_limit(int n) { token_limit_ = n; }   // use only the first n token files (0 = all)
+    // true (default): issue every operation main.cpp issues, including the ones whose results it never reads (queries of
+    // rows 1.., W_O on the S-1 zero rows, the final unwrap of all rows).  false: skip those; the logits are identical.
+    void set_dead_work(bool on) { dead_work_ = on; }
+
+    Ctxt encoder();                       // main.cpp:145-425
+    Ctxt pooler(const Ctxt& encoded);     // main.cpp:427-451
+    Ctxt classifier(const Ctxt& pooled);  // main.cpp:453-475
+    std::vector<double> logits(const Ctxt& classified, int classes = 20);   // main.cpp:115-123: slot 128 i holds class i
+    std::vector<double> run(int classes = 20);                               // the three stages + decrypt
+    static int argmax_softmax(const std::vector<double>& logits, std::vector<double>* prob = nullptr);   // main.cpp:125-142
+
+    const std::vector<StageTime>& timings() const { return times_; }
+    int tokens() const { return tokens_; }
+
+private:
+    struct Attention;   // K/V side of the CLS-only attention
+    std::string w(const std::string& name) const { return files_.weights + "/" + name; }
+    std::string layer(const std::string& name) const { return w("linformer_transformerLayers_transformer0_" + name); }
+    double scalar(const std::string& path) const;
+    void checkpoint(const std::string& name, const Ctxt& c);
+    void lap(const std::string& name);
+    std::vector<Ctxt> load_expanded(const std::string& dir, const std::string& stem, int count);
+
+    Ctxt attend_cls(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
+    std::vector<Ctxt> self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows);
+    std::pair<Ctxt, Ctxt> affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh);
+    std::vector<Ctxt> feed_forward(const Ctxt& half0, const Ctxt& half1, int rows);
+
+    FHEController& fc_;
+    LinformerFiles files_;
+    bool verbose_;
+    int token_limit_ = 0;
+    bool dead_work_ = true;
+    int tokens_ = 0;
+    std::function<void(const std::string&, const std::vector<double>&, int)> sink_;
+    std::vector<StageTime> times_;
+    utils::time_point t0_;
+};
+
+}  // namespace flh

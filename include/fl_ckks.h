@@ -97,7 +97,9 @@ int fl_export_evk(fl_ctx* c, uint32_t galois /* 0 = mult key */, uint64_t* out);
 int fl_import_keys(fl_ctx* c, const uint64_t* sk_or_null, const uint64_t* pk_or_null);
 int fl_import_evk(fl_ctx* c, uint32_t galois, const uint64_t* evk);
 int fl_keys_save(fl_ctx* c, const char* path);    /* one file: sk, pk, mult key, all automorphism keys */
-int fl_keys_load(fl_ctx* c, const char* path);
+/* what: 1 secret-key.txt | 2 public-key.txt | 4 mult-keys.txt | 8 rot_<name> (the four files of F.cpp:59-89,251) */
+int fl_keys_save_sel(fl_ctx* c, const char* path, int what);
+int fl_keys_load(fl_ctx* c, const char* path);   /* merges whatever records the file holds */
 
 /* MakeCKKSPackedPlaintext(vec, 1, level, nullptr, slots) F.cpp:353; im may be NULL */
 int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out);
@@ -114,6 +116,9 @@ int fl_mul(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out);         
 int fl_mul_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out);
 int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out);                /* EvalMultMany F.cpp:1297 */
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out);                   /* EvalRotate F.cpp:435,833,843 */
+int fl_has_rot_key(fl_ctx* c, int k);                                           /* is the EvalRotateKeyGen key for index k resident? */
+/* out = sum_{t < 2^steps} rot(a, t * stride): FHEController::rotsum / rotsum_padded / repeat, F.cpp:829-867 */
+int fl_rotsum(fl_ctx* c, const fl_ct* a, int steps, int stride, fl_ct** out);
 int fl_conjugate(fl_ctx* c, const fl_ct* a, fl_ct** out);
 int fl_rescale(fl_ctx* c, const fl_ct* a, fl_ct** out);
 int fl_eval_poly(fl_ctx* c, const fl_ct* a, const double* coeffs, int n, fl_ct** out);                       /* EvalPoly F.cpp:1291 */
@@ -125,6 +130,7 @@ int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, 
 int fl_bootstrap_setup(fl_ctx* c, int budget_cts, int budget_stc, int slots);
 int fl_bootstrap_keygen(fl_ctx* c, int slots);
 int fl_bootstrap(fl_ctx* c, const fl_ct* a, fl_ct** out);
+int fl_bootstrap_iter(fl_ctx* c, const fl_ct* a, int iterations, int precision, fl_ct** out);   /* EvalBootstrap(c, 2, precision) F.cpp:461 */
 
 /* Ciphertext / Plaintext accessors: GetLevel (M:231..), GetSlots F.cpp:448, Clone M:223 */
 int fl_elem_level(const fl_elem* a);

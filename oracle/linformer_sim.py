@@ -1,0 +1,278 @@
+"""TEST INFRASTRUCTURE -- slot-level and matrix-level float restatement of the reference's encrypted circuit.
+
+Only tests/, __graft_entry__.smoke() and bench.py's checker may import this; the product never does.
+
+Two independent restatements of what /root/reference/src/main.cpp:145-475 computes through
+/root/reference/src/FHEController.cpp:829-1336, both in plain numpy float64:
+
+* `SlotSim`     -- every FHEController method on a vector of 16384 plaintext slots: rotate = cyclic shift, mult = slot-wise
+                   product, Chebyshev / Taylor evaluation in double.  Mirrors the reference method by method (file:line
+                   cited per method), so a decrypted ciphertext of the engine must equal the simulated slots up to CKKS noise.
+* `float_forward` -- the same network as ordinary linear algebra on 128-vectors (what the slots mean), used to check the
+                   simulator itself.
+
+parity unpinned: the reference holds no golden vectors for this path; the two restatements are
+checked against each other (tests/test_linformer_sim.py).
+
+OpenFHE's EvalChebyshevFunction is restated from its published algorithm: coefficients
+c_i = 2/(n) sum_k f(x_k) cos(pi i (k + 1/2) / n) at the n = degree + 1 Chebyshev nodes of [a, b], series c_0/2 + sum c_i T_i(u).
+"""
+import math
+
+import numpy as np
+
+SLOTS = 1 << 14
+
+
+def chebyshev_coefficients(f, a, b, degree):
+    n = degree + 1
+    k = np.arange(n)
+    theta = math.pi * (k + 0.5) / n
+    fx = np.array([f(0.5 * (b - a) * math.cos(t) + 0.5 * (b + a)) for t in theta])
+    return np.array([2.0 / n * float(np.sum(fx * np.cos(i * theta))) for i in range(n)])
+
+
+def chebyshev_eval(coeffs, a, b, x):
+    u = (2.0 * np.asarray(x, np.float64) - (a + b)) / (b - a)
+    c = np.array(coeffs, np.float64)
+    c[0] *= 0.5
+    return np.polynomial.chebyshev.chebval(u, c)
+
+
+class SlotSim:
+    """FHEController on plaintext slot vectors (np.float64[16384])."""
+
+    def __init__(self, slots=SLOTS):
+        self.n = slots
+
+    # -- primitives (F.cpp:409-436)
+    def rotate(self, v, k): return np.roll(v, -k)
+    def add(self, a, b): return a + b
+    def mult(self, a, b): return a * b
+
+    # -- layouts of the readers (F.cpp:515-698)
+    def plain(self, values, scale=1.0):
+        v = np.zeros(self.n); a = np.asarray(values, np.float64).ravel(); v[:a.size] = a * scale; return v
+    def repeated(self, vec, scale=1.0): return np.tile(np.asarray(vec, np.float64)[:128], 128) * scale
+    def expanded(self, vec, scale=1.0, filled=128):
+        v = np.zeros((128, 128)); v[:, :filled] = (np.asarray(vec, np.float64)[:128] * scale)[:, None]; return v.ravel()
+
+    # -- ladders (F.cpp:829-867)
+    def rotsum(self, v, slots, padding):
+        r = v.copy()
+        for i in range(int(math.ceil(math.log2(slots)))):
+            r = r + self.rotate(r, padding * (1 << i))
+        return r
+    def rotsum_padded(self, v, slots): return self.rotsum(v, slots, slots)
+    def repeat(self, v, slots, padding=1): return self.rotsum(v, slots, -padding)
+
+    # -- masks (F.cpp:1207-1286)
+    def _idx(self): return np.arange(self.n)
+    def mask_block(self, v, lo, hi, value=1.0): i = self._idx(); return v * np.where((i >= lo) & (i < hi), value, 0.0)
+    def mask_heads(self, v, value=1.0): return v * np.where(self._idx() % 64 == 0, value, 0.0)
+    def mask_heads_128(self, v, value=1.0): return v * np.where(self._idx() % 128 == 0, value, 0.0)
+    def mask_mod_n(self, v, n, padding=0): return v * np.where(self._idx() % n == padding, 1.0, 0.0)
+    def mask_first_n(self, v, n, value=1.0): return v * np.where(self._idx() < n, value, 0.0)
+
+    # -- matrix products (F.cpp:869-1058)
+    def matmulRE(self, rows, weight, bias=None, row_size=128, padding=128):
+        return [self.rotsum(r * weight, row_size, padding) + (0 if bias is None else bias) for r in rows]
+    def matmulRElarge(self, rows, weights, bias, mask_value=1.0):
+        out = []
+        for r in rows:
+            acc = None
+            for j in range(len(weights) - 1, -1, -1):
+                part = self.mask_first_n(self.rotsum(r * weights[j], 128, 128), 128, mask_value)
+                acc = part if acc is None else self.rotate(self.rotate(acc, -64), -64) + part
+            out.append(acc + bias)
+        return out
+    def matmulCR(self, rows, weight, bias=None):
+        return [self.rotsum(r * weight, 128, 1) + (0 if bias is None else bias) for r in rows]
+    def matmulCR_ct(self, rows, matrix): return [self.rotsum(r * matrix, 64, 1) for r in rows]
+    def matmulCR_128(self, rows, matrix): return [self.rotsum(r * matrix, 128, 1) for r in rows]
+    def matmulCRlarge(self, quads, weights, bias=None):
+        return [self.rotsum(sum(q[b] * weights[b] for b in range(4)), 128, 1) + (0 if bias is None else bias) for q in quads]
+    def matmulScores(self, queries, key):
+        scale = (1 / 8.0) * (1 / 8.0)
+        sc = self.matmulCR_128(queries, key)
+        if len(sc) == 1:
+            return self.mask_heads_128(sc[0], scale)
+        packed = self.rotate(self.mask_heads_128(sc[-1], scale), -1)
+        for i in range(len(sc) - 2, -1, -1):
+            packed = packed + self.mask_heads_128(sc[i], scale)
+            if i > 0:
+                packed = self.rotate(packed, -1)
+        return packed
+
+    # -- layout conversions (F.cpp:1060-1205)
+    def wrapUpRepeated(self, vectors): return sum(self.mask_block(v, 128 * i, 128 * (i + 1)) for i, v in enumerate(vectors))
+    def wrapUpExpanded(self, vectors):
+        acc = self.mask_mod_n(vectors[-1], 128)
+        if len(vectors) > 1:
+            acc = self.rotate(acc, -1)
+        for i in range(len(vectors) - 2, -1, -1):
+            acc = acc + self.mask_mod_n(vectors[i], 128)
+            if i > 0:
+                acc = self.rotate(acc, -1)
+        return acc
+    def unwrapExpanded(self, c, count):
+        out = []
+        for t in range(count):
+            out.append(self.repeat(self.mask_mod_n(c, 128, 0), 128))
+            if t < count - 1:
+                c = self.rotate(c, 1)
+        return out
+    def unwrapScoresExpanded(self, c, count):
+        out = []
+        for t in range(count):
+            lo = self.repeat(self.mask_mod_n(c, 128, 0), 64); hi = self.repeat(self.mask_mod_n(c, 128, 64), 64)
+            if t < count - 1:
+                c = self.rotate(c, 1)
+            out.append(lo + hi)
+        return out
+    def unwrap_512_in_4_128(self, c, index):
+        return [self.repeat(self.mask_block(c, index * 512 + 128 * b, index * 512 + 128 * (b + 1)), 128, -128) for b in range(4)]
+    def unwrapRepeatedLarge(self, containers, count):
+        out = []
+        for i, c in enumerate(containers):
+            for j in range(min(32, count - 32 * i)):
+                out.append(self.unwrap_512_in_4_128(c, j))
+        return out
+    def wrap_containers(self, cs, count):
+        acc = cs[0]
+        for i in range(1, count):
+            acc = self.rotate(acc, -512) + cs[i]
+        return acc
+    def generate_containers(self, inputs, bias=None):
+        out = []
+        for first in range(0, len(inputs), 32):
+            group = inputs[first:first + 32][::-1]
+            packed = self.wrap_containers(group, len(group))
+            out.append(packed if bias is None else packed + bias)
+        return out
+
+    # -- activations (F.cpp:1289-1336)
+    def eval_exp(self, v, inputs):
+        t = sum(c * v ** i for i, c in enumerate([1, 1, 1 / 2., 1 / 6., 1 / 24., 1 / 120., 1 / 720.]))
+        i = self._idx()
+        return t ** 8 + np.where((i % 128 < inputs) & (i < 128 * inputs), 0.0, -1.0)
+    def chebyshev(self, f, v, a, b, degree): return chebyshev_eval(chebyshev_coefficients(f, a, b, degree), a, b, v)
+    def eval_inverse_naive(self, v, lo, hi): return self.chebyshev(lambda x: 1 / x, v, lo, hi, 119)
+    def eval_inverse_naive_2(self, v, lo, hi, mult): return self.chebyshev(lambda x: mult / x, v, lo, hi, 200)
+    def eval_inverse(self, v, lo, hi):
+        middle = (hi - lo) / 2
+        return self.chebyshev(lambda x: 1 / ((x * 9895) + 9995), (v + (-middle - lo)) * (1 / middle), -1, 1, 200)
+    def eval_gelu_function(self, v, lo, hi, mult, degree):
+        return self.chebyshev(lambda x: 0.5 * (x / mult) * (1 + math.erf((x / mult) / 1.41421356237)), v, lo, hi, degree)
+    def eval_tanh_function(self, v, lo, hi, mult, degree): return self.chebyshev(lambda x: math.tanh(x / mult), v, lo, hi, degree)
+    def relu(self, v, scale, degree=119): return self.chebyshev(lambda x: 0.0 if x < 0 else x / scale, v, -1, 1, degree)
+
+
+def sim_forward(model, sample, checkpoints=None):
+    """The circuit of main.cpp:145-475 on plaintext slots.  Returns the 20 logits; fills `checkpoints` (name -> slots) with the
+    same intermediates host/linformer.cpp hands to its checkpoint sink.  Bootstraps are the identity here."""
+    s = SlotSim()
+    cp = checkpoints if checkpoints is not None else {}
+    rows = [s.expanded(model["cls_token"])] + [s.expanded(t) for t in sample["tokens"]]
+    xe = [s.expanded(r) for r in sample["XE"]]
+    xf = [s.expanded(r) for r in sample["XF"]]
+    S = len(rows)
+    # attention for the CLS query (M:176-215)
+    q = s.matmulRE(rows[:1], s.plain(model["WQ_T"]), s.repeated(model["bQ"]))
+    keys = s.wrapUpRepeated(s.matmulRE(xe, s.plain(model["WK_T"]), s.repeated(model["bK"])))
+    cp["query_cls"], cp["keys_wrapped"] = q[0], keys
+    scores = s.matmulScores(q[:1], keys)
+    cp["scores_raw"] = scores
+    scores = s.eval_exp(scores, 32)
+    cp["scores_exp"] = scores
+    inv = s.eval_inverse_naive(s.rotsum(scores, 32, 128), -1, 128)
+    cp["scores_inverse"] = inv
+    scores = scores * inv
+    cp["scores_normalised"] = scores
+    weights = s.unwrapExpanded(scores, 1)
+    values = s.wrapUpRepeated(s.matmulRE(xf, s.plain(model["WV_T"]), s.repeated(model["bV"])))
+    cp["values_wrapped"] = values
+    context = s.matmulRE(weights, values, None, 128, 128)[0]
+    cp["attention_cls"] = context
+    # W_O, bias, residual (M:217-239)
+    out = s.matmulCR([context] + [np.zeros(s.n)] * (S - 1), s.plain(model["WO"]))
+    out[0] = out[0] + s.expanded(model["bO"])
+    out = [o + r for o, r in zip(out, rows)]
+    cp["attended_row0"], cp["attended_row1"] = out[0], out[1]
+    # affine1 (+ bootstrap) (M:292-320)
+    f1 = model["c1"][0] + model["c1"][1] / math.sqrt(S) + model["c1"][2] / S
+    halves = [s.wrapUpExpanded(out[:128]), s.wrapUpExpanded(out[128:])]
+    halves = [h * s.repeated(model["a1"], f1) + s.repeated(model["b1"], f1) for h in halves]
+    cp["affine1_0"], cp["affine1_1"] = halves
+    cp["affine1_refreshed_0"] = halves[0]
+    # FFN (M:325-380)
+    x = s.unwrapExpanded(halves[0], 128) + s.unwrapExpanded(halves[1], S - 128)
+    cp["self_output_row0"] = x[0]
+    w0 = [s.plain(model["W0_T"][:, 128 * b:128 * (b + 1)], 1 / 8.) for b in range(4)]
+    hidden = s.matmulRElarge(x, w0, s.plain(model["b0"], 1 / 8.))
+    cp["hidden_row0"] = hidden[0]
+    containers = s.generate_containers(hidden)
+    cp["container0_pre_gelu"] = containers[0]
+    containers = [s.eval_gelu_function(c, -1, 1, 1 / 8., 119) for c in containers]
+    cp["container0_gelu"] = containers[0]
+    quads = s.unwrapRepeatedLarge(containers, S)
+    w2 = [s.plain(model["W2"][:, 128 * b:128 * (b + 1)]) for b in range(4)]
+    ffn = s.matmulCRlarge(quads, w2, s.expanded(model["b2"]))
+    cp["ffn_row0"] = ffn[0]
+    # residual + affine2 (M:382-417)
+    o = [s.wrapUpExpanded(ffn[:128]) + halves[0], s.wrapUpExpanded(ffn[128:]) + halves[1]]
+    f2 = model["c2"][0] + model["c2"][1] / math.sqrt(S) + model["c2"][2] / S
+    o = [h * s.repeated(model["a2"], f2) + s.repeated(model["b2n"], f2) for h in o]
+    cp["affine2_0"] = o[0]
+    enc = s.unwrapExpanded(o[0], 1)[0]
+    cp["encoder_out"] = enc
+    # pooler (M:427-451)
+    y = s.rotsum(enc * s.plain(model["Wp_T"], 1 / 50.), 128, 128) + s.repeated(model["bp"], 1 / 50.)
+    cp["pooler_pre_tanh"] = y
+    y = s.eval_tanh_function(y, -1, 1, 1 / 50., 300)
+    cp["pooler_out"] = y
+    # classifier (M:453-475)
+    bc = np.concatenate([model["bc"], np.zeros(128 - len(model["bc"]))])
+    z = s.rotsum(y * s.plain(model["Wc"]), 128, 1) + s.expanded(bc)
+    pick = np.zeros(s.n); pick[np.arange(20) * 128] = 1
+    z = z * pick
+    cp["classified"] = z
+    return z[np.arange(20) * 128]
+
+
+def float_forward(model, sample):
+    """The same network as linear algebra on 128-vectors (the meaning of the slot layouts), with the C++ circuit's choices
+    (SURVEY.md section 3.5): no positional embedding on token rows, CLS-only attention, exp = T6(x/64)^8, 1/x and GELU and
+    tanh as Chebyshev interpolants, affine in place of LayerNorm."""
+    T6 = lambda x: sum(c * x ** i for i, c in enumerate([1, 1, 1 / 2., 1 / 6., 1 / 24., 1 / 120., 1 / 720.]))
+    rows = np.vstack([model["cls_token"][None, :], sample["tokens"]])
+    S = rows.shape[0]
+    q = rows[0] @ model["WQ_T"] + model["bQ"]
+    k = sample["XE"] @ model["WK_T"] + model["bK"]
+    v = sample["XF"] @ model["WV_T"] + model["bV"]
+    e = T6((k @ q) / 64.0) ** 8
+    # rotsum(scores, 32, 128) (M:201) adds slots 128 (j + t), t < 32, of a 16384-slot vector whose score region ends at slot
+    # 4096: key j is divided by the SUFFIX sum e_j + ... + e_31, not by the total -- a property of the reference circuit
+    suffix = np.cumsum(e[::-1])[::-1]
+    inv = chebyshev_eval(chebyshev_coefficients(lambda x: 1 / x, -1, 128, 119), -1, 128, suffix)
+    context = (e * inv) @ v
+    att = np.zeros_like(rows)
+    att[0] = model["WO"] @ context + model["bO"]
+    h = att + rows
+    f1 = model["c1"][0] + model["c1"][1] / math.sqrt(S) + model["c1"][2] / S
+    # wrapped-expanded slot 128 j + t holds (row t)[j] while R(a) holds a[t] there (M:311-317): the circuit scales row t
+    # (t counted inside its 128-row half) by a[t], i.e. the affine parameters are indexed by TOKEN position, not by feature
+    pos = np.arange(S) % 128
+    h1 = h * (model["a1"][pos] * f1)[:, None] + (model["b1"][pos] * f1)[:, None]
+    pre = (h1 @ model["W0_T"] + model["b0"]) / 8.0
+    cg = chebyshev_coefficients(lambda x: 0.5 * (x * 8) * (1 + math.erf((x * 8) / 1.41421356237)), -1, 1, 119)
+    g = chebyshev_eval(cg, -1, 1, pre)
+    ffn = g @ model["W2"].T + model["b2"]
+    f2 = model["c2"][0] + model["c2"][1] / math.sqrt(S) + model["c2"][2] / S
+    h2 = (ffn + h1) * (model["a2"][pos] * f2)[:, None] + (model["b2n"][pos] * f2)[:, None]
+    pre_t = (h2[0] @ model["Wp_T"] + model["bp"]) / 50.0
+    pooled = chebyshev_eval(chebyshev_coefficients(lambda x: math.tanh(x * 50), -1, 1, 300), -1, 1, pre_t)
+    logits = model["Wc"] @ pooled + model["bc"]
+    return {"logits": logits, "pre_gelu_max": float(np.abs(pre).max()), "pre_tanh_max": float(np.abs(pre_t).max()),
+            "exp_sum": float(e.sum()), "h1_max": float(np.abs(h1).max()), "gelu_max": float(np.abs(g).max()),
+            "scores_max": float(np.abs((k @ q) / 64.0).max())}
