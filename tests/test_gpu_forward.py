@@ -1,0 +1,74 @@
+"""GPU parity of the encrypted Linformer forward (FHEController + host/linformer.cpp on the CUDA engine) against the slot
+simulator: every checkpoint slot by slot, the 20 logits within the north star's 1e-3 absolute tolerance, identical class.
+Reference parameters (N = 2^15, 28 limbs, dnum 4, 2^14 slots), S = 129 rows (the circuit's minimum)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3          # BASELINE.json north_star: decrypted logits within 1e-3 absolute, identical predicted class
+CHECKPOINT_TOL = 2e-4     # intermediate ciphertexts; the loosest is tanh (slope 50) right after a bootstrap
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    from fhe_linformer_b200 import host, synth
+    root = str(tmp_path_factory.mktemp("linformer"))
+    model = synth.make_model(n_classes=8)
+    sample = synth.make_sample(model, 128, seed=20261018 + 1)
+    dirs = synth.write_files(root, model, sample)
+    fc = host.FHEController(root=root).generate()
+    yield fc, model, sample, dirs, root
+    fc.close()
+
+
+def test_forward_matches_slot_simulator(setup):
+    from oracle import linformer_sim as ls
+    fc, model, sample, dirs, _ = setup
+    fc.ckks.ledger(True); fc.ckks.ledger_reset()
+    got = {}
+    logits, stages, S = fc.forward(dirs, dead_work=True, checkpoints=got)
+    ref_cp = {}
+    ref = ls.sim_forward(model, sample, ref_cp)
+    assert S == 129
+    assert len(got) >= 20
+    for name, (slots, level) in got.items():
+        assert np.abs(slots - ref_cp[name]).max() < CHECKPOINT_TOL, name
+    assert np.abs(logits - ref).max() < LOGIT_TOL
+    assert int(np.argmax(logits)) == int(np.argmax(ref))
+    # the op ledger sees the reference's operation census (13 637 rotations at S = 129, plus the
+    # rotations inside the 8 bootstraps)
+    led = fc.ckks.ledger_dump()
+    rotations = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
+    assert 13637 <= rotations < 13637 + 8 * 120
+    fc.ckks.ledger(False)
+    setup[0].__dict__["_faithful_logits"] = logits
+
+
+def test_lean_mode_gives_the_same_logits(setup):
+    fc, model, sample, dirs, _ = setup
+    lean, _, _ = fc.forward(dirs, dead_work=False)
+    full = fc.__dict__.get("_faithful_logits")
+    if full is None:
+        full, _, _ = fc.forward(dirs, dead_work=True)
+    assert np.abs(lean - full).max() < 1e-4   # same circuit minus dead operations; fresh encryption noise only
+
+
+def test_key_files_roundtrip_and_resume(setup):
+    """generate_context(serialize) / load_context / rotation-key file / ciphertext checkpoint (F.cpp:59-89,184-301,1360-1394)."""
+    from fhe_linformer_b200 import host
+    fc, model, sample, dirs, root = setup
+    c = fc.ckks
+    v = np.random.default_rng(5).uniform(-1, 1, 16384)
+    ct = c.encrypt(v)
+    c.save(ct, root + "/checkpoint/x.bin")
+    c.save_keys(root + "/keys/all.bin")
+    other = host.FHEController(root=root)
+    other.hl.flh_generate(other.h, 0, None, 0, 16384, 0)   # fresh context, different key pair would be generated from the same seed
+    other.ckks = host._Borrowed(other.hl.flh_native(other.h))
+    other.ckks.load_keys(root + "/keys/all.bin")
+    back = other.ckks.load(root + "/checkpoint/x.bin")
+    assert np.abs(other.ckks.decrypt(back) - v).max() < 1e-8
+    r = other.ckks.rotate(back, 4)
+    assert np.abs(other.ckks.decrypt(r) - np.roll(v, -4)).max() < 1e-8
+    other.close()

@@ -1,0 +1,146 @@
+"""GPU parity of every FHEController method against the slot simulator, method by
+method on random inputs, called by name through libflhost.so.  Tolerances are CKKS noise at 52-bit scale."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-7
+
+
+@pytest.fixture(scope="module")
+def env():
+    from fhe_linformer_b200 import host
+    from oracle.linformer_sim import SlotSim
+    fc = host.FHEController(root="/tmp/flb200_layouts").generate()
+    yield fc, fc.ckks, SlotSim(), np.random.default_rng(11)
+    fc.close()
+
+
+def enc(c, v, level=0): return c.encrypt(v, level=level)
+def err(c, ct, ref): return float(np.abs(c.decrypt(ct) - ref).max())
+
+
+def test_ladders(env):
+    fc, c, s, rng = env
+    v = rng.uniform(-1, 1, s.n); ct = enc(c, v)
+    for slots, pad in [(128, 128), (128, 1), (32, 128), (64, 1)]:
+        assert err(c, fc.invoke("rotsum", [ct], ints=[slots, pad])[0], s.rotsum(v, slots, pad)) < TOL * slots
+    assert err(c, fc.invoke("rotsum_padded", [ct], ints=[8])[0], s.rotsum_padded(v, 8)) < TOL * 8
+    assert err(c, fc.invoke("repeat", [ct], ints=[128])[0], s.repeat(v, 128)) < TOL * 128
+    assert err(c, fc.invoke("repeat", [ct], ints=[128, -128])[0], s.repeat(v, 128, -128)) < TOL * 128
+    for k in [1, -1, 64, -64, -512, 8192, -8, -16]:
+        assert err(c, fc.invoke("rotate", [ct], ints=[k])[0], s.rotate(v, k)) < TOL
+
+
+def test_masks(env):
+    fc, c, s, rng = env
+    v = rng.uniform(-1, 1, s.n); ct = enc(c, v)
+    assert err(c, fc.invoke("mask_block", [ct], ints=[256, 384], reals=[0.5])[0], s.mask_block(v, 256, 384, 0.5)) < TOL
+    assert err(c, fc.invoke("mask_heads", [ct], reals=[2.0])[0], s.mask_heads(v, 2.0)) < TOL
+    assert err(c, fc.invoke("mask_heads_128", [ct], reals=[1 / 64.])[0], s.mask_heads_128(v, 1 / 64.)) < TOL
+    assert err(c, fc.invoke("mask_mod_n", [ct], ints=[128])[0], s.mask_mod_n(v, 128)) < TOL
+    assert err(c, fc.invoke("mask_mod_n", [ct], ints=[128, 64, 0])[0], s.mask_mod_n(v, 128, 64)) < TOL
+    assert err(c, fc.invoke("mask_first_n", [ct], ints=[128], reals=[1.0])[0], s.mask_first_n(v, 128)) < TOL
+    m = fc.invoke("mask_first_n", [ct], ints=[128])[0]
+    assert m.level == ct.level and m.deg == 2      # EvalMult(ct, pt): product not yet rescaled (FLEXIBLEAUTO)
+
+
+def test_matmuls_plain_weights(env):
+    fc, c, s, rng = env
+    W = rng.uniform(-0.1, 0.1, (128, 128)); b = rng.uniform(-0.1, 0.1, 128)
+    xs = [rng.uniform(-1, 1, 128) for _ in range(3)]
+    rows_e = [enc(c, s.expanded(x)) for x in xs]
+    out = fc.invoke("matmulRE", rows_e, pts=[c.encode(s.plain(W)), c.encode(s.repeated(b), level=1)])
+    ref = s.matmulRE([s.expanded(x) for x in xs], s.plain(W), s.repeated(b))
+    for o, r, x in zip(out, ref, xs):
+        assert err(c, o, r) < 1e-6
+        assert np.abs(c.decrypt(o)[:128] - (x @ W + b)).max() < 1e-6          # Repeated(x W + b)
+    rows_r = [enc(c, s.repeated(x)) for x in xs]
+    out = fc.invoke("matmulCR", rows_r, pts=[c.encode(s.plain(W)), None])
+    for o, x in zip(out, xs):
+        assert np.abs(c.decrypt(o)[::128] - W @ x).max() < 1e-6               # entry j at slot 128 j
+    # 128 -> 512 and 512 -> 128
+    W0 = rng.uniform(-0.1, 0.1, (128, 512)); b0 = rng.uniform(-0.1, 0.1, 512)
+    blocks = [c.encode(s.plain(W0[:, 128 * k:128 * (k + 1)])) for k in range(4)]
+    out = fc.invoke("matmulRElarge", rows_e[:2], pts=blocks + [c.encode(s.plain(b0), level=2)])
+    for o, x in zip(out, xs):
+        assert np.abs(c.decrypt(o)[:512] - (x @ W0 + b0)).max() < 1e-6
+    W2 = rng.uniform(-0.1, 0.1, (128, 512)); h = rng.uniform(-1, 1, 512)
+    quad = [enc(c, s.repeated(h[128 * k:128 * (k + 1)])) for k in range(4)]
+    out = fc.invoke("matmulCRlarge", quad, pts=[c.encode(s.plain(W2[:, 128 * k:128 * (k + 1)])) for k in range(4)] + [None])
+    assert np.abs(c.decrypt(out[0])[::128] - W2 @ h).max() < 1e-6
+
+
+def test_matmuls_ciphertext_weights_and_scores(env):
+    fc, c, s, rng = env
+    M = rng.uniform(-0.5, 0.5, s.n); x = [rng.uniform(-1, 1, s.n) for _ in range(3)]
+    cm = enc(c, M); cx = [enc(c, v) for v in x]
+    for name, simf in [("matmulCR", s.matmulCR_ct), ("matmulCR_128", s.matmulCR_128)]:
+        out = fc.invoke(name, cx + [cm])
+        for o, r in zip(out, simf(x, M)):
+            assert err(c, o, r) < 1e-5
+    out = fc.invoke("matmulRE", cx[:1] + [cm], ints=[128, 128])
+    assert err(c, out[0], s.matmulRE(x[:1], M, None, 128, 128)[0]) < 1e-5
+    one = fc.invoke("matmulScores", [cx[0], cm])[0]
+    assert err(c, one, s.matmulScores(x[:1], M)) < 1e-6
+    many = fc.invoke("matmulScoresVec", cx + [cm])[0]
+    assert err(c, many, s.matmulScores(x, M)) < 1e-6
+
+
+def test_wraps_and_containers(env):
+    fc, c, s, rng = env
+    vec = [rng.uniform(-1, 1, s.n) for _ in range(4)]
+    cts = [enc(c, v) for v in vec]
+    assert err(c, fc.invoke("wrapUpRepeated", cts)[0], s.wrapUpRepeated(vec)) < TOL
+    assert err(c, fc.invoke("wrapUpExpanded", cts)[0], s.wrapUpExpanded(vec)) < TOL
+    w = s.wrapUpExpanded(vec); cw = enc(c, w)
+    for o, r in zip(fc.invoke("unwrapExpanded", [cw], ints=[4]), s.unwrapExpanded(w, 4)):
+        assert err(c, o, r) < 1e-5
+    for o, r in zip(fc.invoke("unwrapScoresExpanded", [cw], ints=[2]), s.unwrapScoresExpanded(w, 2)):
+        assert err(c, o, r) < 1e-5
+    hid = [np.concatenate([rng.uniform(-1, 1, 512), np.zeros(s.n - 512)]) for _ in range(34)]
+    ch = [enc(c, h) for h in hid]
+    cont = fc.invoke("generate_containers", ch)
+    ref = s.generate_containers(hid)
+    assert len(cont) == 2
+    for o, r in zip(cont, ref):
+        assert err(c, o, r) < 1e-6
+    quads = fc.invoke("unwrapRepeatedLarge", cont, ints=[34])
+    flat = [q for quad in s.unwrapRepeatedLarge(ref, 34) for q in quad]
+    assert len(quads) == 34 * 4
+    for i in [0, 1, 5, 127, 128, 135]:
+        assert err(c, quads[i], flat[i]) < 1e-5
+    for o, r in zip(fc.invoke("unwrap_512_in_4_128", cont[:1], ints=[3]), s.unwrap_512_in_4_128(ref[0], 3)):
+        assert err(c, o, r) < 1e-5
+    sl = fc.invoke("slicing", cts, ints=[1, 3])
+    assert len(sl) == 2 and err(c, sl[0], vec[1]) < TOL
+
+
+def test_activations(env):
+    fc, c, s, rng = env
+    sc = np.zeros(s.n); sc[(np.arange(32) * 128)] = rng.uniform(-0.05, 0.05, 32)
+    assert err(c, fc.invoke("eval_exp", [enc(c, sc)], ints=[32])[0], s.eval_exp(sc, 32)) < 1e-6
+    u = rng.uniform(20, 100, s.n)
+    assert err(c, fc.invoke("eval_inverse_naive", [enc(c, u)], reals=[-1, 128])[0], s.eval_inverse_naive(u, -1, 128)) < 1e-5
+    assert err(c, fc.invoke("eval_inverse_naive_2", [enc(c, u)], reals=[1, 128, 2.0])[0], s.eval_inverse_naive_2(u, 1, 128, 2.0)) < 1e-5
+    big = rng.uniform(150, 19000, s.n)
+    assert err(c, fc.invoke("eval_inverse", [enc(c, big)], reals=[100, 19890])[0], s.eval_inverse(big, 100, 19890)) < 1e-6
+    x = rng.uniform(-1, 1, s.n)
+    assert err(c, fc.invoke("eval_gelu_function", [enc(c, x)], reals=[-1, 1, 1 / 8.], ints=[119])[0], s.eval_gelu_function(x, -1, 1, 1 / 8., 119)) < 1e-5
+    t = rng.uniform(-0.02, 0.02, s.n)
+    assert err(c, fc.invoke("eval_tanh_function", [enc(c, t)], reals=[-1, 1, 1 / 50.], ints=[300])[0], s.eval_tanh_function(t, -1, 1, 1 / 50., 300)) < 1e-5
+    assert err(c, fc.invoke("relu", [enc(c, x)], reals=[2.0])[0], s.relu(x, 2.0)) < 1e-5
+
+
+def test_bootstrap_variants_and_scalar_mult(env):
+    fc, c, s, rng = env
+    v = rng.uniform(-1, 1, s.n)
+    deep = enc(c, v, level=24)
+    b = fc.invoke("bootstrap", [deep])[0]
+    assert b.level <= 16 and err(c, b, v) < 1e-5
+    b2 = fc.invoke("bootstrap", [deep], ints=[17])[0]            # EvalBootstrap(c, 2, precision) F.cpp:461
+    assert err(c, b2, v) < 1e-5
+    m = fc.invoke("mult", [enc(c, v)], reals=[0.37])[0]
+    assert err(c, m, 0.37 * v) < TOL
