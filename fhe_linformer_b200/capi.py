@@ -49,6 +49,8 @@ def load_library():
         "fl_raw_modup": (ci, [vp, vp, vp, ci, ci]), "fl_raw_moddown": (ci, [vp, vp, vp, ci]),
         "fl_raw_keyswitch": (ci, [vp, vp, vp, vp, ci]),
         "fl_raw_rotate": (ci, [vp, vp, vp, ci, u32, vp]),
+        "fl_raw_rotate_batch": (ci, [vp, vp, vp, ci, u32, vp, ci]),
+        "fl_host_rotate_batch": (ci, [vp, vp, vp, ci, u32, vp, ci]),
         "fl_raw_mul_relin": (ci, [vp, vp, vp, vp, ci, vp]),
         "fl_raw_mul_plain": (ci, [vp, vp, vp, vp, ci]),
         "fl_host_ntt": (ci, [vp, vp, ci, ci]),
@@ -191,6 +193,15 @@ class Engine:
     def rotate(self, ct, g, evk, out=None):
         out = out or self.buf(ct.shape)
         self._ck(self.lib.fl_raw_rotate(self.h, out.ptr, ct.ptr, ct.shape[1], g, evk.ptr)); return out
+
+    def rotate_batch(self, cts, g, evk, out=None):
+        """cts: DevBuf [B][2][l][N]; one launch per key-switch stage for the whole batch."""
+        out = out or self.buf(cts.shape)
+        self._ck(self.lib.fl_raw_rotate_batch(self.h, out.ptr, cts.ptr, cts.shape[2], g, evk.ptr, cts.shape[0])); return out
+
+    def host_rotate_batch(self, cts, g, evk, out=None):
+        out = np.empty_like(cts) if out is None else out
+        self._ck(self.lib.fl_host_rotate_batch(self.h, _ptr(out), _ptr(cts), cts.shape[2], g, evk.ptr, cts.shape[0])); return out
 
     def mul_relin(self, a, b, evk, out=None):
         out = out or self.buf(a.shape)

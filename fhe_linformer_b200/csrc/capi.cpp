@@ -97,6 +97,9 @@ int fl_raw_keyswitch(fl_ctx* c, uint64_t* out2, const uint64_t* poly, const uint
 int fl_raw_rotate(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uint32_t g, const uint64_t* evk) {
     FL_TRY(c->eng->rotate(out, ct, l, g, evk))
 }
+int fl_raw_rotate_batch(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uint32_t g, const uint64_t* evk, int batch) {
+    FL_TRY(c->eng->rotate_batch(out, ct, l, g, evk, batch, false))
+}
 int fl_raw_mul_relin(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, int l, const uint64_t* evk) {
     FL_TRY(c->eng->mul_relin(out, a, b, l, evk))
 }
@@ -122,6 +125,17 @@ int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l
         u64* in = e.alloc(w); u64* out = e.alloc(w);
         e.upload(in, ct_host, w);
         e.rotate(out, in, l, g, evk_dev);
+        e.download(out_host, out, w);
+        e.release(in); e.release(out);
+    })
+}
+int fl_host_rotate_batch(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch) {
+    FL_TRY({
+        Engine& e = *c->eng;
+        const size_t w = (size_t)batch * 2 * l * e.P.N;
+        u64* in = e.alloc(w); u64* out = e.alloc(w);
+        e.upload(in, ct_host, w);
+        e.rotate_batch(out, in, l, g, evk_dev, batch, false);
         e.download(out_host, out, w);
         e.release(in); e.release(out);
     })
@@ -213,10 +227,15 @@ int fl_elem_deg(const fl_elem* a) { return a->e.deg; }
 int fl_elem_slots(const fl_elem* a) { return a->e.slots; }
 int fl_elem_ncomp(const fl_elem* a) { return a->e.ncomp; }
 double fl_elem_scale(const fl_elem* a) { return a->e.scale; }
+int fl_elem_batch(const fl_elem* a) { return a->e.batch; }
+int fl_batch_pack(fl_ctx* c, fl_elem* const* v, int n, fl_elem** out) {
+    FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->pack(e)); })
+}
+int fl_batch_slice(fl_ctx* c, const fl_elem* a, int i, fl_elem** out) { FL_TRY(*out = wrap(c->sch->slice(a->e, i))) }
 int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out) { FL_TRY(*out = wrap(c->sch->clone(a->e))) }
 void fl_elem_free(fl_elem* a) { delete a; }
 int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host) {
-    FL_TRY(c->eng->download(host, a->e.data(), (size_t)a->e.ncomp * a->e.l * c->eng->P.N))
+    FL_TRY(c->eng->download(host, a->e.data(), (size_t)a->e.batch * a->e.ncomp * a->e.l * c->eng->P.N))
 }
 int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int deg, double scale, int slots, fl_elem** out) {
     FL_TRY(*out = wrap(c->sch->import_elem(host, ncomp, limbs, deg, scale, slots)))

@@ -31,6 +31,7 @@ struct DevTables {
     const ulonglong2* itw2;   // [T][N] {psi^-bitrev(i), Shoup companion}
     const u64* ninv;     // [T]
     const u64* ninv_sh;
+    const u64* redc;     // [T][8]: dev::RedC per modulus (q, -q, floor(2^64/q), 2^30 mod q, 2^60 mod q with Shoup companions)
     int logN, N, L, K;
 };
 

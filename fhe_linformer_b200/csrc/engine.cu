@@ -49,6 +49,17 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     }
     T.q = to_device(P.q); T.mu_lo = to_device(P.mu_lo); T.mu_hi = to_device(P.mu_hi);
     T.ninv = to_device(P.ninv); T.ninv_sh = to_device(P.ninv_sh);
+    {
+        std::vector<u64> rc((size_t)Tn * 8, 0);
+        for (int m = 0; m < Tn; ++m) {
+            const u64 qq = P.q[m];
+            if (qq >> 60) throw std::invalid_argument("moduli must be below 2^60");
+            const u64 c30 = (1ull << 30) % qq, c60 = (1ull << 60) % qq;
+            u64* r = &rc[(size_t)m * 8];
+            r[0] = qq; r[1] = 0 - qq; r[2] = P.mu_hi[m]; r[3] = c30; r[4] = nt::shoup(c30, qq); r[5] = c60; r[6] = nt::shoup(c60, qq);
+        }
+        T.redc = to_device(rc);
+    }
     T.logN = P.logN; T.N = N; T.L = P.L; T.K = P.K;
 
     // ModDown constants (A.6)
@@ -154,35 +165,41 @@ const KsLevel& Engine::ks_level(int l) {
     return ks_.emplace(l, k).first->second;
 }
 
+// DropLastElementAndScale of `polys` polynomials stored back to back ([polys][l][N] -> [polys][l-1][N]); a batch of
+// ciphertexts is simply polys = 2 * batch.
 void Engine::rescale(u64* out, const u64* in, int l, int polys) {
     if (l < 2) throw std::invalid_argument("rescale: no limb left to drop");
     const int N = P.N;
     u64* xlast = alloc((size_t)polys * N);
-    for (int p = 0; p < polys; ++p) copy(xlast + (size_t)p * N, in + ((size_t)p * l + (l - 1)) * N, N);
-    LimbSel s1; s1.n = polys;
-    for (int p = 0; p < polys; ++p) { s1.m[p] = (uint8_t)(l - 1); s1.pos[p] = (uint8_t)p; }
-    intt(xlast, s1);
+    FLK_CUDA(cudaMemcpy2DAsync(xlast, (size_t)N * 8, in + (size_t)(l - 1) * N, (size_t)l * N * 8, (size_t)N * 8, polys, cudaMemcpyDeviceToDevice, stream));
+    LimbSel s1; s1.n = 1; s1.m[0] = (uint8_t)(l - 1); s1.pos[0] = 0;
+    launch_intt(T, xlast, s1, polys, (size_t)N, nullptr, nullptr, stream);
     u64* tq = alloc((size_t)polys * (l - 1) * N);
     launch_rescale_conv(T, tq, xlast, l, polys, stream);
-    LimbSel s2; s2.n = polys * (l - 1);
-    for (int p = 0; p < polys; ++p)
-        for (int i = 0; i < l - 1; ++i) { s2.m[p * (l - 1) + i] = (uint8_t)i; s2.pos[p * (l - 1) + i] = (uint8_t)(p * (l - 1) + i); }
-    ntt(tq, s2);
+    launch_ntt(T, tq, sel_range(0, l - 1), polys, (size_t)(l - 1) * N, stream);
     launch_rescale_finish(T, rs_, out, in, tq, l, polys, stream);
     release(xlast); release(tq);
-    if (ledger_on) ledger.add("rescale", l, (double)polys / 2 * (32.0 * l - 16.0) * N);
+    if (ledger_on) ledger.add("rescale", l, (32.0 * l - 16.0) * N, polys / 2 > 0 ? polys / 2 : 1);
 }
 
-void Engine::keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g) {
+// Hybrid key switch of a batch of polynomials with one evaluation key (HYBRID KeySwitch of EvalRotate / EvalMult, A.6):
+//   INTT digits (pre-scaled) -> ModUp base conversion -> NTT -> inner product with the key over Q_l u P -> INTT of the P part
+//   -> ModDown conversion -> NTT -> (acc - conv) P^-1 + addends, optionally permuted by the automorphism of g.
+// Every stage is one launch over the whole batch; work buffers are batch-contiguous.
+void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
+    const int l = io.l, B = io.B;
+    if (B <= 0) return;
     const KsLevel& ks = ks_level(l);
     const int N = P.N, K = P.K, ext = l + K, beta = ks.beta;
+    const size_t dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N, acc_bs = (size_t)2 * ext * N, tq_bs = (size_t)2 * l * N;
     // 1. digits to coefficient form, pre-scaled by (Q_d/q_i)^-1
-    u64* dco = alloc((size_t)l * N);
-    copy(dco, c, (size_t)l * N);
-    launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
+    u64* dco = alloc(dco_bs * B);
+    if (B == 1) copy(dco, io.c, dco_bs);
+    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, io.c, io.c_bs * 8, dco_bs * 8, B, cudaMemcpyDeviceToDevice, stream));
+    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream);
     // 2. ModUp: basis-extend every digit to the limbs outside it, back to evaluation form
-    u64* up = alloc((size_t)beta * ext * N);
-    launch_modup_conv(T, ks, up, dco, stream);
+    u64* up = alloc(up_bs * B);
+    launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
     LimbSel su; su.n = 0;
     for (int d = 0; d < beta; ++d) {
         const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
@@ -191,35 +208,41 @@ void Engine::keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64*
             su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
         }
     }
-    ntt(up, su);
+    launch_ntt(T, up, su, B, up_bs, stream);
     // 3. inner product with the evaluation key over Q_l u P
-    u64* acc = alloc((size_t)2 * ext * N);
-    launch_inner_product(T, ks, acc, acc + (size_t)ext * N, up, c, evk, stream);
+    u64* acc = alloc(acc_bs * B);
+    launch_inner_product(T, ks, acc, up, io.c, evk, B, acc_bs, up_bs, io.c_bs, stream);
     // 4. ModDown both accumulators
     LimbSel sp; sp.n = 2 * K;
     for (int p = 0; p < 2; ++p)
         for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
-    launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
-    u64* tq = alloc((size_t)2 * l * N);
-    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, stream);
+    launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
+    u64* tq = alloc(tq_bs * B);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
     LimbSel sq; sq.n = 2 * l;
     for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
-    ntt(tq, sq);
-    launch_moddown_finish(T, md_, out, acc, (size_t)ext * N, tq, add0, add1, g ? automorph_map(g) : nullptr, l, 2, stream);
+    launch_ntt(T, tq, sq, B, tq_bs, stream);
+    FinishArgs fa{io.out, io.out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, io.add0, io.add0_bs, io.add1, io.add1_bs, io.plus, io.plus_bs};
+    launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, B, stream);
     release(dco); release(up); release(acc); release(tq);
 }
 
-void Engine::rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) {
-    keyswitch(out, ct + (size_t)l * P.N, evk, l, ct, nullptr, g);
-    if (ledger_on) ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
+void Engine::keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g) {
+    KsBatch io{1, l, c, 0, out, 0, add0, 0, add1, 0, nullptr, 0};
+    keyswitch(io, evk, g);
 }
 
-void Engine::rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) {
-    keyswitch(out, ct + (size_t)l * P.N, evk, l, ct, nullptr, g);
-    launch_ew(T, EwOp::Add, out, out, ct, sel_range(0, l), 2, 1, 0, 0, (size_t)l * P.N, stream);
+void Engine::rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) { rotate_batch(out, ct, l, g, evk, 1, false); }
+void Engine::rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk) { rotate_batch(out, ct, l, g, evk, 1, true); }
+
+// out[b] = rotate(ct[b]) (+ ct[b] when `accumulate`) for B ciphertexts stored back to back ([B][2][l][N])
+void Engine::rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64* evk, int B, bool accumulate) {
+    const size_t cs = (size_t)2 * l * P.N;
+    KsBatch io{B, l, ct + (size_t)l * P.N, cs, out, cs, ct, cs, nullptr, 0, accumulate ? ct : nullptr, cs};
+    keyswitch(io, evk, g);
     if (ledger_on) {
-        ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
-        ledger.add("add", l, 48.0 * l * P.N);
+        ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B);
+        if (accumulate) ledger.add("add", l, 48.0 * l * P.N, B);
     }
 }
 
@@ -239,7 +262,7 @@ void Engine::modup(u64* out_ext, const u64* c_eval, int l, int digit) {
     copy(dco, c_eval, (size_t)l * N);
     launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
     u64* up = alloc((size_t)ks.beta * ext * N);
-    launch_modup_conv(T, ks, up, dco, stream);
+    launch_modup_conv(T, ks, up, dco, 1, 0, 0, stream);
     const int lo = digit * ks.alpha, hi = std::min(lo + ks.alpha, l);
     LimbSel su; su.n = 0;
     for (int t = 0; t < ext; ++t) {
@@ -260,9 +283,10 @@ void Engine::moddown(u64* out, const u64* in_ext, int l) {
     for (int k = 0; k < K; ++k) { sp.m[k] = (uint8_t)(P.L + k); sp.pos[k] = (uint8_t)(l + k); }
     launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
     u64* tq = alloc((size_t)l * N);
-    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 1, stream);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 1, 1, 0, 0, stream);
     ntt(tq, sel_range(0, l));
-    launch_moddown_finish(T, md_, out, acc, (size_t)ext * N, tq, nullptr, nullptr, nullptr, l, 1, stream);
+    FinishArgs fa{out, 0, acc, (size_t)ext * N, 0, tq, 0, nullptr, 0, nullptr, 0, nullptr, 0};
+    launch_moddown_finish(T, md_, fa, nullptr, l, 1, 1, stream);
     release(acc); release(tq);
 }
 

@@ -14,11 +14,21 @@ namespace flk {
 struct OpLedger {   // algorithmic-byte accounting per SURVEY.md section 8(d)
     struct Row { long count = 0; double bytes = 0; };
     std::map<std::string, Row> rows;
-    void add(const std::string& op, int l, double bytes) {
+    void add(const std::string& op, int l, double bytes, int times = 1) {
         Row& r = rows[op + "@" + std::to_string(l)];
-        r.count++; r.bytes += bytes;
+        r.count += times; r.bytes += bytes * times;
     }
     void reset() { rows.clear(); }
+};
+
+// A batch of key switches sharing one evaluation key; *_bs are batch strides in words (0 when B = 1).
+struct KsBatch {
+    int B, l;
+    const u64* c; size_t c_bs;          // polynomials to switch, [l][N] each
+    u64* out; size_t out_bs;            // results, [2][l][N] each
+    const u64* add0; size_t add0_bs;    // optional [l][N] addends of the two result polynomials (permuted with them)
+    const u64* add1; size_t add1_bs;
+    const u64* plus; size_t plus_bs;    // optional [2][l][N] addend that is NOT permuted (rotate-and-add)
 };
 
 class Engine {
@@ -50,6 +60,8 @@ public:
     void rescale(u64* out, const u64* in, int l, int polys);
     // out[2][l][N] = KeySwitch(c) (+add0 / +add1), optionally permuted by the automorphism map of g (0 = none)
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
+    void keyswitch(const KsBatch& io, const u64* evk, uint32_t g);
+    void rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64* evk, int B, bool accumulate);   // ct, out: [B][2][l][N]
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
     void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);

@@ -77,90 +77,132 @@ __global__ void __launch_bounds__(kThreads) tensor_kernel(u64* __restrict__ d0, 
 }
 
 // ---------------- fast basis conversion (ModUp / ModDown) ----------------
-// One thread per coefficient: the ns source residues stay in registers while it walks its strip of targets.
-// hm[i * tstride + t] = (S/s_i) mod target_t, staged in shared memory.
-__global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ up, const u64* __restrict__ dcoef, DevTables T, KsLevel ks) {
-    extern __shared__ u64 shm[];
-    const int d = blockIdx.z, l = ks.l, ext = l + T.K;
-    const int lo = d * ks.alpha, hi = min(lo + ks.alpha, l), ns = hi - lo;
-    for (int i = threadIdx.x; i < ks.alpha * ext; i += kThreads) shm[i] = ks.hm[(size_t)d * ks.alpha * ext + i];
+__device__ __forceinline__ RedC load_redc(const DevTables& T, int m) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(T.redc) + (size_t)m * 4;
+    const ulonglong2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    return RedC{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+
+// One thread per coefficient: the A source residues stay in registers (as 30-bit halves) while the thread walks its strip
+// of targets; products accumulate carry-free (dev::mac3, 4 IMAD.WIDE each), one reduction per output (dev::reduce3).
+// sh[i * ext + t] = (S/s_i) mod target_t as 30-bit halves (zero for the missing sources of a short last digit).
+// grid: (N / 256, target groups, batch * beta); buffers carry a batch stride.
+template <int A>
+__global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ up, const u64* __restrict__ dcoef, DevTables T, KsLevel ks,
+                                                              size_t up_bs, size_t dco_bs) {
+    extern __shared__ uint2 shs[];
+    const int d = blockIdx.z % ks.beta, b = blockIdx.z / ks.beta, l = ks.l, ext = l + T.K;
+    const int lo = d * A, hi = min(lo + A, l), ns = hi - lo;
+    for (int i = threadIdx.x; i < A * ext; i += kThreads) {
+        const Split30 h = split30(ks.hm[(size_t)d * A * ext + i]);
+        shs[i] = make_uint2(h.lo, h.hi);
+    }
     __syncthreads();
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
-    u64 y[kAlphaMax];
+    Split30 y[A];
 #pragma unroll
-    for (int i = 0; i < kAlphaMax; ++i) y[i] = i < ns ? dcoef[(size_t)(lo + i) * T.N + j] : 0;
+    for (int i = 0; i < A; ++i) y[i] = split30(i < ns ? dcoef[(size_t)b * dco_bs + (size_t)(lo + i) * T.N + j] : 0);
     const int tg = gridDim.y, per = (ext + tg - 1) / tg;
     const int t0 = blockIdx.y * per, t1 = min(t0 + per, ext);
+    u64* dst = up + (size_t)b * up_bs + (size_t)d * ext * T.N + j;
     for (int t = t0; t < t1; ++t) {
         if (t >= lo && t < hi) continue;
-        const int m = t < l ? t : T.L + (t - l);
-        U128 acc{0, 0};
+        const RedC rc = load_redc(T, t < l ? t : T.L + (t - l));
+        Acc3 acc{0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < kAlphaMax; ++i)
-            if (i < ns) mad128(acc, y[i], shm[i * ext + t]);
-        up[((size_t)d * ext + t) * T.N + j] = barrett128(acc, T.q[m], T.mu_lo[m], T.mu_hi[m]);
+        for (int i = 0; i < A; ++i) { const uint2 h = shs[i * ext + t]; mac3(acc, y[i], Split30{h.x, h.y}); }
+        dst[(size_t)t * T.N] = reduce3(acc, rc);
     }
 }
 
-__global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc0, u64* __restrict__ acc1, const u64* __restrict__ up,
-                                                                 const u64* __restrict__ c_eval, const u64* __restrict__ evk, DevTables T,
-                                                                 KsLevel ks) {
-    const int t = blockIdx.y, l = ks.l, ext = l + T.K;
+// acc{0,1}[b][t] = sum_d U_d[b][t] * evk_{b,a}[d][mod(t)].  A thread owns one coefficient of one extended limb for IPB
+// ciphertexts of the batch, so every evaluation-key word it loads (the largest stream of a key switch) is used IPB times.
+constexpr int kIpb = 4;
+__global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
+                                                                 const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,
+                                                                 size_t up_bs, size_t c_bs) {
+    const int t = blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * kIpb;
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
     const size_t kpoly = (size_t)(T.L + T.K) * T.N;
-    U128 s0{0, 0}, s1{0, 0};
+    Acc3 s0[kIpb], s1[kIpb];
+#pragma unroll
+    for (int i = 0; i < kIpb; ++i) { s0[i] = Acc3{0, 0, 0}; s1[i] = Acc3{0, 0, 0}; }
+    const int own_d = t < l ? t / ks.alpha : -1;
     for (int d = 0; d < ks.beta; ++d) {
-        const bool own = t >= d * ks.alpha && t < min((d + 1) * ks.alpha, l);
-        const u64 u = own ? c_eval[(size_t)t * T.N + j] : up[((size_t)d * ext + t) * T.N + j];
         const u64* kb = evk + (size_t)d * 2 * kpoly + (size_t)m * T.N + j;
-        mad128(s0, u, kb[0]);
-        mad128(s1, u, kb[kpoly]);
+        const Split30 k0 = split30(__ldg(kb)), k1 = split30(__ldg(kb + kpoly));
+        const u64* src = d == own_d ? c_eval + (size_t)t * T.N + j : up + ((size_t)d * ext + t) * T.N + j;
+        const size_t bs = d == own_d ? c_bs : up_bs;
+#pragma unroll
+        for (int i = 0; i < kIpb; ++i) {
+            if (b0 + i < batch) {
+                const Split30 us = split30(src[(size_t)(b0 + i) * bs]);
+                mac3(s0[i], us, k0);
+                mac3(s1[i], us, k1);
+            }
+        }
     }
-    const u64 q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
-    acc0[(size_t)t * T.N + j] = barrett128(s0, q, ml, mh);
-    acc1[(size_t)t * T.N + j] = barrett128(s1, q, ml, mh);
+    const RedC rc = load_redc(T, m);
+#pragma unroll
+    for (int i = 0; i < kIpb; ++i) {
+        if (b0 + i < batch) {
+            u64* o = acc + (size_t)(b0 + i) * acc_bs + (size_t)t * T.N + j;
+            o[0] = reduce3(s0[i], rc);
+            o[(size_t)ext * T.N] = reduce3(s1[i], rc);
+        }
+    }
 }
 
+// grid: (N / 256, target groups, batch * polys); pcoef = P part (coefficient form, pre-scaled) of accumulator (b, p)
+template <int KK>
 __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
-                                                                MdConst md, int l) {
-    extern __shared__ u64 shm[];
-    const int K = T.K, p = blockIdx.z;
-    for (int i = threadIdx.x; i < K * l; i += kThreads) shm[i] = md.phm[(size_t)(i / l) * T.L + (i % l)];
+                                                                MdConst md, int l, int polys, size_t tq_bs, size_t p_bs) {
+    extern __shared__ uint2 shs[];
+    const int p = blockIdx.z % polys, b = blockIdx.z / polys;
+    for (int i = threadIdx.x; i < KK * l; i += kThreads) {
+        const Split30 h = split30(md.phm[(size_t)(i / l) * T.L + (i % l)]);
+        shs[i] = make_uint2(h.lo, h.hi);
+    }
     __syncthreads();
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
-    u64 y[kAlphaMax];
+    Split30 y[KK];
 #pragma unroll
-    for (int k = 0; k < kAlphaMax; ++k) y[k] = k < K ? pcoef[(size_t)p * pstride + (size_t)k * T.N + j] : 0;
+    for (int k = 0; k < KK; ++k) y[k] = split30(pcoef[(size_t)b * p_bs + (size_t)p * pstride + (size_t)k * T.N + j]);
     const int tg = gridDim.y, per = (l + tg - 1) / tg;
     const int t0 = blockIdx.y * per, t1 = min(t0 + per, l);
+    u64* dst = tq + (size_t)b * tq_bs + (size_t)p * l * T.N + j;
     for (int t = t0; t < t1; ++t) {
-        U128 acc{0, 0};
+        const RedC rc = load_redc(T, t);
+        Acc3 acc{0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < kAlphaMax; ++k)
-            if (k < K) mad128(acc, y[k], shm[k * l + t]);
-        tq[((size_t)p * l + t) * T.N + j] = barrett128(acc, T.q[t], T.mu_lo[t], T.mu_hi[t]);
+        for (int k = 0; k < KK; ++k) { const uint2 h = shs[k * l + t]; mac3(acc, y[k], Split30{h.x, h.y}); }
+        dst[(size_t)t * T.N] = reduce3(acc, rc);
     }
 }
 
+// out[b][p][i][j] = ((acc - tq) P^-1 + add_p)[b][i][map ? map[j] : j];  grid (N / 256, l, batch * polys)
 __global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restrict__ out, const u64* __restrict__ acc, size_t acc_ps,
                                                                   const u64* __restrict__ tq, const u64* __restrict__ add0,
                                                                   const u64* __restrict__ add1, const uint32_t* __restrict__ map, DevTables T,
-                                                                  MdConst md, int l) {
-    const int i = blockIdx.y, p = blockIdx.z;
+                                                                  MdConst md, int l, int polys, size_t out_bs, size_t acc_bs, size_t tq_bs,
+                                                                  size_t add0_bs, size_t add1_bs, const u64* __restrict__ plus, size_t plus_bs) {
+    const int i = blockIdx.y, p = blockIdx.z % polys, b = blockIdx.z / polys;
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int src = map ? map[j] : j;
     const u64 q = T.q[i];
     const size_t o = (size_t)i * T.N + src;
-    u64 v = submod(acc[(size_t)p * acc_ps + o], tq[(size_t)p * l * T.N + o], q);
+    u64 v = submod(acc[(size_t)b * acc_bs + (size_t)p * acc_ps + o], tq[(size_t)b * tq_bs + (size_t)p * l * T.N + o], q);
     v = mul_shoup(v, md.pinv[i], md.pinv_sh[i], q);
     const u64* add = p == 0 ? add0 : add1;
-    if (add) v = addmod(v, add[o], q);
-    out[((size_t)p * l + i) * T.N + j] = v;
+    if (add) v = addmod(v, add[(size_t)b * (p == 0 ? add0_bs : add1_bs) + o], q);
+    const size_t oo = ((size_t)p * l + i) * T.N + j;
+    if (plus) v = addmod(v, plus[(size_t)b * plus_bs + oo], q);   // unpermuted addend: out = plus + rotate(...) (rotate-and-add ladders)
+    out[(size_t)b * out_bs + oo] = v;
 }
 
 // ---------------- rescale ----------------
@@ -274,26 +316,42 @@ void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, 
     tensor_kernel<<<cdiv((size_t)l * t.N, kThreads), kThreads, 0, s>>>(d0, d1, d2, a, b, t, l);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, cudaStream_t s) {
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s) {
     if (ks.alpha > kAlphaMax) throw std::invalid_argument("digit size above 8 limbs is not supported");
     const int ext = ks.l + t.K, tg = ext >= 16 ? 4 : 1;
-    modup_conv_kernel<<<dim3(cdiv(t.N, kThreads), tg, ks.beta), kThreads, (size_t)ks.alpha * ext * 8, s>>>(up, dcoef, t, ks);
+    const dim3 grid(cdiv(t.N, kThreads), tg, ks.beta * batch);
+    const size_t shm = (size_t)ks.alpha * ext * 8;
+    switch (ks.alpha) {
+#define FLK_CASE(X) case X: modup_conv_kernel<X><<<grid, kThreads, shm, s>>>(up, dcoef, t, ks, up_bs, dco_bs); break;
+        FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
+#undef FLK_CASE
+    }
     FLK_CUDA(cudaGetLastError());
 }
-void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc0, u64* acc1, const u64* up, const u64* c_eval, const u64* evk,
-                          cudaStream_t s) {
-    inner_product_kernel<<<dim3(cdiv(t.N, kThreads), ks.l + t.K), kThreads, 0, s>>>(acc0, acc1, up, c_eval, evk, t, ks);
+void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
+                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s) {
+    inner_product_kernel<<<dim3(cdiv(t.N, kThreads), ks.l + t.K, (batch + kIpb - 1) / kIpb), kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch,
+                                                                                                            acc_bs, up_bs, c_bs);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, cudaStream_t s) {
+void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
+                         size_t tq_bs, size_t p_bs, cudaStream_t s) {
     if (t.K > kAlphaMax) throw std::invalid_argument("more than 8 P limbs is not supported");
     const int tg = l >= 16 ? 4 : 1;
-    moddown_conv_kernel<<<dim3(cdiv(t.N, kThreads), tg, polys), kThreads, (size_t)t.K * l * 8, s>>>(tq, pcoef, pstride, t, md, l);
+    const dim3 grid(cdiv(t.N, kThreads), tg, polys * batch);
+    const size_t shm = (size_t)t.K * l * 8;
+    switch (t.K) {
+#define FLK_CASE(X) case X: moddown_conv_kernel<X><<<grid, kThreads, shm, s>>>(tq, pcoef, pstride, t, md, l, polys, tq_bs, p_bs); break;
+        FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
+#undef FLK_CASE
+    }
     FLK_CUDA(cudaGetLastError());
 }
-void launch_moddown_finish(const DevTables& t, const MdConst& md, u64* out, const u64* acc, size_t acc_ps, const u64* tq, const u64* add0,
-                           const u64* add1, const uint32_t* map, int l, int polys, cudaStream_t s) {
-    moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), l, polys), kThreads, 0, s>>>(out, acc, acc_ps, tq, add0, add1, map, t, md, l);
+void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
+                           cudaStream_t s) {
+    moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), l, polys * batch), kThreads, 0, s>>>(a.out, a.acc, a.acc_ps, a.tq, a.add0, a.add1, map, t, md, l,
+                                                                                          polys, a.out_bs, a.acc_bs, a.tq_bs, a.add0_bs, a.add1_bs,
+                                                                                          a.plus, a.plus_bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {

@@ -41,18 +41,28 @@ struct MdConst {          // ModDown constants (level independent)
     const u64* pinv_sh;
 };
 
-// up[d][t][N] (coefficient form) for all digits d and all extended limbs t outside digit d.
-// dcoef = INTT(c) already scaled by KsLevel::post, [l][N].
-void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, cudaStream_t s);
-// acc{0,1}[t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[t] inside digit d else up[d][t]
-void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc0, u64* acc1, const u64* up, const u64* c_eval,
-                          const u64* evk, cudaStream_t s);
-// tq[p][i][N] (coefficient form), i < l, from the scaled INTT of the P part of `polys` accumulators.
-// pcoef = [polys][K][N] with poly stride pstride; tq = [polys][l][N]
-void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, cudaStream_t s);
-// out[p][i][j] = ((acc[p][i] - tq[p][i]) * P^-1 + (p == 0 && add0 ? add0[i] : (p == 1 && add1 ? add1[i]: 0)))[map ? map[j] : j]
-void launch_moddown_finish(const DevTables& t, const MdConst& md, u64* out, const u64* acc, size_t acc_pstride, const u64* tq, const u64* add0,
-                           const u64* add1, const uint32_t* map, int l, int polys, cudaStream_t s);
+// All key-switch kernels take a batch of ciphertexts (same limb count, same key); *_bs are batch strides in words.
+// up[b][d][t][N] (coefficient form) for all digits d and all extended limbs t outside digit d.
+// dcoef = INTT(c) already scaled by KsLevel::post, [b][l][N].
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s);
+// acc[b][{0,1}][t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[b][t] inside digit d else up[b][d][t]
+void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
+                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
+// tq[b][p][i][N] (coefficient form), i < l, from the scaled INTT of the P part of `polys` accumulators.
+// pcoef = [b][polys][K][N] with poly stride pstride and batch stride p_bs
+void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
+                         size_t tq_bs, size_t p_bs, cudaStream_t s);
+// out[b][p][i][j] = ((acc[b][p][i] - tq[b][p][i]) * P^-1 + add_p[b][i])[map ? map[j] : j] + (plus ? plus[b][p][i][j] : 0)
+struct FinishArgs {
+    u64* out; size_t out_bs;
+    const u64* acc; size_t acc_ps, acc_bs;
+    const u64* tq; size_t tq_bs;
+    const u64* add0; size_t add0_bs;
+    const u64* add1; size_t add1_bs;
+    const u64* plus; size_t plus_bs;
+};
+void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
+                           cudaStream_t s);
 
 // ---- rescale ----
 struct RsConst {

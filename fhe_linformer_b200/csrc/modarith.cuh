@@ -20,6 +20,15 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 a, u64 w, u64 ws, u64 q) {
 }
 __device__ __forceinline__ u64 mul_shoup(u64 a, u64 w, u64 ws, u64 q) { return csub(mul_shoup_lazy(a, w, ws, q), q); }
 
+// floor(a*b / 2^64) - e with e in {0,1,2}: the three partial products that reach the high word (IMAD.WIDE.U32 x3);
+// the low x low product and the low halves of the cross products are dropped.
+__device__ __forceinline__ u64 mulhi_lazy(u64 a, u64 b) {
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    const u64 t = (u64)ah * bl;
+    const u64 u = (u64)al * bh;
+    return (u64)ah * bh + (t >> 32) + (u >> 32);
+}
+
 struct U128 {
     u64 lo, hi;
 };
@@ -39,6 +48,50 @@ __device__ __forceinline__ u64 barrett128(U128 x, u64 q, u64 mu_lo, u64 mu_hi) {
 __device__ __forceinline__ u64 mulmod(u64 a, u64 b, u64 q, u64 mu_lo, u64 mu_hi) {
     U128 x{a * b, __umul64hi(a, b)};
     return barrett128(x, q, mu_lo, mu_hi);
+}
+
+// ---- carry-free multiply-accumulate for the base conversions and the evaluation-key inner product ----
+// Every modulus is below 2^60, so a residue splits into two 30-bit halves and a product into four partial products below
+// 2^60.  Up to 8 products (16 cross terms) accumulate in plain 64-bit registers -- one IMAD.WIDE.U32 each, no carry chain:
+//   sum = a0 + a1 2^30 + a2 2^60,  a0 < 2^63, a1 < 2^64, a2 < 2^63.
+struct Split30 {
+    u32 lo, hi;
+};
+__device__ __forceinline__ Split30 split30(u64 x) { return Split30{(u32)x & 0x3fffffffu, (u32)(x >> 30)}; }
+struct Acc3 {
+    u64 a0, a1, a2;
+};
+// acc += a * b as one IMAD.WIDE.U32 (written in PTX: the C form compiles to a product plus separate 64-bit additions)
+__device__ __forceinline__ void wmad(u64& acc, u32 a, u32 b) { asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a), "r"(b)); }
+__device__ __forceinline__ void mac3(Acc3& s, Split30 x, Split30 y) {
+    wmad(s.a0, x.lo, y.lo);
+    wmad(s.a1, x.lo, y.hi);
+    wmad(s.a1, x.hi, y.lo);
+    wmad(s.a2, x.hi, y.hi);
+}
+// conditional subtraction for operands below 2^63 (sign test instead of a 64-bit compare)
+__device__ __forceinline__ u64 csub_s(u64 a, u64 q) {
+    const u64 t = a - q;
+    return (long long)t < 0 ? a : t;
+}
+// a*w - qhat*q with qhat low by at most 2 (mulhi_lazy): any a < 2^64, result in [0,4q); nq = -q
+__device__ __forceinline__ u64 shoup_lazy4(u64 a, u64 w, u64 ws, u64 nq) { return a * w + mulhi_lazy(a, ws) * nq; }
+// per-modulus constants of the accumulator reduction
+struct __align__(16) RedC {
+    u64 q, nq, mu64;        // mu64 = floor(2^64 / q)
+    u64 c30, c30s;          // 2^30 mod q and its Shoup companion
+    u64 c60, c60s;          // 2^60 mod q
+    u64 pad;
+};
+// (a0 + a1 2^30 + a2 2^60) mod q, canonical: the two high accumulators through lazy Shoup products with 2^30, 2^60 mod q,
+// then one single-word Barrett step.  a0 + 8q < 2^64 since q < 2^60.
+__device__ __forceinline__ u64 reduce3(const Acc3& s, const RedC& k) {
+    const u64 t1 = shoup_lazy4(s.a1, k.c30, k.c30s, k.nq);
+    const u64 t2 = shoup_lazy4(s.a2, k.c60, k.c60s, k.nq);
+    const u64 u = s.a0 + t1 + t2;
+    u64 r = u + mulhi_lazy(u, k.mu64) * k.nq;      // Barrett quotient low by at most 3: r < 4q
+    r = csub_s(r, k.q << 1);
+    return csub_s(r, k.q);
 }
 
 // Harvey lazy butterflies.  Cooley-Tukey (forward): x,y in [0,4q) -> [0,4q)

@@ -11,9 +11,11 @@
 //   chunk pass  : the remaining logN-4 stages on contiguous chunks of 2^(logN-4) words, one CTA per
 //                 chunk, radix-8 register blocks exchanged through XOR-swizzled shared memory, the
 //                 next round's twiddles prefetched (16-byte {w, w'} loads) across the barrier.
-// Butterflies are Harvey lazy with Shoup twiddles.  Forward values grow by 2q per stage; for moduli
-// below 2^56 (every Q limb) 33q < 2^64, so the forward transform carries NO conditional subtraction
-// until one Barrett-style reduction at the very end; the 60-bit P limbs keep values below 4q.
+// Butterflies are Harvey lazy with Shoup twiddles whose quotient is estimated from three 32x32 partial products
+// (dev::mulhi_lazy: low by at most 2), so a twiddle product lies in [0,4q).  Forward values grow by 4q per stage;
+// for moduli below 2^56 (every Q limb) 65q < 2^64, so the forward transform carries NO conditional subtraction
+// until one Barrett-style reduction at the very end; the 60-bit P limbs keep values below 8q.  The inverse keeps
+// values below 4q with one conditional subtraction per butterfly.  Per butterfly: 9 IMAD-class + 9 IADD3-class SASS.
 #include "device_ctx.h"
 #include "modarith.cuh"
 
@@ -24,20 +26,22 @@ using namespace dev;
 
 __device__ __forceinline__ bool is_wide(u64 q) { return (q >> 56) != 0; }
 
-// a*w - floor(a*ws/2^64)*q, written as two fused multiply-adds with nq = -q
-__device__ __forceinline__ u64 shoup_nq(u64 a, u64 w, u64 ws, u64 nq) { return a * w + __umul64hi(a, ws) * nq; }
+// a*w - qhat*q with qhat in [floor(a*ws/2^64) - 2, floor(a*ws/2^64)], as fused multiply-adds with nq = -q: result in [0,4q)
+__device__ __forceinline__ u64 shoup_nq(u64 a, u64 w, u64 ws, u64 nq) { return a * w + mulhi_lazy(a, ws) * nq; }
 
+// forward: x,y < B  ->  < B + 4q  (narrow limbs: no reduction at all; wide limbs: B = 8q kept by one conditional subtraction)
 template <bool WIDE>
-__device__ __forceinline__ void ct_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q2) {
+__device__ __forceinline__ void ct_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q4) {
     u64 u = x;
-    if (WIDE) u = csub(u, q2);
+    if (WIDE) u = csub(u, q4);
     const u64 v = shoup_nq(y, t.x, t.y, nq);
     x = u + v;
-    y = u - v + q2;
+    y = u - v + q4;
 }
-__device__ __forceinline__ void gs_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q2) {
-    const u64 s = csub(x + y, q2);
-    const u64 d = x - y + q2;
+// inverse: x,y in [0,4q) -> [0,4q)
+__device__ __forceinline__ void gs_bf(u64& x, u64& y, ulonglong2 t, u64 nq, u64 q4) {
+    const u64 s = csub(x + y, q4);
+    const u64 d = x - y + q4;
     x = s;
     y = shoup_nq(d, t.x, t.y, nq);
 }
@@ -51,32 +55,32 @@ __device__ __forceinline__ void load_tw(ulonglong2* t, const ulonglong2* __restr
         for (int g = 0; g < (1 << s); ++g) t[(1 << s) - 1 + g] = __ldg(tab + ((J << s) + g));
 }
 template <int LOG, bool WIDE>
-__device__ __forceinline__ void ct_block(u64* e, const ulonglong2* t, u64 nq, u64 q2) {
+__device__ __forceinline__ void ct_block(u64* e, const ulonglong2* t, u64 nq, u64 q4) {
 #pragma unroll
     for (int s = 0; s < LOG; ++s) {
         const int half = (1 << LOG) >> (s + 1);
 #pragma unroll
         for (int g = 0; g < (1 << s); ++g)
 #pragma unroll
-            for (int j = 0; j < half; ++j) ct_bf<WIDE>(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q2);
+            for (int j = 0; j < half; ++j) ct_bf<WIDE>(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q4);
     }
 }
 template <int LOG>
-__device__ __forceinline__ void gs_block(u64* e, const ulonglong2* t, u64 nq, u64 q2) {
+__device__ __forceinline__ void gs_block(u64* e, const ulonglong2* t, u64 nq, u64 q4) {
 #pragma unroll
     for (int s = LOG - 1; s >= 0; --s) {
         const int half = (1 << LOG) >> (s + 1);
 #pragma unroll
         for (int g = 0; g < (1 << s); ++g)
 #pragma unroll
-            for (int j = 0; j < half; ++j) gs_bf(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q2);
+            for (int j = 0; j < half; ++j) gs_bf(e[g * 2 * half + j], e[g * 2 * half + half + j], t[(1 << s) - 1 + g], nq, q4);
     }
 }
 // canonical residue of a lazily accumulated forward value
 template <bool WIDE>
-__device__ __forceinline__ u64 final_reduce(u64 v, u64 q, u64 q2, u64 nq, u64 qinv64) {
-    if (WIDE) return csub(csub(v, q2), q);          // v < 4q
-    return csub(v + __umul64hi(v, qinv64) * nq, q);  // v < 33q: one Barrett step with floor(2^64/q)
+__device__ __forceinline__ u64 final_reduce(u64 v, u64 q, u64 q4, u64 nq, u64 qinv64) {
+    if (WIDE) return csub(csub(csub(v, q4), q4 >> 1), q);   // v < 8q
+    return csub(v + __umul64hi(v, qinv64) * nq, q);          // v < 65q: one Barrett step with floor(2^64/q)
 }
 
 // ---------------- column pass (register radix-16) ----------------
@@ -90,18 +94,18 @@ __global__ void __launch_bounds__(256) ntt_column_kernel(u64* __restrict__ data,
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + c;
-    const u64 q = T.q[m], nq = 0 - q, q2 = q << 1;
+    const u64 q = T.q[m], nq = 0 - q, q4 = q << 2;
     u64 e[R1];
 #pragma unroll
     for (int k = 0; k < R1; ++k) e[k] = a[(size_t)k * cols];
     ulonglong2 t[R1 - 1];
     load_tw<kRadix1Log>(t, (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N, 1);
     if (FWD) {
-        if (is_wide(q)) ct_block<kRadix1Log, true>(e, t, nq, q2); else ct_block<kRadix1Log, false>(e, t, nq, q2);
+        if (is_wide(q)) ct_block<kRadix1Log, true>(e, t, nq, q4); else ct_block<kRadix1Log, false>(e, t, nq, q4);
 #pragma unroll
-        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 4q (wide) or < 9q (narrow)
+        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 8q (wide) or < 17q (narrow)
     } else {
-        gs_block<kRadix1Log>(e, t, nq, q2);
+        gs_block<kRadix1Log>(e, t, nq, q4);
         const u64 w = post ? post[m] : T.ninv[m], ws = post ? post_sh[m] : T.ninv_sh[m];
 #pragma unroll
         for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = mul_shoup(e[k], w, ws, q);
@@ -176,7 +180,7 @@ struct Rounds {
     // tw: this round's twiddles (already in flight / loaded).  Data: forward round 0 reads global memory directly,
     // inverse last round writes global memory directly; everything else goes through swizzled shared memory.
     __device__ static __forceinline__ void run(u64* __restrict__ a, u64* sm, int tid, u32 chunk, int logN, const ulonglong2* tab,
-                                               ulonglong2* tw, u64 q, u64 nq, u64 q2, u64 qinv64, bool wide) {
+                                               ulonglong2* tw, u64 q, u64 nq, u64 q4, u64 qinv64, bool wide) {
         u64 e[8];
         if constexpr (FWD && FIRST) {
 #pragma unroll
@@ -188,15 +192,15 @@ struct Rounds {
 #pragma unroll
         for (int h = 0; h < G::G; ++h) {
             if (FWD) {
-                if (wide) ct_block<LOG, true>(e + h * G::E, tw + h * G::TW, nq, q2);
-                else ct_block<LOG, false>(e + h * G::E, tw + h * G::TW, nq, q2);
+                if (wide) ct_block<LOG, true>(e + h * G::E, tw + h * G::TW, nq, q4);
+                else ct_block<LOG, false>(e + h * G::E, tw + h * G::TW, nq, q4);
             } else {
-                gs_block<LOG>(e + h * G::E, tw + h * G::TW, nq, q2);
+                gs_block<LOG>(e + h * G::E, tw + h * G::TW, nq, q4);
             }
         }
         if constexpr (FWD && LAST) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) e[k] = wide ? final_reduce<true>(e[k], q, q2, nq, qinv64) : final_reduce<false>(e[k], q, q2, nq, qinv64);
+            for (int k = 0; k < 8; ++k) e[k] = wide ? final_reduce<true>(e[k], q, q4, nq, qinv64) : final_reduce<false>(e[k], q, q4, nq, qinv64);
         }
         if constexpr (!LAST) {
             // prefetch the next round's twiddles so their L2 latency overlaps the exchange and the barrier
@@ -204,13 +208,13 @@ struct Rounds {
         }
         if constexpr (!FWD && LAST) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) a[tid + k * S::NT] = e[k];    // lazy < 2q, consumed by the column pass
+            for (int k = 0; k < 8; ++k) a[tid + k * S::NT] = e[k];    // lazy < 4q, consumed by the column pass
         } else {
 #pragma unroll
             for (int h = 0; h < G::G; ++h) sts_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
             __syncthreads();
         }
-        if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q2, qinv64, wide);
+        if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q4, qinv64, wide);
     }
 };
 
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kern
     const int limb = blockIdx.y, m = sel.m[limb], tid = threadIdx.x;
     const u32 chunk = blockIdx.x;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + (size_t)chunk * C;
-    const u64 q = T.q[m], nq = 0 - q, q2 = q << 1, qinv64 = T.mu_hi[m];
+    const u64 q = T.q[m], nq = 0 - q, q4 = q << 2, qinv64 = T.mu_hi[m];
     const bool wide = is_wide(q);
     const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
     ulonglong2 tw[7];
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kern
         copy_in<S2, 0>(sm, a, tid, SBase(tid));
         __syncthreads();
     }
-    Rounds<S2, FWD, 0>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q2, qinv64, wide);
+    Rounds<S2, FWD, 0>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, wide);
     if constexpr (FWD) copy_out<S2, 0>(a, sm, tid, SBase(tid));
 }
 

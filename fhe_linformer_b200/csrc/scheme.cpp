@@ -128,11 +128,56 @@ Scheme::~Scheme() {
     } catch (...) {}
 }
 
-Elem Scheme::make(int ncomp, int l, int deg, double scale, int slots) {
+Elem Scheme::make(int ncomp, int l, int deg, double scale, int slots, int batch) {
     Elem e;
-    e.mem = std::make_shared<DevMem>(&eng, (size_t)ncomp * l * P.N);
-    e.ncomp = ncomp; e.l = l; e.deg = deg; e.scale = scale; e.slots = slots;
+    e.mem = std::make_shared<DevMem>(&eng, (size_t)batch * ncomp * l * P.N);
+    e.batch = batch; e.ncomp = ncomp; e.l = l; e.deg = deg; e.scale = scale; e.slots = slots;
     return e;
+}
+
+Elem Scheme::slice(const Elem& a, int i) const {
+    if (i < 0 || i >= a.batch) throw std::out_of_range("batch slice out of range");
+    Elem e = a;
+    e.off = a.off + (size_t)i * a.words_each(P.N);
+    e.batch = 1;
+    return e;
+}
+
+Elem Scheme::pack(const std::vector<Elem>& v) {
+    if (v.empty()) throw std::invalid_argument("pack: empty input");
+    const Elem& f = v[0];
+    size_t total = 0;
+    bool contiguous = true;
+    for (const Elem& e : v) {
+        if (e.ncomp != f.ncomp || e.l != f.l || e.deg != f.deg || e.scale != f.scale || e.slots != f.slots)
+            throw std::invalid_argument("pack: ciphertexts differ in level, degree or scale");
+        contiguous = contiguous && e.mem == f.mem && e.off == f.off + total * f.words_each(P.N);
+        total += e.batch;
+    }
+    if (contiguous) {   // slices of one batch, in order: a view is enough
+        Elem r = f;
+        r.batch = (int)total;
+        return r;
+    }
+    Elem r = make(f.ncomp, f.l, f.deg, f.scale, f.slots, (int)total);
+    size_t at = 0;
+    for (const Elem& e : v) {
+        eng.copy(r.data() + at, e.data(), e.batch * e.words_each(P.N));
+        at += e.batch * e.words_each(P.N);
+    }
+    return r;
+}
+
+int Scheme::max_batch(int l) const {
+    const double per = (double)(l + P.beta(l) * (l + P.K) + 2 * (l + P.K) + 2 * l + 4 * l) * P.N * 8.0;   // key-switch workspace + in/out
+    return std::max(1, std::min(64, (int)(6.0e9 / per)));
+}
+
+// run a single-ciphertext routine over every element of a batched operand
+std::vector<Elem> Scheme::split_run(const Elem& a, const std::function<Elem(const Elem&)>& f) {
+    std::vector<Elem> out;
+    for (int i = 0; i < a.batch; ++i) out.push_back(f(slice(a, i)));
+    return out;
 }
 
 // ---------------------------------------------------------------- keys
@@ -358,6 +403,7 @@ Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) {
 Elem Scheme::encrypt(const Elem& pt) { return encrypt_seeded(pt, SplitMix::sub(key_seed_, 0xE0000 + (seed_counter++))); }
 
 void Scheme::decrypt(const Elem& ct_in, cplx* out, int slots) {
+    if (ct_in.batch != 1) throw std::invalid_argument("Decrypt: take a slice of the batched ciphertext first");
     if (!sk_) throw std::runtime_error("Decrypt: no secret key");
     Elem ct = ct_in;
     if (ct.deg >= 2 && ct.l >= 2) rescale_inplace(ct);      // bring the message under two limbs before decoding
@@ -371,24 +417,25 @@ void Scheme::decrypt(const Elem& ct_in, cplx* out, int slots) {
 
 // ---------------------------------------------------------------- level / scale plumbing
 Elem Scheme::clone(const Elem& a) {
-    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
-    eng.copy(r.data(), a.data(), (size_t)a.ncomp * a.l * P.N);
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots, a.batch);
+    eng.copy(r.data(), a.data(), (size_t)a.batch * a.words_each(P.N));
     return r;
 }
 
 void Scheme::drop_to(Elem& a, int l) {
     if (l == a.l) return;
     if (l > a.l || l < 1) throw std::invalid_argument("LevelReduce: bad target");
-    Elem r = make(a.ncomp, l, a.deg, a.scale, a.slots);
-    for (int c = 0; c < a.ncomp; ++c) eng.copy(r.data() + (size_t)c * l * P.N, a.data() + (size_t)c * a.l * P.N, (size_t)l * P.N);
+    Elem r = make(a.ncomp, l, a.deg, a.scale, a.slots, a.batch);
+    FLK_CUDA(cudaMemcpy2DAsync(r.data(), (size_t)l * P.N * 8, a.data(), (size_t)a.l * P.N * 8, (size_t)l * P.N * 8, (size_t)a.ncomp * a.batch,
+                               cudaMemcpyDeviceToDevice, eng.stream));
     a = r;
 }
 void Scheme::level_reduce_inplace(Elem& a, int levels) { if (levels > 0) drop_to(a, a.l - levels); }
 
 void Scheme::rescale_inplace(Elem& a) {
     if (a.l < 2) throw std::runtime_error("rescale: ciphertext is at the last level");
-    Elem r = make(a.ncomp, a.l - 1, a.deg - 1, a.scale / (double)P.q[a.l - 1], a.slots);
-    eng.rescale(r.data(), a.data(), a.l, a.ncomp);
+    Elem r = make(a.ncomp, a.l - 1, a.deg - 1, a.scale / (double)P.q[a.l - 1], a.slots, a.batch);
+    eng.rescale(r.data(), a.data(), a.l, a.ncomp * a.batch);
     a = r;
 }
 Elem Scheme::rescaled(const Elem& a) { Elem r = a; rescale_inplace(r); return r; }
@@ -404,8 +451,8 @@ ScalarSet Scheme::scalar_set(i128 k, int l) const {
 }
 
 void Scheme::mult_int_inplace(Elem& a, i128 k) {
-    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
-    launch_mul_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), a.ncomp, eng.stream);
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots, a.batch);
+    launch_mul_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), a.ncomp * a.batch, eng.stream);
     a = r;
 }
 
@@ -472,18 +519,21 @@ void Scheme::adjust_pair_to_one(Elem& a, Elem& b) {
 Elem Scheme::binary(const Elem& a_in, const Elem& b_in, bool subtract) {
     if (a_in.ncomp == 1 && b_in.ncomp == 2 && !subtract) return binary(b_in, a_in, false);
     if (a_in.ncomp < b_in.ncomp) throw std::invalid_argument("EvalSub(plaintext, ciphertext) is not supported");
+    if (a_in.batch == 1 && b_in.batch > 1 && !subtract) return binary(b_in, a_in, false);
+    if (b_in.batch != 1 && b_in.batch != a_in.batch) throw std::invalid_argument("EvalAdd: batch sizes differ");
     Elem a = a_in, b = b_in;
     adjust_pair(a, b);
-    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
-    const size_t pl = (size_t)a.l * P.N;
+    Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots, a.batch);
+    const size_t pl = (size_t)a.l * P.N, ca = a.ncomp * pl;
     const LimbSel sel = sel_range(0, a.l);
-    if (b.ncomp == a.ncomp) {
-        launch_ew(eng.T, subtract ? EwOp::Sub : EwOp::Add, r.data(), a.data(), b.data(), sel, a.ncomp, 1, 0, 0, pl, eng.stream);
-    } else {
-        launch_ew(eng.T, subtract ? EwOp::Sub : EwOp::Add, r.data(), a.data(), b.data(), sel, 1, 1, 0, 0, 0, eng.stream);
-        eng.copy(r.data() + pl, a.data() + pl, pl * (a.ncomp - 1));
+    const EwOp op = subtract ? EwOp::Sub : EwOp::Add;
+    if (b.ncomp == a.ncomp) {   // batch b against batch b, or one operand broadcast over the batch
+        launch_ew(eng.T, op, r.data(), a.data(), b.data(), sel, a.ncomp, a.batch, ca, b.batch > 1 ? ca : 0, pl, eng.stream);
+    } else {                    // ciphertext + plaintext: only c0 changes
+        launch_ew(eng.T, op, r.data(), a.data(), b.data(), sel, 1, a.batch, ca, 0, 0, eng.stream);
+        FLK_CUDA(cudaMemcpy2DAsync(r.data() + pl, ca * 8, a.data() + pl, ca * 8, pl * (a.ncomp - 1) * 8, a.batch, cudaMemcpyDeviceToDevice, eng.stream));
     }
-    if (eng.ledger_on) eng.ledger.add("add", a.l, 48.0 * P.N * a.l);
+    if (eng.ledger_on) eng.ledger.add("add", a.l, 48.0 * P.N * a.l, a.batch);
     return r;
 }
 Elem Scheme::add(const Elem& a, const Elem& b) { return binary(a, b, false); }
@@ -499,6 +549,7 @@ Elem Scheme::add_many(std::vector<Elem> v) {
 
 Elem Scheme::add_const(const Elem& a, double c) {
     // constant polynomial round(c * scale): every evaluation-format entry of c0 receives the same residue
+    if (a.batch > 1) return pack(split_run(a, [&](const Elem& e) { return add_const(e, c); }));
     const i128 k = (i128)std::rint(c * a.scale);
     Elem r = clone(a);
     launch_add_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), eng.stream);
@@ -508,15 +559,22 @@ Elem Scheme::add_const(const Elem& a, double c) {
 Elem Scheme::mult(const Elem& a_in, const Elem& b_in) {
     if (a_in.ncomp == 1 && b_in.ncomp == 2) return mult(b_in, a_in);
     if (a_in.ncomp != 2) throw std::invalid_argument("EvalMult: ciphertext expected");
+    if (a_in.batch == 1 && b_in.batch > 1) return mult(b_in, a_in);
+    if (b_in.ncomp == 2 && a_in.batch > 1) {   // ciphertext x ciphertext has no batched kernel path: element by element
+        std::vector<Elem> out;
+        for (int i = 0; i < a_in.batch; ++i) out.push_back(mult(slice(a_in, i), b_in.batch > 1 ? slice(b_in, i) : b_in));
+        return pack(out);
+    }
     Elem a = a_in, b = b_in;
     adjust_pair_to_one(a, b);
-    Elem r = make(2, a.l, a.deg + b.deg, a.scale * b.scale, a.slots);
+    Elem r = make(2, a.l, a.deg + b.deg, a.scale * b.scale, a.slots, a.batch);
     if (b.ncomp == 2) {
         if (!mk_) throw std::runtime_error("EvalMult: relinearisation key missing");
         eng.mul_relin(r.data(), a.data(), b.data(), a.l, mk_);
     } else {
-        eng.ew(EwOp::Mul, r.data(), a.data(), b.data(), a.l, 2, true);
-        if (eng.ledger_on) eng.ledger.add("mul_plain", a.l, 40.0 * P.N * a.l);
+        const size_t pl = (size_t)a.l * P.N;
+        launch_ew(eng.T, EwOp::Mul, r.data(), a.data(), b.data(), sel_range(0, a.l), 2, a.batch, 2 * pl, 0, 0, eng.stream);
+        if (eng.ledger_on) eng.ledger.add("mul_plain", a.l, 40.0 * P.N * a.l, a.batch);
     }
     return r;
 }
@@ -546,8 +604,11 @@ Elem Scheme::apply_galois(const Elem& a, uint32_t g) {
     if (a.ncomp != 2) throw std::invalid_argument("EvalAutomorphism: ciphertext expected");
     auto it = gk_.find(g);
     if (it == gk_.end()) throw std::runtime_error("EvalAutomorphism: no evaluation key for Galois element " + std::to_string(g));
-    Elem r = make(2, a.l, a.deg, a.scale, a.slots);
-    eng.rotate(r.data(), a.data(), a.l, g, it->second);
+    Elem r = make(2, a.l, a.deg, a.scale, a.slots, a.batch);
+    for (int b0 = 0, mb = max_batch(a.l); b0 < a.batch; b0 += mb) {
+        const size_t o = (size_t)b0 * a.words_each(P.N);
+        eng.rotate_batch(r.data() + o, a.data() + o, a.l, g, it->second, std::min(mb, a.batch - b0), false);
+    }
     return r;
 }
 Elem Scheme::rotate(const Elem& a, int k) {
@@ -565,8 +626,11 @@ Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
         const uint32_t g = P.galois_for_rotation(stride * (1 << i));
         auto it = gk_.find(g);
         if (it == gk_.end()) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(stride * (1 << i)));
-        Elem nx = make(2, r.l, r.deg, r.scale, r.slots);
-        eng.rotate_add(nx.data(), r.data(), r.l, g, it->second);
+        Elem nx = make(2, r.l, r.deg, r.scale, r.slots, r.batch);
+        for (int b0 = 0, mb = max_batch(r.l); b0 < r.batch; b0 += mb) {
+            const size_t o = (size_t)b0 * r.words_each(P.N);
+            eng.rotate_batch(nx.data() + o, r.data() + o, r.l, g, it->second, std::min(mb, r.batch - b0), true);
+        }
         r = nx;
     }
     return steps == 0 ? clone(a) : r;

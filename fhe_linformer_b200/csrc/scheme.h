@@ -3,6 +3,7 @@
 // `CryptoContext<DCRTPoly> context` (FHEController.h:23); every public method names the OpenFHE call it replaces.
 #pragma once
 #include <complex>
+#include <functional>
 #include <map>
 #include <memory>
 #include <vector>
@@ -24,14 +25,20 @@ struct DevMem {   // stream-ordered HBM allocation, returned to the engine pool 
 using Mem = std::shared_ptr<DevMem>;
 
 // Ciphertext (ncomp = 2) or plaintext (ncomp = 1): ncomp polynomials of l limbs, evaluation format.
+// batch > 1: that many ciphertexts with identical metadata stored back to back ([batch][ncomp][l][N]); the leveled
+// operations below treat them as one operand (one kernel launch per stage for the whole batch) -- this is how the
+// independent row ciphertexts of the reference's `for (i < rows.size())` loops (F.cpp:872-1120) share launches.
 struct Elem {
     Mem mem;
+    size_t off = 0;     // first word inside mem (slices of a batch share the allocation)
+    int batch = 1;
     int ncomp = 0;
     int l = 0;          // active Q limbs; GetLevel() = L - l
     int deg = 1;        // noiseScaleDeg
     double scale = 0;   // scalingFactor
     int slots = 0;
-    u64* data() const { return mem->p; }
+    u64* data() const { return mem->p + off; }
+    size_t words_each(int N) const { return (size_t)ncomp * l * N; }
     bool valid() const { return (bool)mem; }
 };
 
@@ -91,6 +98,9 @@ public:
     Elem rotsum(const Elem& a, int steps, int stride);   // FHEController::rotsum / repeat ladders F.cpp:829-867
     Elem apply_galois(const Elem& a, uint32_t g);
     Elem clone(const Elem& a);                        // Ciphertext::Clone M:223
+    Elem pack(const std::vector<Elem>& v);            // gather ciphertexts of identical level / scale into one batched operand
+    Elem slice(const Elem& a, int i) const;           // zero-copy view of element i of a batched operand
+    int max_batch(int l) const;                       // batch size that keeps the key-switch workspace within budget
     Elem rescaled(const Elem& a);                     // ModReduceInternal
     void rescale_inplace(Elem& a);
     void level_reduce_inplace(Elem& a, int levels);   // LevelReduceInternal
@@ -125,7 +135,8 @@ public:
 
 private:
     friend struct BootPrecomp;
-    Elem make(int ncomp, int l, int deg, double scale, int slots);
+    Elem make(int ncomp, int l, int deg, double scale, int slots, int batch = 1);
+    std::vector<Elem> split_run(const Elem& a, const std::function<Elem(const Elem&)>& f);
     void keyswitch_gen(const u64* sk_old_dev, const u64* sk_new_dev, u64 seed, u64* evk_dev);
     void sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSel& sel);
     void uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel);

@@ -442,6 +442,52 @@ Ctxt FHEController::rotsum_padded(const Ctxt& in, int slots) { return ladder(in,
 Ctxt FHEController::repeat(const Ctxt& in, int slots) { return ladder(in, slots, -1); }
 Ctxt FHEController::repeat(const Ctxt& in, int slots, int padding) { return ladder(in, slots, -padding); }
 
+/* ------------------------------------------------------------------ row batching ------------------------------------------------------------------ */
+// The reference walks its row ciphertexts one by one (`for (i < rows.size())`, F.cpp:872-1120) although the iterations are
+// independent.  Here rows of identical level / degree / scale are packed into one batched operand, the per-row recipe
+// runs once on the pack (each engine stage is a single launch for all rows) and the results are handed back as views.
+
+Ctxt FHEController::pack(const vector<Ctxt>& rows) const {
+    if (rows.size() == 1) return rows[0];
+    auto h = handles(rows);
+    fl_elem* e = nullptr;
+    need(fl_batch_pack(ctx_, h.data(), (int)h.size(), &e), "pack");
+    return wrap(e);
+}
+
+vector<Ctxt> FHEController::unpack(const Ctxt& packed) const {
+    const int n = fl_elem_batch(packed->handle());
+    if (n == 1) return {packed};
+    vector<Ctxt> out((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        fl_elem* e = nullptr;
+        need(fl_batch_slice(ctx_, packed->handle(), i, &e), "slice");
+        out[i] = wrap(e);
+    }
+    return out;
+}
+
+vector<Ctxt> FHEController::per_row(const vector<Ctxt>& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const {
+    vector<Ctxt> out(rows.size());
+    if (!batch_rows) {
+        for (size_t i = 0; i < rows.size(); ++i) out[i] = recipe(rows[i]);
+        return out;
+    }
+    auto same = [](const Ctxt& a, const Ctxt& b) {
+        return a->GetLevel() == b->GetLevel() && a->GetNoiseScaleDeg() == b->GetNoiseScaleDeg() && a->GetScalingFactor() == b->GetScalingFactor() &&
+               a->GetSlots() == b->GetSlots();
+    };
+    size_t first = 0;
+    while (first < rows.size()) {
+        size_t last = first + 1;
+        while (last < rows.size() && last - first < (size_t)max_rows_per_batch && same(rows[first], rows[last])) ++last;
+        const vector<Ctxt> part = unpack(recipe(pack(vector<Ctxt>(rows.begin() + first, rows.begin() + last))));
+        for (size_t i = 0; i < part.size(); ++i) out[first + i] = part[i];
+        first = last;
+    }
+    return out;
+}
+
 /* ------------------------------------------------------------------ packed matrix products ------------------------------------------------------------------ */
 // "RE": rows arrive Expanded, weight is the row-major 128x128 matrix, summing over the 128 blocks (stride 128) leaves the
 // product Repeated.  "CR": rows arrive Repeated, summing inside each block (stride 1) leaves product entry j at slot 128 j.
@@ -449,75 +495,64 @@ Ctxt FHEController::repeat(const Ctxt& in, int slots, int padding) { return ladd
 vector<Ctxt> FHEController::matmulRE(vector<Ctxt> rows, const Ptxt& weight, const Ptxt& bias) { return matmulRE(rows, weight, bias, 128, 128); }
 
 vector<Ctxt> FHEController::matmulRE(vector<Ctxt> rows, const Ptxt& weight, const Ptxt& bias, int row_size, int padding) {
-    vector<Ctxt> out;
-    out.reserve(rows.size());
-    for (const Ctxt& r : rows) {
+    return per_row(rows, [&](const Ctxt& r) {
         Ctxt acc = rotsum(mult(r, weight), row_size, padding);
-        out.push_back(bias != nullptr ? add(acc, bias) : acc);
-    }
-    return out;
+        return bias != nullptr ? add(acc, bias) : acc;
+    });
 }
 
 vector<Ctxt> FHEController::matmulRE(vector<Ctxt> rows, const Ctxt& weight, int row_size, int padding) {
-    vector<Ctxt> out;
-    out.reserve(rows.size());
-    for (const Ctxt& r : rows) out.push_back(rotsum(mult(r, weight), row_size, padding));
-    return out;
+    return per_row(rows, [&](const Ctxt& r) { return rotsum(mult(r, weight), row_size, padding); });
 }
 
 // 128 -> 512: four 128x128 blocks, each product masked to its first 128 slots and shifted into place by two rotations of
 // -64 (the reference's stand-in for -128, F.cpp:930-931); block 3 is produced first and ends up highest.
 vector<Ctxt> FHEController::matmulRElarge(vector<Ctxt>& rows, const vector<Ptxt>& weight, const Ptxt& bias, double mask_value) {
-    vector<Ctxt> out;
-    out.reserve(rows.size());
     const int nb = (int)weight.size();
-    for (const Ctxt& r : rows) {
+    return per_row(rows, [&](const Ctxt& r) {
         Ctxt acc;
         for (int j = nb - 1; j >= 0; --j) {
             Ctxt part = mask_first_n(rotsum(mult(r, weight[j]), 128, 128), 128, mask_value);
             if (j == nb - 1) acc = part;
             else acc = add(rotate(rotate(acc, -64), -64), part);
         }
-        out.push_back(add(acc, bias));
-    }
-    return out;
+        return add(acc, bias);
+    });
 }
 
 vector<Ctxt> FHEController::matmulCR(vector<Ctxt> rows, const Ptxt& weight, const Ptxt& bias) {
-    vector<Ctxt> out;
-    out.reserve(rows.size());
-    for (const Ctxt& r : rows) {
+    return per_row(rows, [&](const Ctxt& r) {
         Ctxt acc = rotsum(mult(r, weight), 128, 1);
-        out.push_back(bias != nullptr ? add(acc, bias) : acc);
-    }
-    return out;
+        return bias != nullptr ? add(acc, bias) : acc;
+    });
 }
 
 vector<Ctxt> FHEController::matmulCR(vector<Ctxt> rows, const Ctxt& matrix) {
-    vector<Ctxt> out;
-    for (const Ctxt& r : rows) out.push_back(rotsum(mult(r, matrix), 64, 1));
-    return out;
+    return per_row(rows, [&](const Ctxt& r) { return rotsum(mult(r, matrix), 64, 1); });
 }
 
 Ctxt FHEController::matmulCR_128(Ctxt row, const Ctxt& matrix) { return rotsum(mult(row, matrix), 128, 1); }
 
 vector<Ctxt> FHEController::matmulCR_128(vector<Ctxt> rows, const Ctxt& matrix) {
-    vector<Ctxt> out;
-    for (const Ctxt& r : rows) out.push_back(matmulCR_128(r, matrix));
-    return out;
+    return per_row(rows, [&](const Ctxt& r) { return matmulCR_128(r, matrix); });
 }
 
 // 512 -> 128: the four block products are summed first, then one stride-1 ladder (F.cpp:998-1026)
 vector<Ctxt> FHEController::matmulCRlarge(vector<vector<Ctxt>> rows, vector<Ptxt> weights, const Ptxt& bias) {
-    vector<Ctxt> out;
-    out.reserve(rows.size());
-    for (const vector<Ctxt>& quad : rows) {
-        vector<Ctxt> parts;
-        for (int b = 0; b < 4; ++b) parts.push_back(mult(quad[b], weights[b]));
+    // per_row over the row index, with the four block operands of a row travelling together
+    vector<Ctxt> index(rows.size());
+    vector<vector<Ctxt>> column(4, vector<Ctxt>(rows.size()));
+    for (size_t i = 0; i < rows.size(); ++i)
+        for (int b = 0; b < 4; ++b) column[b][i] = rows[i][b];
+    size_t at = 0;   // per_row hands out contiguous, ordered groups of column[0]; the other columns are cut the same way
+    return per_row(column[0], [&](const Ctxt& first) {
+        const size_t n = (size_t)fl_elem_batch(first->handle());
+        vector<Ctxt> parts = {mult(first, weights[0])};
+        for (int b = 1; b < 4; ++b) parts.push_back(mult(pack(vector<Ctxt>(column[b].begin() + at, column[b].begin() + at + n)), weights[b]));
+        at += n;
         Ctxt acc = rotsum(add(parts), 128, 1);
-        out.push_back(bias != nullptr ? add(acc, bias) : acc);
-    }
-    return out;
+        return bias != nullptr ? add(acc, bias) : acc;
+    });
 }
 
 // scores of up to 128 queries against the wrapped keys; each query's 128 scores sit at slots 128 j and are scaled by
@@ -560,23 +595,27 @@ Ctxt FHEController::wrapUpExpanded(vector<Ctxt> vectors) {
 
 // inverse of wrapUpExpanded: vector t comes back Expanded (entry j replicated over block j)
 vector<Ctxt> FHEController::unwrapExpanded(Ctxt c, int inputs_num) {
-    vector<Ctxt> out;
-    out.reserve(inputs_num);
+    // the rotate(c, 1) chain is sequential; the 7-step replication ladders of the picked columns are independent
+    vector<Ctxt> picked;
+    picked.reserve(inputs_num);
     for (int t = 0; t < inputs_num; ++t) {
-        out.push_back(repeat(mask_mod_n(c, 128, 0, inputs_num * 128), 128));
+        picked.push_back(mask_mod_n(c, 128, 0, inputs_num * 128));
         if (t < inputs_num - 1) c = rotate(c, 1);
     }
-    return out;
+    return per_row(picked, [&](const Ctxt& r) { return repeat(r, 128); });
 }
 
 vector<Ctxt> FHEController::unwrapScoresExpanded(Ctxt c, int inputs_num) {
-    vector<Ctxt> out;
+    vector<Ctxt> lo, hi;
     for (int t = 0; t < inputs_num; ++t) {
-        Ctxt lo = repeat(mask_mod_n(c, 128, 0, inputs_num * 128), 64);
-        Ctxt hi = repeat(mask_mod_n(c, 128, 64, inputs_num * 128), 64);
+        lo.push_back(mask_mod_n(c, 128, 0, inputs_num * 128));
+        hi.push_back(mask_mod_n(c, 128, 64, inputs_num * 128));
         if (t < inputs_num - 1) c = rotate(c, 1);
-        out.push_back(add(lo, hi));
     }
+    lo = per_row(lo, [&](const Ctxt& r) { return repeat(r, 64); });
+    hi = per_row(hi, [&](const Ctxt& r) { return repeat(r, 64); });
+    vector<Ctxt> out;
+    for (int t = 0; t < inputs_num; ++t) out.push_back(add(lo[t], hi[t]));
     return out;
 }
 
@@ -591,11 +630,16 @@ vector<Ctxt> FHEController::unwrap_512_in_4_128(const Ctxt& c, int index) {
 }
 
 vector<vector<Ctxt>> FHEController::unwrapRepeatedLarge(vector<Ctxt> containers, int input_number) {
-    vector<vector<Ctxt>> out;
+    // every (token, 128-block) ladder of unwrap_512_in_4_128 is independent: mask them all, replicate them as batches
+    vector<Ctxt> blocks;
     for (size_t i = 0; i < containers.size(); ++i) {
         const int held = std::min(32, input_number - 32 * (int)i);
-        for (int j = 0; j < held; ++j) out.push_back(unwrap_512_in_4_128(containers[i], j));
+        for (int j = 0; j < held; ++j)
+            for (int b = 0; b < 4; ++b) blocks.push_back(mask_block(containers[i], j * 512 + 128 * b, j * 512 + 128 * (b + 1), 1));
     }
+    blocks = per_row(blocks, [&](const Ctxt& r) { return repeat(r, 128, -128); });
+    vector<vector<Ctxt>> out;
+    for (size_t i = 0; i + 3 < blocks.size(); i += 4) out.push_back({blocks[i], blocks[i + 1], blocks[i + 2], blocks[i + 3]});
     return out;
 }
 

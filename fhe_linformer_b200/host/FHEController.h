@@ -148,6 +148,12 @@ public:
     Ctxt chebyshev(const std::function<double(double)>& f, const Ctxt& c, double a, double b, int degree);
     Ctxt ladder(const Ctxt& in, int slots, int stride);   // shared body of rotsum / rotsum_padded / repeat
     Ctxt adopt(fl_elem* e) const;                          // take ownership of a raw C-ABI handle
+    // row batching (FHEController.cpp "row batching"): independent rows share kernel launches
+    bool batch_rows = true;
+    int max_rows_per_batch = 256;
+    Ctxt pack(const vector<Ctxt>& rows) const;
+    vector<Ctxt> unpack(const Ctxt& packed) const;
+    vector<Ctxt> per_row(const vector<Ctxt>& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const;
 
 private:
     void create(int log_ring, int depth, int digits, int first_bits, int scale_bits);

@@ -70,12 +70,15 @@ int fl_raw_modup(fl_ctx* c, uint64_t* out_ext, const uint64_t* c_eval, int l, in
 int fl_raw_moddown(fl_ctx* c, uint64_t* out, const uint64_t* in_ext, int l);                /* ApproxModDown */
 int fl_raw_keyswitch(fl_ctx* c, uint64_t* out2 /* [2][l][N] */, const uint64_t* poly, const uint64_t* evk, int l);   /* KeySwitch (HYBRID) */
 int fl_raw_rotate(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uint32_t g, const uint64_t* evk);   /* EvalRotate F.cpp:435,833,843 */
+/* the same for `batch` ciphertexts stored back to back ([batch][2][l][N]) and one key: every stage is one launch */
+int fl_raw_rotate_batch(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uint32_t g, const uint64_t* evk, int batch);
 int fl_raw_mul_relin(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, int l, const uint64_t* evk);   /* EvalMult(ct,ct) F.cpp:431 */
 int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_t* pt, int l);   /* EvalMult(ct,pt) F.cpp:427 */
 
 /* ---- the same operations with HOST buffers: H2D copy, kernels, D2H copy (what a host-resident caller pays) ---- */
 int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse);
 int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev);
+int fl_host_rotate_batch(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch);
 int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev);
 
 /* ================= scheme level: what FHEController's methods call on `context` ================= */
@@ -140,6 +143,12 @@ int fl_elem_slots(const fl_elem* a);
 int fl_elem_ncomp(const fl_elem* a);
 double fl_elem_scale(const fl_elem* a);
 int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out);
+/* Batched operands: n ciphertexts of identical level / degree / scale stored back to back.  fl_add / fl_mul (ct x pt) /
+ * fl_rotate / fl_rotsum / fl_rescale accept a batched ciphertext and launch once per stage for the whole batch: the
+ * independent iterations of the reference's `for (i < rows.size())` loops (F.cpp:872-1120) share kernel launches. */
+int fl_batch_pack(fl_ctx* c, fl_elem* const* v, int n, fl_elem** out);
+int fl_batch_slice(fl_ctx* c, const fl_elem* a, int i, fl_elem** out);   /* zero-copy view of element i */
+int fl_elem_batch(const fl_elem* a);
 void fl_elem_free(fl_elem* a);
 int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host /* ncomp * limbs * N */);
 int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int deg, double scale, int slots, fl_elem** out);

@@ -1,22 +1,28 @@
-"""Summarise an .ncu-rep (raw page) into the handful of numbers DESIGN.md / profiles/ quote."""
-import csv, subprocess, sys
-rep = sys.argv[1]
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-hdr, units, data = rows[0], rows[1], rows[2:]
-want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "smsp__inst_executed.sum",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
-want += [h for h in hdr if "issue_stalled" in h and "per_issue_active" in h and "not_issued" not in h]
-for w in want:
-    if w in hdr:
-        i = hdr.index(w)
-        vals = [r[i] for r in data]
-        if "issue_stalled" in w:
-            if max(float(v or 0) for v in vals) < 0.15: continue
-            w = w.replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active.ratio", "")
-        print(f"{w} [{units[i]}]: {vals}")
+"""Summarise an ncu --csv metrics log per kernel: count, total/avg duration, share, and any extra metrics averaged."""
+import collections, csv, sys
+rows = list(csv.reader(open(sys.argv[1], errors="ignore")))
+hdr = None
+per = collections.OrderedDict()
+for r in rows:
+    if "Kernel Name" in r:
+        hdr = r; continue
+    if not hdr or len(r) != len(hdr):
+        continue
+    d = dict(zip(hdr, r))
+    name = d["Kernel Name"].split("(")[0].replace("void ", "").replace("unnamed>::", "").replace("flk::", "")
+    tmpl = d["Kernel Name"].split("(")[0]
+    name = tmpl.split("::")[-1]
+    key = (name, d["Grid Size"], d["Block Size"])
+    try:
+        v = float(d["Metric Value"].replace(",", ""))
+    except ValueError:
+        continue
+    per.setdefault(key, collections.defaultdict(list))[d["Metric Name"]].append(v)
+tot = sum(sum(m.get("gpu__time_duration.sum", [0])) for m in per.values())
+print("%-44s %-16s %5s %9s %6s  %s" % ("kernel", "grid", "n", "avg us", "share", "other metrics (avg)"))
+for (name, grid, blk), m in sorted(per.items(), key=lambda kv: -sum(kv[1].get("gpu__time_duration.sum", [0]))):
+    t = m.get("gpu__time_duration.sum", [0])
+    unit = 1e3  # ns -> us
+    others = "  ".join("%s=%.3g" % (k.replace("__", ".").split(".")[-2] + "." + k.split(".")[-1] if False else k, sum(v) / len(v)) for k, v in m.items() if k != "gpu__time_duration.sum")
+    print("%-44s %-16s %5d %9.1f %5.1f%%  %s" % (name[:44], grid.replace(" ", ""), len(t), sum(t) / len(t) / unit, 100 * sum(t) / tot if tot else 0, others))
+print("total %.1f us" % (tot / 1e3))

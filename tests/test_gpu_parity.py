@@ -176,3 +176,19 @@ def test_full_size_properties_N65536():
     evk = o.gen_galois_key(4, sk, gp)
     assert (r1.download() == o.rotate(ct, gp, evk)).all()
     e.close()
+
+
+def test_batched_rotation_equals_single(pair):
+    """A batch of ciphertexts through one batched key switch gives, per ciphertext, the oracle's limbs."""
+    o, e = pair
+    rng = np.random.default_rng(21)
+    sk = o.gen_sk(3, h=64)
+    g = o.galois(5)
+    evk = o.gen_galois_key(9, sk, g)
+    d_evk = e.to_dev(evk)
+    for l in sorted({o.L, max(1, o.L - 2)}):
+        cts = np.stack([rnd_ct(o, rng, l) for _ in range(5)])        # 5 is not a multiple of the 4-wide inner-product group
+        got = e.rotate_batch(e.to_dev(cts), g, d_evk).download()
+        for b in range(5):
+            assert (got[b] == o.rotate(cts[b], g, evk)).all(), (l, b)
+        assert (e.host_rotate_batch(cts, g, d_evk) == got).all()
