@@ -212,6 +212,13 @@ def run_b200(a):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes per launch of the same kernel pair from the committed ncu capture (scaled to this limb count)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["ntt_pass_pair_2x28_limbs_per_ciphertext"]
+        if a.logN == 16:
+            traffic = tj["dram_bytes_per_launch"] * l / 28.0
+    except Exception:
+        pass
     rot_bytes = algorithmic_bytes_rotate(N, l, e.K, e.alpha)
     rot_gbs = rot_bytes * value / world / 1e9
     for s in scratch:
@@ -263,7 +270,7 @@ def run_b200(a):
             "config": {"workload": f"EvalRotate N=2^{a.logN} l={l} K={e.K} dnum={e.dnum} (BASELINE.json configs[1])", "batch_per_gpu": B,
                        "parallelism": f"ciphertext-parallel x{world}", "ciphertexts_per_launch": G, "l2": f"inputs larger than L2 ({B * 2 * 2 * l * N * 8 / 1e6:.0f} MB touched per step)"},
             "roofline": {"bound": "hbm", "kernel": "ntt pass pair (ntt_column_kernel + ntt_chunk_kernel)", "achieved": ntt_gbs, "peak": peak,
-                         "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ntt_bytes, "avg_launch_ms": ntt_ms},
             "rotate_roofline": {"algorithmic_bytes_per_rotation": rot_bytes, "achieved": rot_gbs, "unit": "GB/s", "frac": rot_gbs / peak},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 2 * l * N * 8, "d2h_bytes_per_step": B * 2 * l * N * 8,

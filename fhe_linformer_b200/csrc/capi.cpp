@@ -130,15 +130,7 @@ int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l
     })
 }
 int fl_host_rotate_batch(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch) {
-    FL_TRY({
-        Engine& e = *c->eng;
-        const size_t w = (size_t)batch * 2 * l * e.P.N;
-        u64* in = e.alloc(w); u64* out = e.alloc(w);
-        e.upload(in, ct_host, w);
-        e.rotate_batch(out, in, l, g, evk_dev, batch, false);
-        e.download(out_host, out, w);
-        e.release(in); e.release(out);
-    })
+    FL_TRY(c->eng->rotate_batch_host(out_host, ct_host, l, g, evk_dev, batch, 2))
 }
 int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev) {
     FL_TRY({

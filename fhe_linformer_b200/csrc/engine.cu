@@ -97,6 +97,8 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     for (auto& kv : maps_) cudaFree(kv.second);
     for (void* p : owned_) cudaFree(p);
+    if (h2d_stream) cudaStreamDestroy(h2d_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
     cudaStreamDestroy(stream);
 }
 
@@ -244,6 +246,49 @@ void Engine::rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64*
         ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B);
         if (accumulate) ledger.add("add", l, 48.0 * l * P.N, B);
     }
+}
+
+// Host-resident caller (the reference keeps ciphertexts in host memory): chunk c+1 is uploaded while chunk c is key
+// switched and chunk c-1 is downloaded, so a PCIe-bound call costs max(H2D, D2H, compute) instead of their sum.
+void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk) {
+    if (B <= 0) return;
+    if (!h2d_stream) {
+        FLK_CUDA(cudaStreamCreateWithFlags(&h2d_stream, cudaStreamNonBlocking));
+        FLK_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    }
+    chunk = std::max(1, std::min(chunk, B));
+    const size_t cs = (size_t)2 * l * P.N;
+    u64* in = alloc(cs * B);
+    u64* out = alloc(cs * B);
+    automorph_map(g);   // table upload (first use of g) happens before the pipeline starts
+    ks_level(l);
+    cudaEvent_t ready;
+    FLK_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    FLK_CUDA(cudaEventRecord(ready, stream));             // the stream-ordered allocations above are valid from here on
+    FLK_CUDA(cudaStreamWaitEvent(h2d_stream, ready, 0));
+    const int nch = (B + chunk - 1) / chunk;
+    std::vector<cudaEvent_t> up(nch), done(nch);
+    for (int c = 0; c < nch; ++c) {
+        FLK_CUDA(cudaEventCreateWithFlags(&up[c], cudaEventDisableTiming));
+        FLK_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+        FLK_CUDA(cudaMemcpyAsync(in + b0 * cs, ct_host + b0 * cs, cs * nb * 8, cudaMemcpyHostToDevice, h2d_stream));
+        FLK_CUDA(cudaEventRecord(up[c], h2d_stream));
+        FLK_CUDA(cudaStreamWaitEvent(stream, up[c], 0));
+        rotate_batch(out + b0 * cs, in + b0 * cs, l, g, evk, nb, false);
+        FLK_CUDA(cudaEventRecord(done[c], stream));
+        FLK_CUDA(cudaStreamWaitEvent(d2h_stream, done[c], 0));
+        FLK_CUDA(cudaMemcpyAsync(out_host + b0 * cs, out + b0 * cs, cs * nb * 8, cudaMemcpyDeviceToHost, d2h_stream));
+    }
+    FLK_CUDA(cudaEventRecord(ready, d2h_stream));
+    FLK_CUDA(cudaStreamWaitEvent(stream, ready, 0));      // buffers are released only after the last download
+    release(in); release(out);
+    FLK_CUDA(cudaStreamSynchronize(d2h_stream));
+    FLK_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < nch; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(done[c]); }
+    cudaEventDestroy(ready);
 }
 
 void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) {

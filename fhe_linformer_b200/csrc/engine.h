@@ -40,6 +40,7 @@ public:
     const Params P;
     DevTables T{};
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-operand pipeline (created on first use)
     OpLedger ledger;
     bool ledger_on = false;
 
@@ -62,6 +63,8 @@ public:
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
     void keyswitch(const KsBatch& io, const u64* evk, uint32_t g);
     void rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64* evk, int B, bool accumulate);   // ct, out: [B][2][l][N]
+    // the same with HOST operands: uploads, key switches and downloads of successive chunks overlap on three streams
+    void rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk);
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
     void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);

@@ -27,7 +27,7 @@ using namespace dev;
 __device__ __forceinline__ bool is_wide(u64 q) { return (q >> 56) != 0; }
 
 // a*w - qhat*q with qhat in [floor(a*ws/2^64) - 2, floor(a*ws/2^64)], as fused multiply-adds with nq = -q: result in [0,4q)
-__device__ __forceinline__ u64 shoup_nq(u64 a, u64 w, u64 ws, u64 nq) { return a * w + mulhi_lazy(a, ws) * nq; }
+__device__ __forceinline__ u64 shoup_nq(u64 a, u64 w, u64 ws, u64 nq) { return shoup_lazy4(a, w, ws, nq); }
 
 // forward: x,y < B  ->  < B + 4q  (narrow limbs: no reduction at all; wide limbs: B = 8q kept by one conditional subtraction)
 template <bool WIDE>
