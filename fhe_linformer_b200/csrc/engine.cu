@@ -4,6 +4,7 @@
 // SURVEY.md Appendix A.5-A.7.
 #include "engine.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace flk {
@@ -34,6 +35,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     uint64_t keep = ~0ull;
     FLK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 
+    if (const char* ev = std::getenv("FLK_L2_BUDGET_MB")) l2_budget_bytes = std::atol(ev) << 20;   // tuning knob (bench sweeps it)
     const int Tn = P.T, N = P.N;
     {   // twiddles interleaved with their Shoup companions so one 16-byte load fetches both
         std::vector<u64> tw(N), tws(N), itw(N), itws(N);
@@ -184,6 +186,14 @@ void Engine::rescale(u64* out, const u64* in, int l, int polys) {
     if (ledger_on) ledger.add("rescale", l, (32.0 * l - 16.0) * N, polys / 2 > 0 ? polys / 2 : 1);
 }
 
+// Forward NTT of a batch in sub-batches small enough that the first pass's output is still in L2 (126 MB) when the second
+// pass reads it: the transform is latency-bound, and an L2 hit costs less than half of an HBM access.
+void Engine::ntt_l2(u64* data, const LimbSel& sel, int batch, size_t bs) {
+    const size_t per = (size_t)sel.n * P.N * 8;
+    int sub = (int)std::max<size_t>(1, (size_t)l2_budget_bytes / std::max<size_t>(per, 1));
+    for (int b0 = 0; b0 < batch; b0 += sub) launch_ntt(T, data + (size_t)b0 * bs, sel, std::min(sub, batch - b0), bs, stream);
+}
+
 // Hybrid key switch of a batch of polynomials with one evaluation key (HYBRID KeySwitch of EvalRotate / EvalMult, A.6):
 //   INTT digits (pre-scaled) -> ModUp base conversion -> NTT -> inner product with the key over Q_l u P -> INTT of the P part
 //   -> ModDown conversion -> NTT -> (acc - conv) P^-1 + addends, optionally permuted by the automorphism of g.
@@ -210,7 +220,7 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
             su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
         }
     }
-    launch_ntt(T, up, su, B, up_bs, stream);
+    ntt_l2(up, su, B, up_bs);
     // 3. inner product with the evaluation key over Q_l u P
     u64* acc = alloc(acc_bs * B);
     launch_inner_product(T, ks, acc, up, io.c, evk, B, acc_bs, up_bs, io.c_bs, stream);
@@ -223,7 +233,7 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
     LimbSel sq; sq.n = 2 * l;
     for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
-    launch_ntt(T, tq, sq, B, tq_bs, stream);
+    ntt_l2(tq, sq, B, tq_bs);
     FinishArgs fa{io.out, io.out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, io.add0, io.add0_bs, io.add1, io.add1_bs, io.plus, io.plus_bs};
     launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, B, stream);
     release(dco); release(up); release(acc); release(tq);

@@ -59,6 +59,8 @@ public:
     void ew_sel(EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel);
     void automorph(u64* out, const u64* in, uint32_t g, int limbs);
     void rescale(u64* out, const u64* in, int l, int polys);
+    void ntt_l2(u64* data, const LimbSel& sel, int batch, size_t batch_stride);   // batched forward NTT in L2-sized sub-batches
+    long l2_budget_bytes = 1l << 40;   // sub-batching measured slower on B200 (2460 vs 2625 rot/s): off unless FLK_L2_BUDGET_MB is set
     // out[2][l][N] = KeySwitch(c) (+add0 / +add1), optionally permuted by the automorphism map of g (0 = none)
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
     void keyswitch(const KsBatch& io, const u64* evk, uint32_t g);
