@@ -116,43 +116,50 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
     }
 }
 
-// acc{0,1}[b][t] = sum_d U_d[b][t] * evk_{b,a}[d][mod(t)].  A thread owns one coefficient of one extended limb for IPB
-// ciphertexts of the batch, so every evaluation-key word it loads (the largest stream of a key switch) is used IPB times.
+// acc{0,1}[b][t] = sum_d U_d[b][t] * evk_{b,a}[d][mod(t)].  A thread owns two adjacent coefficients (16-byte accesses) of one
+// extended limb for IPB ciphertexts of the batch, so every evaluation-key word it loads (the largest stream of a key switch)
+// is used IPB times.  The digit loop is unrolled (BETA is a template parameter) so all loads of a thread are in flight together.
 constexpr int kIpb = 4;
+template <int BETA>
 __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                  const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,
                                                                  size_t up_bs, size_t c_bs) {
     const int t = blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * kIpb;
-    const int j = blockIdx.x * kThreads + threadIdx.x;
+    const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
     const size_t kpoly = (size_t)(T.L + T.K) * T.N;
-    Acc3 s0[kIpb], s1[kIpb];
-#pragma unroll
-    for (int i = 0; i < kIpb; ++i) { s0[i] = Acc3{0, 0, 0}; s1[i] = Acc3{0, 0, 0}; }
     const int own_d = t < l ? t / ks.alpha : -1;
-    for (int d = 0; d < ks.beta; ++d) {
-        const u64* kb = evk + (size_t)d * 2 * kpoly + (size_t)m * T.N + j;
-        const Split30 k0 = split30(__ldg(kb)), k1 = split30(__ldg(kb + kpoly));
-        const u64* src = d == own_d ? c_eval + (size_t)t * T.N + j : up + ((size_t)d * ext + t) * T.N + j;
-        const size_t bs = d == own_d ? c_bs : up_bs;
+    const int nb = min(kIpb, batch - b0);
+    ulonglong2 k0[BETA], k1[BETA], u[BETA], un[BETA];
+    const u64* src[BETA];
+    size_t sbs[BETA];
 #pragma unroll
-        for (int i = 0; i < kIpb; ++i) {
-            if (b0 + i < batch) {
-                const Split30 us = split30(src[(size_t)(b0 + i) * bs]);
-                mac3(s0[i], us, k0);
-                mac3(s1[i], us, k1);
-            }
-        }
+    for (int d = 0; d < BETA; ++d) {
+        const u64* kb = evk + (size_t)d * 2 * kpoly + (size_t)m * T.N + j;
+        k0[d] = __ldg(reinterpret_cast<const ulonglong2*>(kb));
+        k1[d] = __ldg(reinterpret_cast<const ulonglong2*>(kb + kpoly));
+        src[d] = d == own_d ? c_eval + (size_t)t * T.N + j : up + ((size_t)d * ext + t) * T.N + j;
+        sbs[d] = d == own_d ? c_bs : up_bs;
+        un[d] = *reinterpret_cast<const ulonglong2*>(src[d] + (size_t)b0 * sbs[d]);
     }
     const RedC rc = load_redc(T, m);
+    for (int i = 0; i < nb; ++i) {
 #pragma unroll
-    for (int i = 0; i < kIpb; ++i) {
-        if (b0 + i < batch) {
-            u64* o = acc + (size_t)(b0 + i) * acc_bs + (size_t)t * T.N + j;
-            o[0] = reduce3(s0[i], rc);
-            o[(size_t)ext * T.N] = reduce3(s1[i], rc);
+        for (int d = 0; d < BETA; ++d) {
+            u[d] = un[d];
+            if (i + 1 < nb) un[d] = *reinterpret_cast<const ulonglong2*>(src[d] + (size_t)(b0 + i + 1) * sbs[d]);   // next ciphertext's operands
         }
+        Acc3 s0x{0, 0, 0}, s0y{0, 0, 0}, s1x{0, 0, 0}, s1y{0, 0, 0};
+#pragma unroll
+        for (int d = 0; d < BETA; ++d) {
+            const Split30 ux = split30(u[d].x), uy = split30(u[d].y);
+            mac3(s0x, ux, split30(k0[d].x)); mac3(s0y, uy, split30(k0[d].y));
+            mac3(s1x, ux, split30(k1[d].x)); mac3(s1y, uy, split30(k1[d].y));
+        }
+        u64* o = acc + (size_t)(b0 + i) * acc_bs + (size_t)t * T.N + j;
+        *reinterpret_cast<ulonglong2*>(o) = make_ulonglong2(reduce3(s0x, rc), reduce3(s0y, rc));
+        *reinterpret_cast<ulonglong2*>(o + (size_t)ext * T.N) = make_ulonglong2(reduce3(s1x, rc), reduce3(s1y, rc));
     }
 }
 
@@ -330,8 +337,13 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
 }
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s) {
-    inner_product_kernel<<<dim3(cdiv(t.N, kThreads), ks.l + t.K, (batch + kIpb - 1) / kIpb), kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch,
-                                                                                                            acc_bs, up_bs, c_bs);
+    const dim3 grid(cdiv(t.N / 2, kThreads), ks.l + t.K, (batch + kIpb - 1) / kIpb);
+    switch (ks.beta) {
+#define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch, acc_bs, up_bs, c_bs); break;
+        FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
+#undef FLK_CASE
+        default: throw std::invalid_argument("more than 8 key-switch digits is not supported");
+    }
     FLK_CUDA(cudaGetLastError());
 }
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
