@@ -42,6 +42,7 @@ def load_library():
         "fl_dev_alloc": (ci, [vp, sz, C.POINTER(vp)]), "fl_dev_free": (ci, [vp, vp]),
         "fl_dev_upload": (ci, [vp, vp, vp, sz]), "fl_dev_download": (ci, [vp, vp, vp, sz]),
         "fl_raw_ntt": (ci, [vp, vp, vp, ci]), "fl_raw_intt": (ci, [vp, vp, vp, ci]),
+        "fl_raw_ntt_batch": (ci, [vp, vp, vp, ci, ci, ci]),
         "fl_raw_add": (ci, [vp, vp, vp, vp, vp, ci]), "fl_raw_sub": (ci, [vp, vp, vp, vp, vp, ci]),
         "fl_raw_mul": (ci, [vp, vp, vp, vp, vp, ci]),
         "fl_raw_automorph": (ci, [vp, vp, vp, ci, u32]),
@@ -160,6 +161,11 @@ class Engine:
 
     def intt(self, d, midx=None):
         m = self._midx(d.shape[-2], midx); self._ck(self.lib.fl_raw_intt(self.h, d.ptr, _ptr(m), len(m))); return d
+
+    def ntt_batch(self, d, midx=None, inverse=False):
+        """d: DevBuf [batch][limbs][N]; the whole batch in one launch pair."""
+        m = self._midx(d.shape[-2], midx)
+        self._ck(self.lib.fl_raw_ntt_batch(self.h, d.ptr, _ptr(m), len(m), d.shape[0], 1 if inverse else 0)); return d
 
     def _bin(self, fn, a, b, midx):
         m = self._midx(a.shape[-2], midx); out = self.buf(a.shape)

@@ -78,6 +78,13 @@ int fl_dev_download(fl_ctx* c, uint64_t* dst, const uint64_t* src, size_t words)
 
 int fl_raw_ntt(fl_ctx* c, uint64_t* d, const int* midx, int nl) { FL_TRY(c->eng->ntt(d, make_sel(midx, nl))) }
 int fl_raw_intt(fl_ctx* c, uint64_t* d, const int* midx, int nl) { FL_TRY(c->eng->intt(d, make_sel(midx, nl))) }
+int fl_raw_ntt_batch(fl_ctx* c, uint64_t* d, const int* midx, int nl, int batch, int inverse) {
+    FL_TRY({
+        const LimbSel sel = make_sel(midx, nl);
+        const size_t bs = (size_t)nl * c->eng->P.N;
+        if (inverse) c->eng->intt(d, sel, batch, bs); else c->eng->ntt(d, sel, batch, bs);
+    })
+}
 int fl_raw_add(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl) {
     FL_TRY(c->eng->ew_sel(EwOp::Add, out, a, b, make_sel(midx, nl)))
 }

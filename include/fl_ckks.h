@@ -61,6 +61,7 @@ int fl_dev_download(fl_ctx* c, uint64_t* dst_host, const uint64_t* src, size_t w
  * midx[i] = modulus index of limb i (0..L-1 Q limbs, L..L+K-1 P limbs) */
 int fl_raw_ntt(fl_ctx* c, uint64_t* d, const int* midx, int nl);    /* DCRTPoly::SwitchFormat -> EVALUATION */
 int fl_raw_intt(fl_ctx* c, uint64_t* d, const int* midx, int nl);   /* DCRTPoly::SwitchFormat -> COEFFICIENT */
+int fl_raw_ntt_batch(fl_ctx* c, uint64_t* d, const int* midx, int nl, int batch, int inverse);   /* d: [batch][nl][N], one launch pair */
 int fl_raw_add(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);   /* EvalAdd F.cpp:410 */
 int fl_raw_sub(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);
 int fl_raw_mul(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, const int* midx, int nl);

@@ -192,3 +192,38 @@ def test_batched_rotation_equals_single(pair):
         for b in range(5):
             assert (got[b] == o.rotate(cts[b], g, evk)).all(), (l, b)
         assert (e.host_rotate_batch(cts, g, d_evk) == got).all()
+
+
+def test_batched_ntt_equals_single(pair):
+    o, e = pair
+    rng = np.random.default_rng(31)
+    allm = list(range(o.L + o.K))
+    a = np.stack([rnd(o, rng, allm) for _ in range(3)])
+    d = e.to_dev(a)
+    got = e.ntt_batch(d, allm).download()
+    for b in range(3):
+        assert (got[b] == o.ntt(a[b], allm)).all()
+    assert (e.ntt_batch(d, allm, inverse=True).download() == a).all()
+
+
+def test_radix16_transform_variant_is_bit_exact():
+    """The alternative radix-16 head/tail kernels (FLK_NTT_RADIX16=1, logN >= 12) against the oracle, in a fresh process."""
+    import subprocess, sys
+    code = r'''
+import numpy as np
+from fhe_linformer_b200 import Engine
+from oracle.oracle import Oracle
+for P in (dict(logN=12, L=5, dnum=3), dict(logN=13, L=4, dnum=2), dict(logN=15, L=3, dnum=3), dict(logN=16, L=2, dnum=2)):
+    o = Oracle(**P); e = Engine(device=0, sparse_h=64, **P)
+    rng = np.random.default_rng(P["logN"])
+    allm = list(range(o.L + o.K))
+    a = np.stack([rng.integers(0, int(o.moduli[m]), o.N, dtype=np.uint64) for m in allm])
+    d = e.to_dev(a)
+    assert (e.ntt(d, allm).download() == o.ntt(a, allm)).all(), P
+    assert (e.intt(d, allm).download() == a).all(), P
+    e.close()
+print("radix16 ok")
+'''
+    env = dict(os.environ, FLK_NTT_RADIX16="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "radix16 ok" in r.stdout, r.stderr[-2000:]
