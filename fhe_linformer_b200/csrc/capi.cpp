@@ -199,6 +199,7 @@ int fl_mul_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out) { FL_TRY(*out
 int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out) {
     FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->mult_many(std::move(e))); })
 }
+int fl_linear_wsum(fl_ctx* c, const fl_ct* in, const double* w, int n_out, fl_ct** out) { FL_TRY(*out = wrap(c->sch->linear_wsum(in->e, w, n_out))) }
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotate(a->e, k))) }
 int fl_has_rot_key(fl_ctx* c, int k) { return c->sch->has_rotation_key(k) ? 1 : 0; }
 int fl_rotsum(fl_ctx* c, const fl_ct* a, int steps, int stride, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotsum(a->e, steps, stride))) }

@@ -212,6 +212,35 @@ __global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restric
     out[(size_t)b * out_bs + oo] = v;
 }
 
+// ---------------- plaintext-weighted sums of ciphertexts (EvalLinearWSum) ----------------
+// out[o] = sum_t k[o][t] * in[t], limb-wise.  A thread owns one coefficient of one limb of one polynomial for kOt outputs, so
+// every input word is read n_out / kOt times.  k: [n_out][n_in][l] residues with Shoup companions ([.][.][.][2]).
+constexpr int kOt = 8;
+__global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out, const u64* __restrict__ in, const ulonglong2* __restrict__ k,
+                                                           DevTables T, int l, int n_in, int n_out) {
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const int limb = blockIdx.y % l, o0 = blockIdx.z * kOt;
+    const size_t poly_off = (size_t)blockIdx.y * T.N + j, ct = (size_t)2 * l * T.N;
+    const u64 q = T.q[limb];
+    u64 acc[kOt];
+#pragma unroll
+    for (int o = 0; o < kOt; ++o) acc[o] = 0;
+    for (int t = 0; t < n_in; ++t) {
+        const u64 x = in[(size_t)t * ct + poly_off];
+#pragma unroll
+        for (int o = 0; o < kOt; ++o) {
+            if (o0 + o < n_out) {
+                const ulonglong2 c = __ldg(k + ((size_t)(o0 + o) * n_in + t) * l + limb);
+                acc[o] = addmod(acc[o], mul_shoup(x, c.x, c.y, q), q);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < kOt; ++o)
+        if (o0 + o < n_out) out[(size_t)(o0 + o) * ct + poly_off] = acc[o];
+}
+
 // ---------------- rescale ----------------
 __global__ void __launch_bounds__(kThreads) rescale_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ xlast, DevTables T, int l) {
     const int p = blockIdx.z, i = blockIdx.y;
@@ -364,6 +393,11 @@ void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishAr
     moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), l, polys * batch), kThreads, 0, s>>>(a.out, a.acc, a.acc_ps, a.tq, a.add0, a.add1, map, t, md, l,
                                                                                           polys, a.out_bs, a.acc_bs, a.tq_bs, a.add0_bs, a.add1_bs,
                                                                                           a.plus, a.plus_bs);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int n_in, int n_out, cudaStream_t s) {
+    lincomb_kernel<<<dim3(cdiv(t.N, kThreads), 2 * l, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, reinterpret_cast<const ulonglong2*>(k), t, l,
+                                                                                                n_in, n_out);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {

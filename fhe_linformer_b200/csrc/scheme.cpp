@@ -586,6 +586,33 @@ Elem Scheme::mult_const(const Elem& a_in, double c) {
     return a;
 }
 
+Elem Scheme::linear_wsum(const Elem& in_raw, const double* w, int n_out) {
+    if (in_raw.ncomp != 2) throw std::invalid_argument("EvalLinearWSum: ciphertexts expected");
+    Elem in = in_raw;
+    if (in.deg == 2) rescale_inplace(in);
+    const int n_in = in.batch, l = in.l;
+    const double sf = P.sf[level_of(in)];
+    std::vector<u64> k((size_t)n_out * n_in * l * 2);
+    for (int o = 0; o < n_out; ++o)
+        for (int t = 0; t < n_in; ++t) {
+            const i128 v = (i128)std::rint(w[(size_t)o * n_in + t] * sf);
+            for (int i = 0; i < l; ++i) {
+                i128 r = v % (i128)P.q[i];
+                if (r < 0) r += P.q[i];
+                u64* e = &k[(((size_t)o * n_in + t) * l + i) * 2];
+                e[0] = (u64)r; e[1] = nt::shoup((u64)r, P.q[i]);
+            }
+        }
+    u64* kd = eng.alloc(k.size());
+    eng.upload(kd, k.data(), k.size());
+    Elem r = make(2, l, in.deg + 1, in.scale * sf, in.slots, n_out);
+    launch_lincomb(eng.T, r.data(), in.data(), kd, l, n_in, n_out, eng.stream);
+    eng.sync();   // k is a host temporary
+    eng.release(kd);
+    if (eng.ledger_on) eng.ledger.add("linear_wsum", l, (double)(n_in + n_out) * 16.0 * l * P.N);
+    return r;
+}
+
 Elem Scheme::mult_many(std::vector<Elem> v) {
     const size_t n = v.size();
     if (n == 0) throw std::invalid_argument("EvalMultMany: empty input");

@@ -92,6 +92,9 @@ public:
     Elem mult(const Elem& a, const Elem& b);          // EvalMult F.cpp:427 (ct*pt), :431 (ct*ct + relinearisation)
     Elem mult_const(const Elem& a, double c);         // EvalMult(ct, double)
     Elem mult_many(std::vector<Elem> v);              // EvalMultMany F.cpp:1297
+    // EvalLinearWSum: out[o] = sum_t w[o * n_in + t] * in[t] for a batched operand `in` (n_in ciphertexts); result is a batch
+    // of n_out ciphertexts one degree deeper.  The encrypted Linformer E / F projection is one such call.
+    Elem linear_wsum(const Elem& in, const double* w, int n_out);
     Elem square(const Elem& a) { return mult(a, a); }
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);

@@ -488,6 +488,19 @@ vector<Ctxt> FHEController::per_row(const vector<Ctxt>& rows, const std::functio
     return out;
 }
 
+vector<Ctxt> FHEController::project_rows(const vector<Ctxt>& rows, const vector<vector<double>>& weights, const vector<Ptxt>& bias) {
+    const int n_in = (int)rows.size(), n_out = (int)weights.size();
+    vector<double> w((size_t)n_out * n_in);
+    for (int o = 0; o < n_out; ++o)
+        for (int t = 0; t < n_in; ++t) w[(size_t)o * n_in + t] = weights[o].at(t);
+    fl_elem* e = nullptr;
+    need(fl_linear_wsum(ctx_, pack(rows)->handle(), w.data(), n_out, &e), "EvalLinearWSum");
+    vector<Ctxt> out = unpack(wrap(e));
+    if (!bias.empty())
+        for (int o = 0; o < n_out; ++o) out[o] = add(out[o], bias.at(o));
+    return out;
+}
+
 /* ------------------------------------------------------------------ packed matrix products ------------------------------------------------------------------ */
 // "RE": rows arrive Expanded, weight is the row-major 128x128 matrix, summing over the 128 blocks (stride 128) leaves the
 // product Repeated.  "CR": rows arrive Repeated, summing inside each block (stride 1) leaves product entry j at slot 128 j.

@@ -147,6 +147,9 @@ public:
     fl_ctx* native() const { return ctx_; }
     Ctxt chebyshev(const std::function<double(double)>& f, const Ctxt& c, double a, double b, int degree);
     Ctxt ladder(const Ctxt& in, int slots, int stride);   // shared body of rotsum / rotsum_padded / repeat
+    // out[o] = sum_t weights[o][t] * rows[t] + bias[o] (bias: one plaintext per output, may be empty): the Linformer E / F
+    // projection evaluated on the row ciphertexts instead of by the client
+    vector<Ctxt> project_rows(const vector<Ctxt>& rows, const vector<vector<double>>& weights, const vector<Ptxt>& bias);
     Ctxt adopt(fl_elem* e) const;                          // take ownership of a raw C-ABI handle
     // row batching (FHEController.cpp "row batching"): independent rows share kernel launches
     bool batch_rows = true;

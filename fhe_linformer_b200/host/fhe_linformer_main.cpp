@@ -26,6 +26,7 @@ int main(int argc, char** argv) {
                      "       [--root DIR] [--tokens DIR] [--lean] [--resume]\n\n--generate_keys  create context, key pair, relinearisation, rotation and bootstrapping keys under <root>/keys\n"
                      "--verbose        per-stage timings and decrypted intermediates\n--root DIR       parent of keys/ weights-20NG/ input/ checkpoint/ (default ..)\n"
                      "--tokens DIR     folder with input_<i>.txt token embeddings (default <root>/tokens)\n--lean           skip operations whose results the circuit never reads\n"
+                     "--encrypted-projection  compute the Linformer E/F projections on the server from the encrypted rows\n"
                      "--resume         start from <root>/checkpoint/encodered.bin instead of running the encoder\n";
         return 0;
     }
@@ -51,6 +52,7 @@ int main(int argc, char** argv) {
     const auto start = utils::start_time();
     flh::LinformerForward forward(controller, {root + "/weights-20NG", root + "/input", arg_value(argc, argv, "--tokens", root + "/tokens")}, verbose);
     forward.set_dead_work(!has_flag(argc, argv, "--lean"));
+    forward.set_encrypted_projection(has_flag(argc, argv, "--encrypted-projection"));
     Ctxt encoded;
     if (has_flag(argc, argv, "--resume")) {
         encoded = controller.load_ciphertext(root + "/checkpoint/encodered.bin");

@@ -84,7 +84,8 @@ int flh_forward(flh_controller* c, const char* weights_dir, const char* input_di
     return guarded([&] {
         flh::LinformerForward fwd(c->fc, {weights_dir, input_dir, tokens_dir}, false);
         fwd.set_token_limit(token_limit);
-        fwd.set_dead_work(dead_work != 0);
+        fwd.set_dead_work((dead_work & 1) != 0);
+        fwd.set_encrypted_projection((dead_work & 2) != 0);
         if (sink) fwd.set_checkpoint_sink([&](const std::string& name, const std::vector<double>& v, int level) { sink(name.c_str(), v.data(), (int)v.size(), level, user); });
         const std::vector<double> z = fwd.run(classes);
         std::memcpy(logits, z.data(), sizeof(double) * z.size());
@@ -160,7 +161,12 @@ int flh_invoke(flh_controller* c, const char* method, fl_elem* const* cts, int n
         else if (m == "eval_inverse_naive_2") res = {fc.eval_inverse_naive_2(in.at(0), R(0), R(1), R(2))};
         else if (m == "eval_gelu_function") res = {fc.eval_gelu_function(in.at(0), R(0), R(1), R(2), I(0))};
         else if (m == "eval_tanh_function") res = {fc.eval_tanh_function(in.at(0), R(0), R(1), R(2), I(0))};
-        else if (m == "slicing") res = fc.slicing(in, I(0), I(1));
+        else if (m == "project_rows") {
+            std::vector<std::vector<double>> w((size_t)I(0), std::vector<double>(in.size()));
+            for (size_t o = 0; o < w.size(); ++o)
+                for (size_t t = 0; t < in.size(); ++t) w[o][t] = R((int)(o * in.size() + t));
+            res = fc.project_rows(in, w, {});
+        } else if (m == "slicing") res = fc.slicing(in, I(0), I(1));
         else throw std::invalid_argument("flh_invoke: unknown method " + m);
         if ((int)res.size() > out_cap) throw std::runtime_error(m + ": result count exceeds the output capacity");
         for (size_t i = 0; i < res.size(); ++i) out[i] = release(fc, res[i]);

@@ -42,6 +42,20 @@ std::vector<Ctxt> LinformerForward::load_expanded(const std::string& dir, const 
     return rows;
 }
 
+// ---- Linformer projection under encryption (F1): row i of X_E is sum_t E[i][t] rows[t] + E_b[i], still in the Expanded layout --
+std::vector<Ctxt> LinformerForward::project(const std::vector<Ctxt>& rows, const std::string& which) {
+    const std::vector<double> flat = utils::read_values_from_file(layer("selfAttn_" + which + "_weight.txt"));
+    const std::vector<double> b = utils::read_values_from_file(layer("selfAttn_" + which + "_bias.txt"));
+    const size_t S = rows.size(), width = flat.size() / 32;   // 32 x 701 in the reference's checkpoint
+    if (flat.size() % 32 != 0 || width < S || b.size() < 32) throw std::runtime_error("projection weights: expected 32 x (>= S) and 32 biases");
+    std::vector<std::vector<double>> w(32, std::vector<double>(S));
+    for (int i = 0; i < 32; ++i)
+        for (size_t t = 0; t < S; ++t) w[i][t] = flat[(size_t)i * width + t];
+    std::vector<Ctxt> out = fc_.project_rows(rows, w, {});
+    for (int i = 0; i < 32; ++i) out[i] = fc_.add(out[i], fc_.encode(b[i], (int)out[i]->GetLevel() + 1, 0));   // product is rescaled lazily: bias one level lower
+    return out;
+}
+
 // ---- attention for the CLS query only (M:176-215) -------------------------------------------------------------------------
 // K = X_E W_K, V = X_F W_V on the 32 client-projected rows; scores = softmax-like exp / sum over the 32 keys; context = scores V.
 Ctxt LinformerForward::attend_cls(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf) {
@@ -157,13 +171,22 @@ Ctxt LinformerForward::encoder() {
     tokens_ = found + 1;
     if (verbose_) std::cout << tokens_ << " inputs found!" << std::endl << std::endl;
 
-    const std::vector<Ctxt> xe = load_expanded(files_.input, "XE_", 32);                 // M:159-162
-    const std::vector<Ctxt> xf = load_expanded(files_.input, "XF_", 32);                 // M:164-167
     std::vector<Ctxt> rows;
     rows.push_back(fc_.read_expanded_input(w("cls_token.txt")));                         // M:170
     const std::vector<Ctxt> embedded = load_expanded(files_.tokens, "input_", found);    // M:171-173
     rows.insert(rows.end(), embedded.begin(), embedded.end());
+    std::vector<Ctxt> xe, xf;
+    if (!encrypted_projection_) {
+        xe = load_expanded(files_.input, "XE_", 32);                                     // M:159-162
+        xf = load_expanded(files_.input, "XF_", 32);                                     // M:164-167
+    }
     lap("Encrypt");
+    if (encrypted_projection_) {
+        xe = project(rows, "E");
+        xf = project(rows, "F");
+        checkpoint("projected_E0", xe[0]);
+        lap("Projection");
+    }
 
     const Ctxt context = attend_cls(rows, xe, xf);
     checkpoint("attention_cls", context);

@@ -33,6 +33,10 @@ public:
     // true (default): issue every operation main.cpp issues, including the ones whose results it never reads (queries of
     // rows 1.., W_O on the S-1 zero rows, the final unwrap of all rows).  false: skip those; the logits are identical.
     void set_dead_work(bool on) { dead_work_ = on; }
+    // true: the server computes X_E = E[:, :S] X + E_b and X_F on the encrypted rows (fl_linear_wsum) from
+    // <weights>/..._selfAttn_{E,F}_{weight,bias}.txt instead of reading the client's XE_i / XF_i uploads (M:159-167,
+    // src/python/dimReduce.py:153-160) -- SURVEY.md F1
+    void set_encrypted_projection(bool on) { encrypted_projection_ = on; }
 
     Ctxt encoder();                       // main.cpp:145-425
     Ctxt pooler(const Ctxt& encoded);     // main.cpp:427-451
@@ -63,6 +67,8 @@ private:
     bool verbose_;
     int token_limit_ = 0;
     bool dead_work_ = true;
+    bool encrypted_projection_ = false;
+    std::vector<Ctxt> project(const std::vector<Ctxt>& rows, const std::string& which);
     int tokens_ = 0;
     std::function<void(const std::string&, const std::vector<double>&, int)> sink_;
     std::vector<StageTime> times_;

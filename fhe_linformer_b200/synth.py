@@ -70,6 +70,9 @@ def write_files(root, model, sample):
     for n in "QKV":
         w(LAYER + "selfAttn_W%s_weight_T.txt" % n, model["W%s_T" % n])
         w(LAYER + "selfAttn_W%s_bias.txt" % n, model["b" + n])
+    for n in "EF":   # projection matrices, for the encrypted-projection variant (names of src/python/dimReduce.py:146-151)
+        w(LAYER + "selfAttn_%s_weight.txt" % n, model[n])
+        w(LAYER + "selfAttn_%s_bias.txt" % n, model[n + "b"].ravel())
     w(LAYER + "selfAttn_WO_weight.txt", model["WO"])
     w(LAYER + "selfAttn_WO_bias.txt", model["bO"])
     for idx, (a, b, c) in (("1", ("a1", "b1", "c1")), ("2", ("a2", "b2n", "c2"))):

@@ -119,6 +119,10 @@ int fl_add_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out);
 int fl_mul(fl_ctx* c, const fl_elem* a, const fl_elem* b, fl_ct** out);         /* EvalMult F.cpp:427,431 */
 int fl_mul_const(fl_ctx* c, const fl_ct* a, double k, fl_ct** out);
 int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out);                /* EvalMultMany F.cpp:1297 */
+/* EvalLinearWSum over a batched operand: out[o] = sum_t w[o * n_in + t] * in[t] (n_in = fl_elem_batch(in)); the result is a
+ * batch of n_out ciphertexts.  Used for the encrypted Linformer E / F projection that the reference leaves to the client
+ * (src/python/dimReduce.py:153-160). */
+int fl_linear_wsum(fl_ctx* c, const fl_ct* in, const double* w, int n_out, fl_ct** out);
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out);                   /* EvalRotate F.cpp:435,833,843 */
 int fl_has_rot_key(fl_ctx* c, int k);                                           /* is the EvalRotateKeyGen key for index k resident? */
 /* out = sum_{t < 2^steps} rot(a, t * stride): FHEController::rotsum / rotsum_padded / repeat, F.cpp:829-867 */

@@ -177,6 +177,9 @@ def sim_forward(model, sample, checkpoints=None):
     xe = [s.expanded(r) for r in sample["XE"]]
     xf = [s.expanded(r) for r in sample["XF"]]
     S = len(rows)
+    # encrypted-projection variant: the same rows of X_E, computed from the row ciphertexts as
+    # sum_t E[i][t] rows[t] + E_b[i] (src/python/dimReduce.py:153-156); identical slots by linearity
+    cp["projected_E0"] = sum(model["E"][0, t] * rows[t] for t in range(S)) + float(model["Eb"][0, 0])
     # attention for the CLS query (M:176-215)
     q = s.matmulRE(rows[:1], s.plain(model["WQ_T"]), s.repeated(model["bQ"]))
     keys = s.wrapUpRepeated(s.matmulRE(xe, s.plain(model["WK_T"]), s.repeated(model["bK"])))

@@ -54,6 +54,22 @@ def test_lean_mode_gives_the_same_logits(setup):
     assert np.abs(lean - full).max() < 1e-4   # same circuit minus dead operations; fresh encryption noise only
 
 
+def test_encrypted_projection_variant(setup):
+    """X_E / X_F computed on the server from the encrypted rows (fl_linear_wsum) instead of uploaded by the client."""
+    from oracle import linformer_sim as ls
+    fc, model, sample, dirs, _ = setup
+    got = {}
+    logits, stages, S = fc.forward(dirs, dead_work=False, checkpoints=got, encrypted_projection=True)
+    ref_cp = {}
+    ref = ls.sim_forward(model, sample, ref_cp)
+    assert "Projection" in stages and "projected_E0" in got
+    assert np.abs(got["projected_E0"][0] - ref_cp["projected_E0"]).max() < 1e-6
+    assert np.abs(ref_cp["projected_E0"] - ls.SlotSim().expanded(sample["XE"][0])).max() < 1e-12   # equals the client-side projection
+    for name, (slots, level) in got.items():
+        assert np.abs(slots - ref_cp[name]).max() < CHECKPOINT_TOL, name
+    assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
+
+
 def test_key_files_roundtrip_and_resume(setup):
     """generate_context(serialize) / load_context / rotation-key file / ciphertext checkpoint (F.cpp:59-89,184-301,1360-1394)."""
     from fhe_linformer_b200 import host

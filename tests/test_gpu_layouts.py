@@ -118,6 +118,17 @@ def test_wraps_and_containers(env):
     assert len(sl) == 2 and err(c, sl[0], vec[1]) < TOL
 
 
+def test_project_rows_linear_wsum(env):
+    fc, c, s, rng = env
+    rows = [rng.uniform(-1, 1, s.n) for _ in range(5)]
+    W = rng.uniform(-0.5, 0.5, (3, 5))
+    out = fc.invoke("project_rows", [enc(c, r) for r in rows], ints=[3], reals=list(W.ravel()))
+    assert len(out) == 3
+    for o in range(3):
+        assert err(c, out[o], sum(W[o, t] * rows[t] for t in range(5))) < 1e-7
+        assert out[o].deg == 2 and out[o].level == 0
+
+
 def test_activations(env):
     fc, c, s, rng = env
     sc = np.zeros(s.n); sc[(np.arange(32) * 128)] = rng.uniform(-0.05, 0.05, 32)
