@@ -31,6 +31,7 @@ _SIGS = {
     "fl_elem_scale": (dbl, [vp]), "fl_elem_clone": (ci, [vp, vp, C.POINTER(vp)]), "fl_elem_free": (None, [vp]),
     "fl_elem_export": (ci, [vp, vp, vp]), "fl_elem_import": (ci, [vp, vp, ci, ci, ci, dbl, ci, C.POINTER(vp)]),
     "fl_elem_save": (ci, [vp, vp, C.c_char_p]), "fl_elem_load": (ci, [vp, C.c_char_p, C.POINTER(vp)]),
+    "fl_prof_enable": (ci, [vp, ci]), "fl_prof_dump": (ci, [vp, C.c_char_p, C.c_size_t]),
     "fl_ledger_enable": (ci, [vp, ci]), "fl_ledger_reset": (ci, [vp]), "fl_ledger_dump": (ci, [vp, C.c_char_p, C.c_size_t]),
 }
 
@@ -166,6 +167,17 @@ class CKKS(Engine):
         return self._out(self.lib.fl_elem_import, _ptr(a), a.shape[0], a.shape[1], deg, float(scale), slots)
     def save(self, a, path): self._ck(self.lib.fl_elem_save(self.h, a.h, path.encode()))
     def load(self, path): return self._out(self.lib.fl_elem_load, path.encode())
+
+    def prof(self, on=True): self.lib.fl_prof_enable(self.h, 1 if on else 0)
+    def prof_dump(self):
+        """{entry point: (calls, gpu ms, host ms)} since the last dump."""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.lib.fl_prof_dump(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, n, g, h = line.split()
+            out[k] = (int(float(n)), float(g), float(h))
+        return out
 
     def ledger(self, on=True): self.lib.fl_ledger_enable(self.h, 1 if on else 0)
     def ledger_reset(self): self.lib.fl_ledger_reset(self.h)

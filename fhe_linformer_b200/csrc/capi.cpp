@@ -1,19 +1,42 @@
 // capi.cpp -- extern "C" boundary (include/fl_ckks.h) over the device engine.
 #include "../../include/fl_ckks.h"
 
+#include <chrono>
 #include <cstring>
+#include <map>
 #include <string>
 
 #include <cstdio>
+#include <array>
 #include <vector>
 
 #include "scheme.h"
 
 using namespace flk;
 
+struct ProfRec { const char* name; cudaEvent_t a, b; double host_s; };
 struct fl_ctx {
     Scheme* sch;
     Engine* eng;   // = &sch->eng
+    bool prof_on = false;
+    std::vector<ProfRec> prof;
+};
+// GPU time of one C-ABI call: events on the engine stream around everything the call enqueues (fl_prof_*)
+struct ProfScope {
+    fl_ctx* c; ProfRec r; std::chrono::steady_clock::time_point t0;
+    ProfScope(fl_ctx* ctx, const char* name) : c(ctx && ctx->prof_on ? ctx : nullptr) {
+        if (!c) return;
+        r.name = name;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->eng->stream);
+        t0 = std::chrono::steady_clock::now();
+    }
+    ~ProfScope() {
+        if (!c) return;
+        cudaEventRecord(r.b, c->eng->stream);
+        r.host_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        c->prof.push_back(r);
+    }
 };
 struct fl_elem {
     Elem e;
@@ -25,6 +48,7 @@ const char* fl_last_error(void) { return g_err.c_str(); }
 
 #define FL_TRY(...)                      \
     try {                                \
+        ProfScope prof_scope_(prof_ctx(c), __func__); \
         __VA_ARGS__;                     \
         return 0;                        \
     } catch (const std::exception& e) {  \
@@ -34,6 +58,21 @@ const char* fl_last_error(void) { return g_err.c_str(); }
         g_err = "unknown error";         \
         return 2;                        \
     }
+
+#define FL_TRY0(...)                      \
+    try {                                \
+        __VA_ARGS__;                     \
+        return 0;                        \
+    } catch (const std::exception& e) {  \
+        g_err = e.what();                \
+        return 1;                        \
+    } catch (...) {                      \
+        g_err = "unknown error";         \
+        return 2;                        \
+    }
+
+static inline fl_ctx* prof_ctx(fl_ctx* c) { return c; }
+static inline fl_ctx* prof_ctx(const void*) { return nullptr; }   // entry points without a context argument are not timed
 
 static LimbSel make_sel(const int* midx, int nl) {
     if (nl < 0 || nl > kMaxLimbSel) throw std::invalid_argument("limb count out of range");
@@ -45,7 +84,7 @@ static LimbSel make_sel(const int* midx, int nl) {
 extern "C" {
 
 int fl_ctx_create(const fl_params* p, int device, fl_ctx** out) {
-    FL_TRY({
+    FL_TRY0({
         ParamSpec s;
         s.logN = p->logN; s.L = p->L; s.dnum = p->dnum; s.first_bits = p->first_bits; s.scale_bits = p->scale_bits;
         s.aux_bits = p->aux_bits; s.sparse_h = p->sparse_h;
@@ -215,7 +254,7 @@ int fl_eval_chebyshev(fl_ctx* c, const fl_ct* x, const double* coeffs, int n, do
     FL_TRY(*out = wrap(c->sch->eval_chebyshev(x->e, std::vector<double>(coeffs, coeffs + n), a, b)))
 }
 int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree, double* out) {
-    FL_TRY({ auto v = Scheme::chebyshev_coefficients(f, user, a, b, degree); std::memcpy(out, v.data(), 8 * v.size()); })
+    FL_TRY0({ auto v = Scheme::chebyshev_coefficients(f, user, a, b, degree); std::memcpy(out, v.data(), 8 * v.size()); })
 }
 int fl_bootstrap_setup(fl_ctx* c, int b0, int b1, int slots) { FL_TRY(c->sch->bootstrap_setup(b0, b1, slots)) }
 int fl_bootstrap_keygen(fl_ctx* c, int slots) { FL_TRY(c->sch->bootstrap_keygen(slots)) }
@@ -243,6 +282,28 @@ int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int de
 int fl_elem_save(fl_ctx* c, const fl_elem* a, const char* path) { FL_TRY(c->sch->save_elem(a->e, path)) }
 int fl_elem_load(fl_ctx* c, const char* path, fl_elem** out) { FL_TRY(*out = wrap(c->sch->load_elem(path))) }
 
+int fl_prof_enable(fl_ctx* c, int on) { c->prof_on = on != 0; return 0; }
+int fl_prof_dump(fl_ctx* c, char* buf, size_t cap) {
+    c->eng->sync();
+    std::map<std::string, std::array<double, 3>> acc;   // calls, gpu ms, host s
+    for (auto& r : c->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = acc[r.name];
+        e[0] += 1; e[1] += ms; e[2] += r.host_s;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    c->prof.clear();
+    std::string s;
+    for (auto& kv : acc) {
+        char line[200];
+        std::snprintf(line, sizeof line, "%s %.0f %.3f %.3f\n", kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2] * 1e3);
+        s += line;
+    }
+    if (s.size() + 1 > cap) { g_err = "profile buffer too small"; return 1; }
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
 int fl_ledger_enable(fl_ctx* c, int on) { c->eng->ledger_on = on != 0; return 0; }
 int fl_ledger_reset(fl_ctx* c) { c->eng->ledger.reset(); return 0; }
 int fl_ledger_dump(fl_ctx* c, char* buf, size_t cap) {

@@ -89,4 +89,14 @@ void launch_reduce_i128(const DevTables& t, u64* out, const int64_t* coef_lohi, 
 // small signed int8 coefficients -> residues
 void launch_reduce_i8(const DevTables& t, u64* out, const int8_t* coef, const LimbSel& sel, cudaStream_t s);
 
+// ---- encode.cu: device-side encoding and samplers ----
+void upload_gauss_table(const u64* cdt30);
+// dst[sel.pos][N] <- residues of a ternary (kind 0) or discrete-Gaussian (kind 1) polynomial drawn from SplitMix64(seed)
+void launch_sample_limbs(const DevTables& t, u64* dst, u64 seed, int kind, const LimbSel& sel, cudaStream_t s);
+// dst limb i <- uniform residues mod q_{sel.m[i]} from SplitMix64(seeds[i])
+void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const LimbSel& sel, cudaStream_t s);
+// special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd)
+void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,
+                   const double* cim, cudaStream_t s);
+
 }  // namespace flk

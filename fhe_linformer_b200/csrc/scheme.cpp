@@ -121,6 +121,8 @@ Scheme::Scheme(const ParamSpec& spec, int device) : eng(spec, device), P(eng.P) 
 Scheme::~Scheme() {
     try {
         eng.sync();
+        for (auto& kv : dev_fft_) { cudaFree(kv.second.rot); cudaFree(kv.second.cre); cudaFree(kv.second.cim); }
+        if (stage_) { cudaFreeHost(stage_); for (auto& ev : stage_ev_) cudaEventDestroy(ev); }
         boot_.clear();
         eng.release(sk_); eng.release(pk_); eng.release(mk_);
         for (auto& kv : gk_) eng.release(kv.second);
@@ -190,16 +192,18 @@ void Scheme::sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSe
     eng.release((u64*)d8);
 }
 
+// Uniform, ternary and Gaussian polynomials are generated on the device from the same SplitMix64 streams the host
+// restatement walks sequentially (encode.cu): no host loop, no upload, no synchronisation.
 void Scheme::uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel) {
-    std::vector<u64> h((size_t)sel.n * P.N);
-    for (int i = 0; i < sel.n; ++i) {
-        SplitMix r(SplitMix::sub(seed, 1000 + sel.m[i]));
-        const u64 q = P.q[sel.m[i]];
-        u64* o = &h[(size_t)i * P.N];
-        for (int j = 0; j < P.N; ++j) o[j] = r.next() % q;
-    }
-    eng.upload(dst, h.data(), h.size());
-    eng.sync();
+    u64 seeds[kMaxLimbSel];
+    for (int i = 0; i < sel.n; ++i) seeds[i] = SplitMix::sub(seed, 1000 + sel.m[i]);
+    launch_uniform_limbs(eng.T, dst, seeds, sel, eng.stream);
+}
+
+void Scheme::sample_dev_to_eval(u64* dst, u64 seed, int kind, const LimbSel& sel) {
+    if (!gauss_table_ready_) { upload_gauss_table(kGaussCdt); gauss_table_ready_ = true; }
+    launch_sample_limbs(eng.T, dst, seed, kind, sel, eng.stream);
+    eng.ntt(dst, sel);
 }
 
 void Scheme::keygen(u64 seed) {
@@ -207,15 +211,15 @@ void Scheme::keygen(u64 seed) {
     const int T = P.T, N = P.N;
     if (!sk_) sk_ = eng.alloc((size_t)T * N);
     if (!pk_) pk_ = eng.alloc((size_t)2 * P.L * N);
-    auto s = P.spec.sparse_h > 0 ? sample_sparse(N, P.spec.sparse_h, SplitMix::sub(seed, 0)) : sample_ternary(N, SplitMix::sub(seed, 0));
-    sample_to_eval(sk_, s, sel_range(0, T));
+    if (P.spec.sparse_h > 0) sample_to_eval(sk_, sample_sparse(N, P.spec.sparse_h, SplitMix::sub(seed, 0)), sel_range(0, T));   // rejection loop: host
+    else sample_dev_to_eval(sk_, SplitMix::sub(seed, 0), 0, sel_range(0, T));
     // pk = (e - a*s, a)
     const LimbSel q = sel_range(0, P.L);
     const size_t pl = (size_t)P.L * N;
     const u64 pseed = seed + 1;
     uniform_to_dev(pk_ + pl, SplitMix::sub(pseed, 10), q);
     u64* e = eng.alloc(pl);
-    sample_to_eval(e, sample_gauss(N, SplitMix::sub(pseed, 11)), q);
+    sample_dev_to_eval(e, SplitMix::sub(pseed, 11), 1, q);
     launch_ew(eng.T, EwOp::Mul, pk_, pk_ + pl, sk_, q, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Sub, pk_, e, pk_, q, 1, 1, 0, 0, 0, eng.stream);
     eng.release(e);
@@ -233,7 +237,7 @@ void Scheme::keyswitch_gen(const u64* sk_old, const u64* sk_new, u64 seed, u64* 
         u64* b = evk + (size_t)d * 2 * kl;
         u64* a = b + kl;
         uniform_to_dev(a, SplitMix::sub(seed, 100 + 2 * d), all);
-        sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 101 + 2 * d)), all);
+        sample_dev_to_eval(e, SplitMix::sub(seed, 101 + 2 * d), 1, all);
         launch_ew(eng.T, EwOp::Mul, b, a, sk_new, all, 1, 1, 0, 0, 0, eng.stream);
         launch_ew(eng.T, EwOp::Sub, b, e, b, all, 1, 1, 0, 0, 0, eng.stream);
         const int lo = d * P.alpha, hi = std::min(lo + P.alpha, P.L), ns = hi - lo;
@@ -325,13 +329,47 @@ void Scheme::coeffs_to_dev(u64* dst, const std::vector<i128>& co, int l) {
     eng.release((u64*)d);
 }
 
+// MakeCKKSPackedPlaintext on the device: the slot values are staged through pinned memory, the special inverse FFT, the
+// scaling / rounding and the reduction into the RNS limbs run as kernels (encode.cu), then the limbs are transformed.
 Elem Scheme::encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg) {
     if (l < 1 || l > P.L) throw std::invalid_argument("encode: level out of range");
-    std::vector<i128> co;
-    encode_coeffs(vals, n, slots, scale, co);
+    const int Nh = P.N / 2;
+    if (slots < 1 || slots > Nh || (slots & (slots - 1))) throw std::invalid_argument("encode: slots must be a power of two <= N/2");
+    DevFft& f = dev_fft(slots);
+    // pinned staging ring: a slot is reused only after the copy that read it has completed
+    if (!stage_) {
+        FLK_CUDA(cudaMallocHost(&stage_, kStageSlots * (size_t)2 * Nh * sizeof(double)));
+        for (auto& ev : stage_ev_) FLK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    const int slot = stage_next_++ % kStageSlots;
+    FLK_CUDA(cudaEventSynchronize(stage_ev_[slot]));
+    double* h = stage_ + (size_t)slot * 2 * Nh;
+    const int m = std::min(n, slots);
+    for (int i = 0; i < m; ++i) { h[i] = vals[i].real(); h[slots + i] = vals[i].imag(); }
+    for (int i = m; i < slots; ++i) { h[i] = 0.0; h[slots + i] = 0.0; }
+    double* d = (double*)eng.alloc((size_t)2 * slots);
+    FLK_CUDA(cudaMemcpyAsync(d, h, (size_t)2 * slots * sizeof(double), cudaMemcpyHostToDevice, eng.stream));
+    FLK_CUDA(cudaEventRecord(stage_ev_[slot], eng.stream));
     Elem e = make(1, l, deg, scale, slots);
-    coeffs_to_dev(e.data(), co, l);
+    launch_encode(eng.T, e.data(), d, d + slots, slots, scale, l, f.rot, f.cre, f.cim, eng.stream);
+    eng.ntt(e.data(), sel_range(0, l));
+    eng.release((u64*)d);
     return e;
+}
+
+Scheme::DevFft& Scheme::dev_fft(int slots) {
+    auto it = dev_fft_.find(slots);
+    if (it != dev_fft_.end()) return it->second;
+    const FftTables& t = fft_tables(slots);
+    DevFft f{};
+    FLK_CUDA(cudaMalloc(&f.rot, t.rot.size() * sizeof(uint32_t)));
+    FLK_CUDA(cudaMalloc(&f.cre, t.cre.size() * sizeof(double)));
+    FLK_CUDA(cudaMalloc(&f.cim, t.cim.size() * sizeof(double)));
+    FLK_CUDA(cudaMemcpyAsync(f.rot, t.rot.data(), t.rot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, eng.stream));
+    FLK_CUDA(cudaMemcpyAsync(f.cre, t.cre.data(), t.cre.size() * sizeof(double), cudaMemcpyHostToDevice, eng.stream));
+    FLK_CUDA(cudaMemcpyAsync(f.cim, t.cim.data(), t.cim.size() * sizeof(double), cudaMemcpyHostToDevice, eng.stream));
+    eng.sync();
+    return dev_fft_.emplace(slots, f).first->second;
 }
 
 Elem Scheme::encode(const cplx* vals, int n, int level, int slots, int deg) {
@@ -388,13 +426,13 @@ Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) {
     Elem ct = make(2, l, pt.deg, pt.scale, pt.slots);
     u64* v = eng.alloc(pl);
     u64* e = eng.alloc(pl);
-    sample_to_eval(v, sample_ternary(N, SplitMix::sub(seed, 1)), sel);
-    sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 2)), sel);
+    sample_dev_to_eval(v, SplitMix::sub(seed, 1), 0, sel);
+    sample_dev_to_eval(e, SplitMix::sub(seed, 2), 1, sel);
     u64* c0 = ct.data(); u64* c1 = c0 + pl;
     launch_ew(eng.T, EwOp::Mul, c0, pk_, v, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c0, c0, e, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c0, c0, pt.data(), sel, 1, 1, 0, 0, 0, eng.stream);
-    sample_to_eval(e, sample_gauss(N, SplitMix::sub(seed, 3)), sel);
+    sample_dev_to_eval(e, SplitMix::sub(seed, 3), 1, sel);
     launch_ew(eng.T, EwOp::Mul, c1, pk_ + pkl, v, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c1, c1, e, sel, 1, 1, 0, 0, 0, eng.stream);
     eng.release(v); eng.release(e);

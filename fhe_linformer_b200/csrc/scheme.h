@@ -143,6 +143,9 @@ private:
     void keyswitch_gen(const u64* sk_old_dev, const u64* sk_new_dev, u64 seed, u64* evk_dev);
     void sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSel& sel);
     void uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel);
+    void sample_dev_to_eval(u64* dst, u64 seed, int kind, const LimbSel& sel);   // kind 0 ternary, 1 Gaussian (device sampler + NTT)
+    struct DevFft { uint32_t* rot; double* cre; double* cim; };               // special-FFT tables of one slot count, on the device
+    DevFft& dev_fft(int slots);
     void encode_coeffs(const cplx* vals, int n, int slots, double scale, std::vector<i128>& co) const;
     void coeffs_to_dev(u64* dst, const std::vector<i128>& co, int l);
     ScalarSet scalar_set(i128 k, int l) const;
@@ -151,6 +154,12 @@ private:
     Elem cheby_ps(const Elem& x, const std::vector<double>& c);
     Elem inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto);
 
+    std::map<int, DevFft> dev_fft_;
+    static constexpr int kStageSlots = 8;
+    double* stage_ = nullptr;                 // pinned staging ring for slot values
+    cudaEvent_t stage_ev_[kStageSlots] = {};
+    int stage_next_ = 0;
+    bool gauss_table_ready_ = false;
     u64 key_seed_ = 1;
     u64* sk_ = nullptr;      // (L+K) limbs eval
     u64* pk_ = nullptr;      // [2][L][N]

@@ -160,6 +160,10 @@ int fl_elem_import(fl_ctx* c, const uint64_t* host, int ncomp, int limbs, int de
 int fl_elem_save(fl_ctx* c, const fl_elem* a, const char* path);    /* Serial::SerializeToFile(ct) F.cpp:1361 */
 int fl_elem_load(fl_ctx* c, const char* path, fl_elem** out);       /* Serial::DeserializeFromFile F.cpp:1386 */
 
+/* per-entry-point GPU time (CUDA events on the engine stream around each call) and host time: "name calls gpu_ms host_ms" lines */
+int fl_prof_enable(fl_ctx* c, int on);
+int fl_prof_dump(fl_ctx* c, char* buf, size_t cap);
+
 /* op ledger: algorithmic bytes per SURVEY.md section 8(d) */
 int fl_ledger_enable(fl_ctx* c, int on);
 int fl_ledger_reset(fl_ctx* c);
