@@ -306,15 +306,22 @@ def run_forward(a, local, rank, world, torch, dist):
         fc = host.FHEController(device=local, root=root).generate()
         fc.forward(dirs, dead_work=True)      # warm-up: mask / weight encodings, allocator pool, lazy rotation keys
         fc.ckks.ledger(True); fc.ckks.ledger_reset()
-        t0 = time.perf_counter()
-        logits, stages, S = fc.forward(dirs, dead_work=True)
-        dt = time.perf_counter() - t0
-        led = fc.ckks.ledger_dump()
-        fc.ckks.ledger(False)
+        runs = []
+        for rep in range(3):                  # three timed samples: shared boxes show +-20 % run-to-run noise; the median is reported
+            if rep == 1:
+                led = fc.ckks.ledger_dump(); fc.ckks.ledger(False)
+            t0 = time.perf_counter()
+            logits, stages_i, S = fc.forward(dirs, dead_work=True)
+            runs.append((time.perf_counter() - t0, stages_i))
+        runs.sort(key=lambda r: r[0])
+        dt, stages = runs[1]
         fc.forward(dirs, dead_work=False)     # warm-up of the lean variant (different batch shapes)
-        t1 = time.perf_counter()
-        fc.forward(dirs, dead_work=False)
-        lean = time.perf_counter() - t1
+        lean_runs = []
+        for rep in range(3):
+            t1 = time.perf_counter()
+            fc.forward(dirs, dead_work=False)
+            lean_runs.append(time.perf_counter() - t1)
+        lean = sorted(lean_runs)[1]
         fc.close()
     finally:
         os.dup2(saved, 1)
@@ -328,6 +335,7 @@ def run_forward(a, local, rank, world, torch, dist):
     return {"seconds_per_sample": dt, "samples_per_s": world / dt, "rows_S": S, "ring": "N=2^15, 28 limbs, dnum 4, 2^14 slots",
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
+            "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
             "note": "text files -> encode/encrypt -> encoder1 -> pooler -> classifier -> decrypt, wall clock incl. host encode; "
                     "lean = same logits without the operations main.cpp issues but never reads"}
 

@@ -258,6 +258,59 @@ void Engine::rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64*
     }
 }
 
+// Hoisted rotate-and-sum: out = (self ? ct : 0) + sum_k sigma_k(ct) for nk rotations of the SAME ciphertexts.  The digit
+// decomposition / ModUp (45 % of a key switch) is done once, the nk evaluation-key inner products accumulate -- each gathered
+// through its automorphism map -- in the extended basis Q_l u P, and a single ModDown brings the sum back (double hoisting,
+// Bossuat et al.).  Used by the rotate-and-add ladders (two doubling steps = three rotations of one operand).
+void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self) {
+    if (B <= 0) return;
+    const KsLevel& ks = ks_level(l);
+    const int N = P.N, K = P.K, ext = l + K, beta = ks.beta;
+    const size_t cs = (size_t)2 * l * N, dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N, acc_bs = (size_t)2 * ext * N, tq_bs = cs;
+    const u64* c1 = ct + (size_t)l * N;
+    const uint32_t* maps[8];
+    for (int k = 0; k < nk; ++k) maps[k] = automorph_map(gs[k]);
+    u64* dco = alloc(dco_bs * B);
+    if (B == 1) copy(dco, c1, dco_bs);
+    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, c1, cs * 8, dco_bs * 8, B, cudaMemcpyDeviceToDevice, stream));
+    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream);
+    u64* up = alloc(up_bs * B);
+    launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
+    LimbSel su; su.n = 0;
+    for (int d = 0; d < beta; ++d) {
+        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
+        for (int t = 0; t < ext; ++t) {
+            if (t >= lo && t < hi) continue;
+            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+        }
+    }
+    launch_ntt(T, up, su, B, up_bs, stream);
+    u64* acc = alloc(acc_bs * B);
+    launch_inner_product_multi(T, ks, acc, up, c1, evks, maps, nk, B, acc_bs, up_bs, cs, stream);
+    u64* s0 = alloc(dco_bs * B);
+    launch_gather_sum(T, s0, ct, maps, nk, l, B, dco_bs, cs, self, stream);
+    LimbSel sp; sp.n = 2 * K;
+    for (int p = 0; p < 2; ++p)
+        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+    launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
+    u64* tq = alloc(tq_bs * B);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
+    LimbSel sq; sq.n = 2 * l;
+    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    launch_ntt(T, tq, sq, B, tq_bs, stream);
+    FinishArgs fa{out, cs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, s0, dco_bs, self ? c1 : nullptr, cs, nullptr, 0};
+    launch_moddown_finish(T, md_, fa, nullptr, l, 2, B, stream);
+    release(dco); release(up); release(acc); release(s0); release(tq);
+    if (ledger_on) {
+        // the ledger follows the reference's operation census, not the work done here: a hoisted group of
+        // 2^s - 1 rotations stands for s rotate-and-add steps of the sequential ladder
+        int s_steps = 0;
+        while ((1 << s_steps) - 1 < nk) ++s_steps;
+        ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B * s_steps);
+        ledger.add("add", l, 48.0 * l * P.N, B * s_steps);
+    }
+}
+
 // Host-resident caller (the reference keeps ciphertexts in host memory): chunk c+1 is uploaded while chunk c is key
 // switched and chunk c-1 is downloaded, so a PCIe-bound call costs max(H2D, D2H, compute) instead of their sum.
 void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk) {

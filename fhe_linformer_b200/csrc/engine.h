@@ -65,6 +65,8 @@ public:
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
     void keyswitch(const KsBatch& io, const u64* evk, uint32_t g);
     void rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64* evk, int B, bool accumulate);   // ct, out: [B][2][l][N]
+    // out[b] = (self ? ct[b] : 0) + sum_k rotate(ct[b], g_k): the rotations share one ModUp and one ModDown (hoisting); nk <= 8
+    void rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self);
     // the same with HOST operands: uploads, key switches and downloads of successive chunks overlap on three streams
     void rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk);
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);

@@ -163,6 +163,74 @@ __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict
     }
 }
 
+// ---- hoisted multi-rotation (rotate-and-sum ladders): acc[b][{0,1}][t][j] = sum_k IP_k(U[b])[t][map_k[j]] ----
+// One ModUp serves nk rotations of the same ciphertext; the automorphism of rotation k is applied while accumulating
+// (gather at map_k[j]), so a single ModDown finishes all of them.  Per key the digit products accumulate carry-free and
+// are reduced once; the nk reduced values add up modulo q.
+struct MultiKeys {
+    const u64* evk[8];
+    const uint32_t* map[8];
+    int n;
+};
+template <int BETA>
+__global__ void __launch_bounds__(kThreads) inner_product_multi_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
+                                                                       MultiKeys mk, DevTables T, KsLevel ks, int batch, size_t acc_bs, size_t up_bs,
+                                                                       size_t c_bs) {
+    constexpr int IPB = 2;
+    const int t = blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * IPB;
+    const int j = blockIdx.x * kThreads + threadIdx.x;
+    if (j >= T.N) return;
+    const int m = t < l ? t : T.L + (t - l);
+    const size_t kpoly = (size_t)(T.L + T.K) * T.N;
+    const int own_d = t < l ? t / ks.alpha : -1;
+    const RedC rc = load_redc(T, m);
+    u64 r0[IPB], r1[IPB];
+#pragma unroll
+    for (int i = 0; i < IPB; ++i) r0[i] = r1[i] = 0;
+    for (int k = 0; k < mk.n; ++k) {
+        const uint32_t src = mk.map[k][j];
+        Split30 k0[BETA], k1[BETA];
+#pragma unroll
+        for (int d = 0; d < BETA; ++d) {
+            const u64* kb = mk.evk[k] + (size_t)d * 2 * kpoly + (size_t)m * T.N + src;
+            k0[d] = split30(__ldg(kb)); k1[d] = split30(__ldg(kb + kpoly));
+        }
+#pragma unroll
+        for (int i = 0; i < IPB; ++i) {
+            if (b0 + i >= batch) break;
+            Acc3 s0{0, 0, 0}, s1{0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < BETA; ++d) {
+                const u64 u = d == own_d ? c_eval[(size_t)(b0 + i) * c_bs + (size_t)t * T.N + src]
+                                         : up[(size_t)(b0 + i) * up_bs + ((size_t)d * ext + t) * T.N + src];
+                const Split30 us = split30(u);
+                mac3(s0, us, k0[d]); mac3(s1, us, k1[d]);
+            }
+            r0[i] = addmod(r0[i], reduce3(s0, rc), rc.q);
+            r1[i] = addmod(r1[i], reduce3(s1, rc), rc.q);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < IPB; ++i) {
+        if (b0 + i >= batch) break;
+        u64* o = acc + (size_t)(b0 + i) * acc_bs + (size_t)t * T.N + j;
+        o[0] = r0[i];
+        o[(size_t)ext * T.N] = r1[i];
+    }
+}
+
+// s0[b][i][j] = (self ? c0[b][i][j] : 0) + sum_k c0[b][i][map_k[j]]     grid (N / 256, l, batch)
+__global__ void __launch_bounds__(kThreads) gather_sum_kernel(u64* __restrict__ s0, const u64* __restrict__ c0, MultiKeys mk, DevTables T, int l,
+                                                              size_t s0_bs, size_t c_bs, int self) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= T.N) return;
+    const u64 q = T.q[i];
+    const u64* src = c0 + (size_t)b * c_bs + (size_t)i * T.N;
+    u64 v = self ? src[j] : 0;
+    for (int k = 0; k < mk.n; ++k) v = addmod(v, src[mk.map[k][j]], q);
+    s0[(size_t)b * s0_bs + (size_t)i * T.N + j] = v;
+}
+
 // grid: (N / 256, target groups, batch * polys); pcoef = P part (coefficient form, pre-scaled) of accumulator (b, p)
 template <int KK>
 __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
@@ -373,6 +441,29 @@ void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const
 #undef FLK_CASE
         default: throw std::invalid_argument("more than 8 key-switch digits is not supported");
     }
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
+                                const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s) {
+    if (nk < 1 || nk > 8) throw std::invalid_argument("hoisted rotation sum: 1..8 rotations per call");
+    MultiKeys mk{};
+    mk.n = nk;
+    for (int k = 0; k < nk; ++k) { mk.evk[k] = evks[k]; mk.map[k] = maps[k]; }
+    const dim3 grid(cdiv(t.N, kThreads), ks.l + t.K, (batch + 1) / 2);
+    switch (ks.beta) {
+#define FLK_CASE(X) case X: inner_product_multi_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, mk, t, ks, batch, acc_bs, up_bs, c_bs); break;
+        FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
+#undef FLK_CASE
+        default: throw std::invalid_argument("more than 8 key-switch digits is not supported");
+    }
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_t* const* maps, int nk, int l, int batch, size_t s0_bs, size_t c_bs,
+                       bool self, cudaStream_t s) {
+    MultiKeys mk{};
+    mk.n = nk;
+    for (int k = 0; k < nk; ++k) mk.map[k] = maps[k];
+    gather_sum_kernel<<<dim3(cdiv(t.N, kThreads), l, batch), kThreads, 0, s>>>(s0, c0, mk, t, l, s0_bs, c_bs, self ? 1 : 0);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,

@@ -48,6 +48,12 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
 // acc[b][{0,1}][t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[b][t] inside digit d else up[b][d][t]
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
+// hoisted multi-rotation: acc[b][{0,1}][t][j] = sum_k (sum_d U_d[b][t] evk_k[d][mod(t)])[map_k[j]], nk <= 8 keys with their gather maps
+void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
+                                const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
+// s0[b][i][j] = (self ? c0[b][i][j] : 0) + sum_k c0[b][i][map_k[j]]
+void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_t* const* maps, int nk, int l, int batch, size_t s0_bs, size_t c_bs,
+                       bool self, cudaStream_t s);
 // tq[b][p][i][N] (coefficient form), i < l, from the scaled INTT of the P part of `polys` accumulators.
 // pcoef = [b][polys][K][N] with poly stride pstride and batch stride p_bs
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace flk {
@@ -686,17 +687,31 @@ Elem Scheme::conjugate(const Elem& a) { return apply_galois(a, P.galois_conj());
 // (F.cpp:829-867) as one call; the running ciphertext never leaves the device.
 Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
     if (a.ncomp != 2) throw std::invalid_argument("rotsum: ciphertext expected");
+    static const bool no_hoist = [] { const char* e = std::getenv("FLK_NO_HOIST"); return e && e[0] == '1'; }();
     Elem r = a;
-    for (int i = 0; i < steps; ++i) {
-        const uint32_t g = P.galois_for_rotation(stride * (1 << i));
-        auto it = gk_.find(g);
-        if (it == gk_.end()) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(stride * (1 << i)));
+    auto key_of = [&](int k) -> const u64* {
+        auto it = gk_.find(P.galois_for_rotation(k));
+        return it == gk_.end() ? nullptr : it->second;
+    };
+    for (int i = 0; i < steps;) {
+        const int k = stride * (1 << i);
         Elem nx = make(2, r.l, r.deg, r.scale, r.slots, r.batch);
+        const u64* k1 = key_of(k);
+        if (!k1) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(k));
+        const u64* k2 = i + 1 < steps ? key_of(2 * k) : nullptr;
+        const u64* k3 = i + 1 < steps ? key_of(3 * k) : nullptr;
+        const bool pair = !no_hoist && k2 && k3;
+        // two doubling steps at once: r + rot(r,k) + rot(r,2k) + rot(r,3k), the three rotations hoisted on one ModUp / ModDown
+        const uint32_t gs[3] = {P.galois_for_rotation(k), P.galois_for_rotation(2 * k), P.galois_for_rotation(3 * k)};
+        const u64* evks[3] = {k1, k2, k3};
         for (int b0 = 0, mb = max_batch(r.l); b0 < r.batch; b0 += mb) {
             const size_t o = (size_t)b0 * r.words_each(P.N);
-            eng.rotate_batch(nx.data() + o, r.data() + o, r.l, g, it->second, std::min(mb, r.batch - b0), true);
+            const int nb = std::min(mb, r.batch - b0);
+            if (pair) eng.rotate_sum_batch(nx.data() + o, r.data() + o, r.l, gs, evks, 3, nb, true);
+            else eng.rotate_batch(nx.data() + o, r.data() + o, r.l, gs[0], k1, nb, true);
         }
         r = nx;
+        i += pair ? 2 : 1;
     }
     return steps == 0 ? clone(a) : r;
 }

@@ -432,6 +432,9 @@ Ctxt FHEController::ladder(const Ctxt& in, int slots, int stride) {
     for (int i = 0; i < steps; ++i) {
         int k = stride * (1 << i);
         if (!fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
+        // the engine takes two doubling steps at once (r + rot(r,k) + rot(r,2k) + rot(r,3k), hoisted) when the 3k key exists
+        int k3 = 3 * k;
+        if (hoist_ladders && i % 2 == 0 && i + 1 < steps && !fl_has_rot_key(ctx_, k3)) need(fl_gen_rot_keys(ctx_, &k3, 1), "EvalRotateKeyGen");
     }
     fl_elem* e = nullptr;
     need(fl_rotsum(ctx_, in->handle(), steps, stride, &e), "EvalRotate ladder");

@@ -152,6 +152,7 @@ public:
     vector<Ctxt> project_rows(const vector<Ctxt>& rows, const vector<vector<double>>& weights, const vector<Ptxt>& bias);
     Ctxt adopt(fl_elem* e) const;                          // take ownership of a raw C-ABI handle
     // row batching (FHEController.cpp "row batching"): independent rows share kernel launches
+    bool hoist_ladders = true;      // generate the extra 3 * stride * 4^i keys that let ladders take two steps per key switch
     bool batch_rows = true;
     int max_rows_per_batch = 256;
     Ctxt pack(const vector<Ctxt>& rows) const;
