@@ -27,6 +27,7 @@ int main(int argc, char** argv) {
                      "--verbose        per-stage timings and decrypted intermediates\n--root DIR       parent of keys/ weights-20NG/ input/ checkpoint/ (default ..)\n"
                      "--tokens DIR     folder with input_<i>.txt token embeddings (default <root>/tokens)\n--lean           skip operations whose results the circuit never reads\n"
                      "--encrypted-projection  compute the Linformer E/F projections on the server from the encrypted rows\n"
+                     "--all-tokens     attention for every row (the circuit of the reference's main_2.cpp)\n"
                      "--resume         start from <root>/checkpoint/encodered.bin instead of running the encoder\n";
         return 0;
     }
@@ -53,6 +54,7 @@ int main(int argc, char** argv) {
     flh::LinformerForward forward(controller, {root + "/weights-20NG", root + "/input", arg_value(argc, argv, "--tokens", root + "/tokens")}, verbose);
     forward.set_dead_work(!has_flag(argc, argv, "--lean"));
     forward.set_encrypted_projection(has_flag(argc, argv, "--encrypted-projection"));
+    forward.set_all_token_attention(has_flag(argc, argv, "--all-tokens"));
     Ctxt encoded;
     if (has_flag(argc, argv, "--resume")) {
         encoded = controller.load_ciphertext(root + "/checkpoint/encodered.bin");

@@ -86,6 +86,7 @@ int flh_forward(flh_controller* c, const char* weights_dir, const char* input_di
         fwd.set_token_limit(token_limit);
         fwd.set_dead_work((dead_work & 1) != 0);
         fwd.set_encrypted_projection((dead_work & 2) != 0);
+        fwd.set_all_token_attention((dead_work & 4) != 0);
         if (sink) fwd.set_checkpoint_sink([&](const std::string& name, const std::vector<double>& v, int level) { sink(name.c_str(), v.data(), (int)v.size(), level, user); });
         const std::vector<double> z = fwd.run(classes);
         std::memcpy(logits, z.data(), sizeof(double) * z.size());

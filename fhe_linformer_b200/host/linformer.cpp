@@ -88,6 +88,34 @@ Ctxt LinformerForward::attend_cls(const std::vector<Ctxt>& rows, const std::vect
     return fc_.matmulRE(weights, values, 128, 128)[0];                                   // M:215-216
 }
 
+// ---- attention for every row (src/main_2.cpp:187-229, "M2:") ---------------------------------------------------------------
+// Queries go in two halves of at most 128; matmulScores(vector) packs query t's 32 scores at slots 128 j + t.
+std::vector<Ctxt> LinformerForward::attend_all(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf) {
+    const Ptxt wq = fc_.read_plain_input(layer("selfAttn_WQ_weight_T.txt"));
+    const Ptxt bq = fc_.read_plain_repeated_input(layer("selfAttn_WQ_bias.txt"));
+    const Ptxt wk = fc_.read_plain_input(layer("selfAttn_WK_weight_T.txt"));
+    const Ptxt bk = fc_.read_plain_repeated_input(layer("selfAttn_WK_bias.txt"));
+    const std::vector<Ctxt> queries = fc_.matmulRE(rows, wq, bq);                         // M2:182
+    const Ctxt keys = fc_.wrapUpRepeated(fc_.matmulRE(xe, wk, bk));                      // M2:183-185
+    std::vector<Ctxt> weights;
+    for (int half = 0; half < 2; ++half) {                                               // M2:187-216
+        const size_t lo = half ? 128 : 0, hi = half ? queries.size() : std::min<size_t>(128, queries.size());
+        if (lo >= hi) break;
+        const std::vector<Ctxt> q(queries.begin() + lo, queries.begin() + hi);
+        Ctxt scores = fc_.eval_exp(fc_.matmulScores(q, keys), (int)q.size());            // M2:196-200
+        if (half == 0) checkpoint("all_scores_exp_0", scores);
+        const Ctxt inverse = fc_.eval_inverse_naive(fc_.rotsum(scores, 32, 128), -1, 190000);   // M2:202-211
+        scores = fc_.mult(scores, inverse);                                              // M2:213-214
+        if (half == 0) checkpoint("all_scores_normalised_0", scores);
+        const std::vector<Ctxt> un = fc_.unwrapExpanded(scores, (int)q.size());          // M2:216-217
+        weights.insert(weights.end(), un.begin(), un.end());
+    }
+    const Ptxt wv = fc_.read_plain_input(layer("selfAttn_WV_weight_T.txt"));
+    const Ptxt bv = fc_.read_plain_repeated_input(layer("selfAttn_WV_bias.txt"));
+    const Ctxt values = fc_.wrapUpRepeated(fc_.matmulRE(xf, wv, bv));                   // M2:226-227
+    return fc_.matmulRE(weights, values, 128, 128);                                      // M2:229
+}
+
 // ---- W_O, bias and residual (M:217-239): only row 0 carries attention output, the other rows are encryptions of zero ------
 std::vector<Ctxt> LinformerForward::self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows) {
     const int level = (int)cls_context->GetLevel();
@@ -188,11 +216,23 @@ Ctxt LinformerForward::encoder() {
         lap("Projection");
     }
 
-    const Ctxt context = attend_cls(rows, xe, xf);
-    checkpoint("attention_cls", context);
-    lap("Self-Attention");
-
-    const std::vector<Ctxt> attended = self_output(context, rows);
+    std::vector<Ctxt> attended;
+    if (all_tokens_) {
+        std::vector<Ctxt> context = attend_all(rows, xe, xf);
+        checkpoint("attention_cls", context[0]);
+        checkpoint("attention_row1", context[1]);
+        lap("Self-Attention");
+        const int level = (int)context[0]->GetLevel();
+        const Ptxt wo = fc_.read_plain_input(layer("selfAttn_WO_weight.txt"), level);            // M2:239
+        const Ptxt bo = fc_.read_plain_expanded_input(layer("selfAttn_WO_bias.txt"), level + 1); // M2:240
+        attended = fc_.matmulCR(context, wo, bo);                                                // M2:242
+        for (size_t i = 0; i < attended.size(); ++i) attended[i] = fc_.add(attended[i], rows[i]); // M2:244-246
+    } else {
+        const Ctxt context = attend_cls(rows, xe, xf);
+        checkpoint("attention_cls", context);
+        lap("Self-Attention");
+        attended = self_output(context, rows);
+    }
     checkpoint("attended_row0", attended[0]);
     checkpoint("attended_row1", attended[1]);
     auto [half0, half1] = affine_and_refresh(attended, "affine1", true);
@@ -219,7 +259,7 @@ Ctxt LinformerForward::encoder() {
 }
 
 Ctxt LinformerForward::pooler(const Ctxt& encoded) {
-    const double tanh_scale = 1.0 / 50;                                                  // M:430
+    const double tanh_scale = all_tokens_ ? 1.0 / 18.0 : 1.0 / 50;                       // M:430 (main_2.cpp:386: 1/18)
     const int level = (int)encoded->GetLevel();
     const Ptxt weight = fc_.read_plain_input(w("pooler_dense_weight_T.txt"), level, tanh_scale);          // M:432
     const Ptxt bias = fc_.read_plain_repeated_input(w("pooler_dense_bias.txt"), level + 1, tanh_scale);   // M:433
@@ -238,7 +278,8 @@ Ctxt LinformerForward::classifier(const Ctxt& pooled) {
     Ctxt y = fc_.add(fc_.rotsum(fc_.mult(pooled, weight), 128, 1), bias);                // M:457-461
     std::vector<double> pick((size_t)fc_.num_slots, 0.0);                                // M:463-470: keep slots 128 i, i < 20
     for (int i = 0; i < 20; ++i) pick[(size_t)i * 128] = 1;
-    y = fc_.mult(y, fc_.encrypt(pick, (int)y->GetLevel()));                              // M:472 (ciphertext mask, as in main.cpp)
+    if (all_tokens_) y = fc_.mult(y, fc_.encode(pick, (int)y->GetLevel(), fc_.num_slots));   // main_2.cpp:427: plaintext mask
+    else y = fc_.mult(y, fc_.encrypt(pick, (int)y->GetLevel()));                         // M:472 (ciphertext mask, as in main.cpp)
     lap("Classifier");
     return y;
 }

@@ -37,6 +37,10 @@ public:
     // <weights>/..._selfAttn_{E,F}_{weight,bias}.txt instead of reading the client's XE_i / XF_i uploads (M:159-167,
     // src/python/dimReduce.py:153-160) -- SURVEY.md F1
     void set_encrypted_projection(bool on) { encrypted_projection_ = on; }
+    // true: the circuit of the reference's src/main_2.cpp (not built by its CMakeLists): attention for EVERY row (two halves of
+    // up to 128 queries packed by matmulScores(vector)), 1/x fitted on [-1, 190000], W_O bias on every row, tanh scale 1/18,
+    // plaintext class mask -- SURVEY.md F4
+    void set_all_token_attention(bool on) { all_tokens_ = on; }
 
     Ctxt encoder();                       // main.cpp:145-425
     Ctxt pooler(const Ctxt& encoded);     // main.cpp:427-451
@@ -68,6 +72,8 @@ private:
     int token_limit_ = 0;
     bool dead_work_ = true;
     bool encrypted_projection_ = false;
+    bool all_tokens_ = false;
+    std::vector<Ctxt> attend_all(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
     std::vector<Ctxt> project(const std::vector<Ctxt>& rows, const std::string& which);
     int tokens_ = 0;
     std::function<void(const std::string&, const std::vector<double>&, int)> sink_;

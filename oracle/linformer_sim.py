@@ -168,7 +168,7 @@ class SlotSim:
     def relu(self, v, scale, degree=119): return self.chebyshev(lambda x: 0.0 if x < 0 else x / scale, v, -1, 1, degree)
 
 
-def sim_forward(model, sample, checkpoints=None):
+def sim_forward(model, sample, checkpoints=None, all_tokens=False):
     """The circuit of main.cpp:145-475 on plaintext slots.  Returns the 20 logits; fills `checkpoints` (name -> slots) with the
     same intermediates host/linformer.cpp hands to its checkpoint sink.  Bootstraps are the identity here."""
     s = SlotSim()
@@ -180,6 +180,8 @@ def sim_forward(model, sample, checkpoints=None):
     # encrypted-projection variant: the same rows of X_E, computed from the row ciphertexts as
     # sum_t E[i][t] rows[t] + E_b[i] (src/python/dimReduce.py:153-156); identical slots by linearity
     cp["projected_E0"] = sum(model["E"][0, t] * rows[t] for t in range(S)) + float(model["Eb"][0, 0])
+    if all_tokens:
+        return _sim_forward_all_tokens(s, cp, model, sample, rows, xe, xf)
     # attention for the CLS query (M:176-215)
     q = s.matmulRE(rows[:1], s.plain(model["WQ_T"]), s.repeated(model["bQ"]))
     keys = s.wrapUpRepeated(s.matmulRE(xe, s.plain(model["WK_T"]), s.repeated(model["bK"])))
@@ -202,6 +204,11 @@ def sim_forward(model, sample, checkpoints=None):
     out[0] = out[0] + s.expanded(model["bO"])
     out = [o + r for o, r in zip(out, rows)]
     cp["attended_row0"], cp["attended_row1"] = out[0], out[1]
+    return _sim_tail(s, cp, model, out, S, 1 / 50.)
+
+
+def _sim_tail(s, cp, model, out, S, tanh_scale):
+    """Everything after the attention block: affine1, FFN, affine2, pooler, classifier (M:292-475)."""
     # affine1 (+ bootstrap) (M:292-320)
     f1 = model["c1"][0] + model["c1"][1] / math.sqrt(S) + model["c1"][2] / S
     halves = [s.wrapUpExpanded(out[:128]), s.wrapUpExpanded(out[128:])]
@@ -230,9 +237,9 @@ def sim_forward(model, sample, checkpoints=None):
     enc = s.unwrapExpanded(o[0], 1)[0]
     cp["encoder_out"] = enc
     # pooler (M:427-451)
-    y = s.rotsum(enc * s.plain(model["Wp_T"], 1 / 50.), 128, 128) + s.repeated(model["bp"], 1 / 50.)
+    y = s.rotsum(enc * s.plain(model["Wp_T"], tanh_scale), 128, 128) + s.repeated(model["bp"], tanh_scale)
     cp["pooler_pre_tanh"] = y
-    y = s.eval_tanh_function(y, -1, 1, 1 / 50., 300)
+    y = s.eval_tanh_function(y, -1, 1, tanh_scale, 300)
     cp["pooler_out"] = y
     # classifier (M:453-475)
     bc = np.concatenate([model["bc"], np.zeros(128 - len(model["bc"]))])
@@ -241,6 +248,31 @@ def sim_forward(model, sample, checkpoints=None):
     z = z * pick
     cp["classified"] = z
     return z[np.arange(20) * 128]
+
+
+def _sim_forward_all_tokens(s, cp, model, sample, rows, xe, xf):
+    """The attention block of the reference's src/main_2.cpp:187-246 (every row attends), then the common tail with tanh scale 1/18."""
+    S = len(rows)
+    q = s.matmulRE(rows, s.plain(model["WQ_T"]), s.repeated(model["bQ"]))
+    keys = s.wrapUpRepeated(s.matmulRE(xe, s.plain(model["WK_T"]), s.repeated(model["bK"])))
+    weights = []
+    for lo, hi in ((0, min(128, S)), (128, S)):
+        if lo >= hi:
+            break
+        scores = s.eval_exp(s.matmulScores(q[lo:hi], keys), hi - lo)
+        if lo == 0:
+            cp["all_scores_exp_0"] = scores
+        scores = scores * s.eval_inverse_naive(s.rotsum(scores, 32, 128), -1, 190000)
+        if lo == 0:
+            cp["all_scores_normalised_0"] = scores
+        weights += s.unwrapExpanded(scores, hi - lo)
+    values = s.wrapUpRepeated(s.matmulRE(xf, s.plain(model["WV_T"]), s.repeated(model["bV"])))
+    context = s.matmulRE(weights, values, None, 128, 128)
+    cp["attention_cls"], cp["attention_row1"] = context[0], context[1]
+    out = s.matmulCR(context, s.plain(model["WO"]), s.expanded(model["bO"]))
+    out = [o + r for o, r in zip(out, rows)]
+    cp["attended_row0"], cp["attended_row1"] = out[0], out[1]
+    return _sim_tail(s, cp, model, out, S, 1 / 18.)
 
 
 def float_forward(model, sample):

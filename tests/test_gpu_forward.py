@@ -70,6 +70,20 @@ def test_encrypted_projection_variant(setup):
     assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
 
 
+def test_all_token_attention_variant(setup):
+    """the circuit of the reference's main_2.cpp (every row attends; matmulScores(vector), 1/x on [-1, 190000])."""
+    from oracle import linformer_sim as ls
+    fc, model, sample, dirs, _ = setup
+    got = {}
+    logits, stages, S = fc.forward(dirs, dead_work=True, checkpoints=got, all_tokens=True)
+    ref_cp = {}
+    ref = ls.sim_forward(model, sample, ref_cp, all_tokens=True)
+    assert "all_scores_exp_0" in got and "attention_row1" in got
+    for name, (slots, level) in got.items():
+        assert np.abs(slots - ref_cp[name]).max() < CHECKPOINT_TOL, name
+    assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
+
+
 def test_key_files_roundtrip_and_resume(setup):
     """generate_context(serialize) / load_context / rotation-key file / ciphertext checkpoint (F.cpp:59-89,184-301,1360-1394)."""
     from fhe_linformer_b200 import host
