@@ -280,23 +280,22 @@ Elem Scheme::bootstrap(const Elem& in) {
         drop_to(ct, 2);
         const double kd = (double)P.q[1] * P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));
         mult_int_inplace(ct, (i128)std::rint(kd));
-        Elem r = make(2, 1, 1, P.sf[0], ct.slots);
-        eng.rescale(r.data(), ct.data(), 2, 2);
+        Elem r = make(2, 1, 1, P.sf[0], ct.slots, ct.batch);
+        eng.rescale(r.data(), ct.data(), 2, 2 * ct.batch);
         ct = r;
     } else {
         post_fix = P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));   // no limb to spend: fix the scale after StC
     }
     // ---- ModRaise: centred coefficients mod q0 -> all L limbs
-    Elem raised = make(2, L, 1, P.sf[0], ct.slots);
+    const int B = ct.batch;   // a batched operand is bootstrapped as one: every stage below is a single launch per batch
+    Elem raised = make(2, L, 1, P.sf[0], ct.slots, B);
     {
-        u64* x = eng.alloc((size_t)2 * N);
-        eng.copy(x, ct.data(), (size_t)2 * N);
-        LimbSel s0; s0.n = 2; s0.m[0] = s0.m[1] = 0; s0.pos[0] = 0; s0.pos[1] = 1;
-        eng.intt(x, s0);
-        launch_mod_switch(eng.T, raised.data(), x, 0, sel_range(0, L), 2, eng.stream);
-        LimbSel sa; sa.n = 2 * L;
-        for (int i = 0; i < 2 * L; ++i) { sa.m[i] = (uint8_t)(i % L); sa.pos[i] = (uint8_t)i; }
-        eng.ntt(raised.data(), sa);
+        u64* x = eng.alloc((size_t)2 * N * B);
+        eng.copy(x, ct.data(), (size_t)2 * N * B);
+        LimbSel s0; s0.n = 1; s0.m[0] = 0; s0.pos[0] = 0;
+        eng.intt(x, s0, 2 * B, (size_t)N);
+        launch_mod_switch(eng.T, raised.data(), x, 0, sel_range(0, L), 2 * B, eng.stream);
+        eng.ntt(raised.data(), sel_range(0, L), 2 * B, (size_t)L * N);
         eng.release(x);
     }
     // ---- CoeffsToSlots
@@ -307,8 +306,8 @@ Elem Scheme::bootstrap(const Elem& in) {
     Elem xlo = add(c, cc);
     Elem dif = sub(c, cc);
     auto times_i = [&](const Elem& a, bool negate) {
-        Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots);
-        launch_mul_i(eng.T, r.data(), a.data(), bp.zeta, sel_range(0, a.l), a.ncomp, eng.stream);
+        Elem r = make(a.ncomp, a.l, a.deg, a.scale, a.slots, a.batch);
+        launch_mul_i(eng.T, r.data(), a.data(), bp.zeta, sel_range(0, a.l), a.ncomp * a.batch, eng.stream);
         if (negate) mult_int_inplace(r, -1);
         return r;
     };

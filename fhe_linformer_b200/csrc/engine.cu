@@ -354,13 +354,18 @@ void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_
     cudaEventDestroy(ready);
 }
 
-void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) {
+void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) { mul_relin_batch(out, a, b, l, evk, 1, 0); }
+
+// EvalMult(ct, ct) for B ciphertext pairs stored back to back (b_bs = 0 broadcasts one right operand): tensor product, then
+// one batched key switch of the d2 components with the relinearisation key
+void Engine::mul_relin_batch(u64* out, const u64* a, const u64* b, int l, const u64* evk, int B, size_t b_bs) {
     const size_t pl = (size_t)l * P.N;
-    u64* d = alloc(3 * pl);
-    launch_tensor(T, d, d + pl, d + 2 * pl, a, b, l, stream);
-    keyswitch(out, d + 2 * pl, evk, l, d, d + pl, 0);
+    u64* d = alloc(3 * pl * B);
+    launch_tensor(T, d, d + pl, d + 2 * pl, a, b, l, B, 3 * pl, 2 * pl, b_bs, stream);
+    KsBatch io{B, l, d + 2 * pl, 3 * pl, out, 2 * pl, d, 3 * pl, d + pl, 3 * pl, nullptr, 0};
+    keyswitch(io, evk, 0);
     release(d);
-    if (ledger_on) ledger.add("mul_relin", l, (6.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N);
+    if (ledger_on) ledger.add("mul_relin", l, (6.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B);
 }
 
 void Engine::modup(u64* out_ext, const u64* c_eval, int l, int digit) {

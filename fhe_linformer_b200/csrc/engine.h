@@ -72,6 +72,7 @@ public:
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
     void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
+    void mul_relin_batch(u64* out, const u64* a, const u64* b, int l, const u64* evk, int B, size_t b_bs);   // a, out: [B][2][l][N]
     // pieces exposed for parity tests
     void modup(u64* out_ext, const u64* c_eval, int l, int digit);     // out: (l+K) limbs eval
     void moddown(u64* out, const u64* in_ext, int l);                  // in: (l+K) limbs eval

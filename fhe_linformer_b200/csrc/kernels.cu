@@ -45,9 +45,10 @@ __global__ void __launch_bounds__(kThreads) mul_scalar_kernel(u64* __restrict__ 
 }
 
 __global__ void __launch_bounds__(kThreads) add_scalar_kernel(u64* __restrict__ out, const u64* __restrict__ a, DevTables T, LimbSel sel,
-                                                              ScalarSet sc) {
+                                                              ScalarSet sc, size_t bs) {
     const size_t e = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 2;
     if (e >= (size_t)sel.n * T.N) return;
+    out += blockIdx.y * bs; a += blockIdx.y * bs;
     const int limb = (int)(e >> T.logN);
     const u64 q = T.q[sel.m[limb]], c = sc.c[limb];
     const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + e);
@@ -64,9 +65,11 @@ __global__ void __launch_bounds__(kThreads) automorph_kernel(u64* __restrict__ o
 }
 
 __global__ void __launch_bounds__(kThreads) tensor_kernel(u64* __restrict__ d0, u64* __restrict__ d1, u64* __restrict__ d2,
-                                                          const u64* __restrict__ a, const u64* __restrict__ b, DevTables T, int l) {
+                                                          const u64* __restrict__ a, const u64* __restrict__ b, DevTables T, int l, size_t d_bs,
+                                                          size_t a_bs, size_t b_bs) {
     const size_t e = (size_t)blockIdx.x * kThreads + threadIdx.x, pl = (size_t)l * T.N;
     if (e >= pl) return;
+    d0 += blockIdx.y * d_bs; d1 += blockIdx.y * d_bs; d2 += blockIdx.y * d_bs; a += blockIdx.y * a_bs; b += blockIdx.y * b_bs;
     const int m = (int)(e >> T.logN);
     const u64 q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
     const u64 a0 = a[e], a1 = a[pl + e], b0 = b[e], b1 = b[pl + e];
@@ -408,16 +411,17 @@ void launch_mul_scalar(const DevTables& t, u64* out, const u64* a, const ScalarS
     mul_scalar_kernel<<<cdiv((size_t)polys * sel.n * t.N / 2, kThreads), kThreads, 0, s>>>(out, a, t, sel, sc, polys);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, cudaStream_t s) {
-    add_scalar_kernel<<<cdiv((size_t)sel.n * t.N / 2, kThreads), kThreads, 0, s>>>(out, a, t, sel, sc);
+void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int batch, size_t bs, cudaStream_t s) {
+    add_scalar_kernel<<<dim3(cdiv((size_t)sel.n * t.N / 2, kThreads), batch), kThreads, 0, s>>>(out, a, t, sel, sc, bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_automorph(u64* out, const u64* in, const uint32_t* map, int N, int limbs, cudaStream_t s) {
     automorph_kernel<<<dim3(cdiv(N, kThreads), limbs), kThreads, 0, s>>>(out, in, map, N);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, cudaStream_t s) {
-    tensor_kernel<<<cdiv((size_t)l * t.N, kThreads), kThreads, 0, s>>>(d0, d1, d2, a, b, t, l);
+void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, int batch, size_t d_bs, size_t a_bs, size_t b_bs,
+                   cudaStream_t s) {
+    tensor_kernel<<<dim3(cdiv((size_t)l * t.N, kThreads), batch), kThreads, 0, s>>>(d0, d1, d2, a, b, t, l, d_bs, a_bs, b_bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s) {

@@ -18,13 +18,14 @@ struct ScalarSet {   // per-limb multiplier with Shoup companion
 // out = a * c[limb]  (polys polynomials of sel.n limbs)
 void launch_mul_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s);
 // out = a + c[limb] broadcast to every slot of the evaluation representation
-void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, cudaStream_t s);
+void launch_add_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int batch, size_t batch_stride, cudaStream_t s);
 
 // out[limb][j] = in[limb][map[j]]
 void launch_automorph(u64* out, const u64* in, const uint32_t* map, int N, int limbs, cudaStream_t s);
 
 // tensor product of two 2-component ciphertexts: d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1
-void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, cudaStream_t s);
+void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, const u64* b, int l, int batch, size_t d_bs, size_t a_bs, size_t b_bs,
+                   cudaStream_t s);
 
 // ---- hybrid key switch pieces ----
 struct KsLevel {          // device constants for key switching at l active limbs

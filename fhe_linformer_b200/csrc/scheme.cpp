@@ -588,10 +588,9 @@ Elem Scheme::add_many(std::vector<Elem> v) {
 
 Elem Scheme::add_const(const Elem& a, double c) {
     // constant polynomial round(c * scale): every evaluation-format entry of c0 receives the same residue
-    if (a.batch > 1) return pack(split_run(a, [&](const Elem& e) { return add_const(e, c); }));
     const i128 k = (i128)std::rint(c * a.scale);
     Elem r = clone(a);
-    launch_add_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), eng.stream);
+    launch_add_scalar(eng.T, r.data(), a.data(), scalar_set(k, a.l), sel_range(0, a.l), a.batch, a.words_each(P.N), eng.stream);
     return r;
 }
 
@@ -599,17 +598,17 @@ Elem Scheme::mult(const Elem& a_in, const Elem& b_in) {
     if (a_in.ncomp == 1 && b_in.ncomp == 2) return mult(b_in, a_in);
     if (a_in.ncomp != 2) throw std::invalid_argument("EvalMult: ciphertext expected");
     if (a_in.batch == 1 && b_in.batch > 1) return mult(b_in, a_in);
-    if (b_in.ncomp == 2 && a_in.batch > 1) {   // ciphertext x ciphertext has no batched kernel path: element by element
-        std::vector<Elem> out;
-        for (int i = 0; i < a_in.batch; ++i) out.push_back(mult(slice(a_in, i), b_in.batch > 1 ? slice(b_in, i) : b_in));
-        return pack(out);
-    }
+    if (b_in.batch != 1 && b_in.batch != a_in.batch) throw std::invalid_argument("EvalMult: batch sizes differ");
     Elem a = a_in, b = b_in;
     adjust_pair_to_one(a, b);
     Elem r = make(2, a.l, a.deg + b.deg, a.scale * b.scale, a.slots, a.batch);
     if (b.ncomp == 2) {
         if (!mk_) throw std::runtime_error("EvalMult: relinearisation key missing");
-        eng.mul_relin(r.data(), a.data(), b.data(), a.l, mk_);
+        for (int b0 = 0, mb = max_batch(a.l); b0 < a.batch; b0 += mb) {
+            const size_t o = (size_t)b0 * a.words_each(P.N);
+            eng.mul_relin_batch(r.data() + o, a.data() + o, b.data() + (b.batch > 1 ? o : 0), a.l, mk_, std::min(mb, a.batch - b0),
+                                b.batch > 1 ? a.words_each(P.N) : 0);
+        }
     } else {
         const size_t pl = (size_t)a.l * P.N;
         launch_ew(eng.T, EwOp::Mul, r.data(), a.data(), b.data(), sel_range(0, a.l), 2, a.batch, 2 * pl, 0, 0, eng.stream);

@@ -154,7 +154,8 @@ std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctx
     w1 = fc_.add(fc_.mult(w1, a), b);                                                    // M:316-317
     checkpoint(which + "_0", w0);
     checkpoint(which + "_1", w1);
-    return {fc_.bootstrap(w0), fc_.bootstrap(w1)};                                       // M:319-320
+    const std::vector<Ctxt> fresh = fc_.per_row({w0, w1}, [&](const Ctxt& c) { return fc_.bootstrap(c); });   // M:319-320, as one batch
+    return {fresh[0], fresh[1]};
 }
 
 // ---- FFN: 128 -> 512 (scaled by 1/8 so GELU's argument lies in [-1, 1]), GELU, bootstrap, 512 -> 128 (M:325-380) ----------
@@ -175,10 +176,10 @@ std::vector<Ctxt> LinformerForward::feed_forward(const Ctxt& half0, const Ctxt& 
     checkpoint("hidden_row0", hidden[0]);
 
     std::vector<Ctxt> containers = fc_.generate_containers(hidden, nullptr);             // M:358
-    for (size_t i = 0; i < containers.size(); ++i) {
-        if (i == 0) checkpoint("container0_pre_gelu", containers[0]);
-        containers[i] = fc_.bootstrap(fc_.eval_gelu_function(containers[i], -1, 1, gelu_scale, 119));   // M:362-363
-    }
+    checkpoint("container0_pre_gelu", containers[0]);
+    // M:360-364 loops over the containers; they are independent and share level and scale, so GELU and the bootstrap run on
+    // all of them as one batched operand
+    containers = fc_.per_row(containers, [&](const Ctxt& c) { return fc_.bootstrap(fc_.eval_gelu_function(c, -1, 1, gelu_scale, 119)); });
     checkpoint("container0_gelu", containers[0]);
     std::vector<std::vector<Ctxt>> quads = fc_.unwrapRepeatedLarge(containers, rows);    // M:366
     lap("Intermediate");

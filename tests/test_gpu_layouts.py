@@ -145,6 +145,36 @@ def test_activations(env):
     assert err(c, fc.invoke("relu", [enc(c, x)], reals=[2.0])[0], s.relu(x, 2.0)) < 1e-5
 
 
+def test_batched_bootstrap_chebyshev_and_ct_mult(env):
+    """Batched operands through ct x ct multiplication, Chebyshev evaluation and bootstrapping equal the per-ciphertext results."""
+    fc, c, s, rng = env
+    vs = [rng.uniform(-1, 1, s.n) for _ in range(3)]
+    import ctypes as C
+    def pack(elems):
+        arr = (C.c_void_p * len(elems))(*[e.h for e in elems]); return c._out(c.lib.fl_batch_pack, arr, len(elems))
+    def slices(b, n):
+        return [c._out(c.lib.fl_batch_slice, b.h, i) for i in range(n)]
+    for f in (c.lib.fl_batch_pack, c.lib.fl_batch_slice):
+        f.restype = C.c_int
+    c.lib.fl_batch_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    c.lib.fl_batch_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    cts = [enc(c, v) for v in vs]
+    b = pack(cts)
+    prod = slices(c.mult(b, b), 3)                                  # batched EvalMult(ct, ct)
+    for p, v in zip(prod, vs):
+        assert err(c, p, v * v) < 1e-7
+    one = enc(c, vs[0])
+    prod1 = slices(c.mult(b, one), 3)                               # right operand broadcast over the batch
+    for p, v in zip(prod1, vs):
+        assert err(c, p, v * vs[0]) < 1e-7
+    g = fc.invoke("eval_gelu_function", [b], reals=[-1, 1, 1 / 8.], ints=[119])[0]
+    for p, v in zip(slices(g, 3), vs):
+        assert err(c, p, s.eval_gelu_function(v, -1, 1, 1 / 8., 119)) < 1e-5
+    deep = pack([enc(c, v, level=24) for v in vs])
+    for p, v in zip(slices(fc.invoke("bootstrap", [deep])[0], 3), vs):
+        assert err(c, p, v) < 1e-5
+
+
 def test_bootstrap_variants_and_scalar_mult(env):
     fc, c, s, rng = env
     v = rng.uniform(-1, 1, s.n)
