@@ -504,6 +504,19 @@ vector<Ctxt> FHEController::project_rows(const vector<Ctxt>& rows, const vector<
     return out;
 }
 
+// FLEXIBLEAUTO rescales a degree-2 ciphertext right before its next multiplication.  When many rows are about to be
+// multiplied by DIFFERENT plaintexts (the mask loops of wrapUp*), the pending rescales are done here for all rows at once;
+// the multiplications that follow find degree-1 operands and produce the same limbs as if each had rescaled on its own.
+vector<Ctxt> FHEController::settle_rows(const vector<Ctxt>& rows) const {
+    if (!batch_rows) return rows;
+    return per_row(rows, [&](const Ctxt& r) {
+        if (r->GetNoiseScaleDeg() < 2) return r;
+        fl_elem* e = nullptr;
+        need(fl_rescale(ctx_, r->handle(), &e), "ModReduce");
+        return wrap(e);
+    });
+}
+
 /* ------------------------------------------------------------------ packed matrix products ------------------------------------------------------------------ */
 // "RE": rows arrive Expanded, weight is the row-major 128x128 matrix, summing over the 128 blocks (stride 128) leaves the
 // product Repeated.  "CR": rows arrive Repeated, summing inside each block (stride 1) leaves product entry j at slot 128 j.
@@ -591,6 +604,7 @@ Ctxt FHEController::matmulScores(Ctxt query, const Ctxt& key) { return mask_head
 
 // vector j (Repeated) keeps only its block j: the result holds vector j in slots 128 j .. 128 j + 127
 Ctxt FHEController::wrapUpRepeated(vector<Ctxt> vectors) {
+    vectors = settle_rows(vectors);
     vector<Ctxt> blocks;
     blocks.reserve(vectors.size());
     for (size_t i = 0; i < vectors.size(); ++i) blocks.push_back(mask_block(vectors[i], 128 * (int)i, 128 * ((int)i + 1), 1));
@@ -600,10 +614,12 @@ Ctxt FHEController::wrapUpRepeated(vector<Ctxt> vectors) {
 // vector t has entry j at slot 128 j; interleave so that slot 128 j + t holds (vector t)[j].  Horner over rotate(-1).
 Ctxt FHEController::wrapUpExpanded(vector<Ctxt> vectors) {
     const int n = (int)vectors.size();
-    Ctxt acc = mask_mod_n(vectors[n - 1], 128);
+    // every vector gets the same mask: one batched multiplication (and one batched pending rescale) for all of them
+    const vector<Ctxt> masked = per_row(vectors, [&](const Ctxt& v) { return mask_mod_n(v, 128); });
+    Ctxt acc = masked[n - 1];
     if (n > 1) acc = rotate(acc, -1);
     for (int i = n - 2; i >= 0; --i) {
-        acc = add(acc, mask_mod_n(vectors[i], 128));
+        acc = add(acc, masked[i]);
         if (i > 0) acc = rotate(acc, -1);
     }
     return acc;
@@ -611,7 +627,9 @@ Ctxt FHEController::wrapUpExpanded(vector<Ctxt> vectors) {
 
 // inverse of wrapUpExpanded: vector t comes back Expanded (entry j replicated over block j)
 vector<Ctxt> FHEController::unwrapExpanded(Ctxt c, int inputs_num) {
-    // the rotate(c, 1) chain is sequential; the 7-step replication ladders of the picked columns are independent
+    // the rotate(c, 1) chain is sequential; the 7-step replication ladders of the picked columns are independent.  The
+    // pending rescale of c is taken once up front instead of once per mask (rescaling commutes with rotation).
+    c = settle_rows({c})[0];
     vector<Ctxt> picked;
     picked.reserve(inputs_num);
     for (int t = 0; t < inputs_num; ++t) {
@@ -622,6 +640,7 @@ vector<Ctxt> FHEController::unwrapExpanded(Ctxt c, int inputs_num) {
 }
 
 vector<Ctxt> FHEController::unwrapScoresExpanded(Ctxt c, int inputs_num) {
+    c = settle_rows({c})[0];
     vector<Ctxt> lo, hi;
     for (int t = 0; t < inputs_num; ++t) {
         lo.push_back(mask_mod_n(c, 128, 0, inputs_num * 128));
@@ -647,6 +666,7 @@ vector<Ctxt> FHEController::unwrap_512_in_4_128(const Ctxt& c, int index) {
 
 vector<vector<Ctxt>> FHEController::unwrapRepeatedLarge(vector<Ctxt> containers, int input_number) {
     // every (token, 128-block) ladder of unwrap_512_in_4_128 is independent: mask them all, replicate them as batches
+    containers = settle_rows(containers);
     vector<Ctxt> blocks;
     for (size_t i = 0; i < containers.size(); ++i) {
         const int held = std::min(32, input_number - 32 * (int)i);

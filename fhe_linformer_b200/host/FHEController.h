@@ -158,6 +158,7 @@ public:
     Ctxt pack(const vector<Ctxt>& rows) const;
     vector<Ctxt> unpack(const Ctxt& packed) const;
     vector<Ctxt> per_row(const vector<Ctxt>& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const;
+    vector<Ctxt> settle_rows(const vector<Ctxt>& rows) const;   // pending FLEXIBLEAUTO rescales of many rows, as one batch
 
 private:
     void create(int log_ring, int depth, int digits, int first_bits, int scale_bits);
