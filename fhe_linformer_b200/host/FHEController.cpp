@@ -613,42 +613,62 @@ Ctxt FHEController::wrapUpRepeated(vector<Ctxt> vectors) {
 
 // vector t has entry j at slot 128 j; interleave so that slot 128 j + t holds (vector t)[j].  Horner over rotate(-1).
 Ctxt FHEController::wrapUpExpanded(vector<Ctxt> vectors) {
-    const int n = (int)vectors.size();
     // every vector gets the same mask: one batched multiplication (and one batched pending rescale) for all of them
     const vector<Ctxt> masked = per_row(vectors, [&](const Ctxt& v) { return mask_mod_n(v, 128); });
-    Ctxt acc = masked[n - 1];
-    if (n > 1) acc = rotate(acc, -1);
-    for (int i = n - 2; i >= 0; --i) {
-        acc = add(acc, masked[i]);
-        if (i > 0) acc = rotate(acc, -1);
+    // the reference's Horner chain acc = rot(acc, -1) + masked[i] equals sum_i rot(masked[i], -i)
+    return shifted_sum(masked, -1);
+}
+
+// sum_i rot(items[i], stride * i) as a binary tree: level b rotates every odd survivor by stride * 2^b -- one batched key
+// switch per level with the power-of-two key -- and adds it to its even neighbour.  Same result as the sequential Horner
+// chain the reference writes (F.cpp:1070-1084, 1193-1205) with log2(n) instead of n dependent rotations per item.
+Ctxt FHEController::shifted_sum(vector<Ctxt> items, int stride) {
+    if (!batch_rows) {
+        Ctxt acc = items.back();
+        for (int i = (int)items.size() - 2; i >= 0; --i) acc = add(rotate(acc, stride), items[i]);
+        return acc;
     }
-    return acc;
+    for (int step = stride; items.size() > 1; step *= 2) {
+        vector<Ctxt> even, odd;
+        for (size_t i = 0; i < items.size(); ++i) (i % 2 ? odd : even).push_back(items[i]);
+        const vector<Ctxt> moved = per_row(odd, [&](const Ctxt& r) { return rotate(r, step); });
+        for (size_t j = 0; j < moved.size(); ++j) even[j] = add(even[j], moved[j]);
+        items = even;
+    }
+    return items[0];
 }
 
 // inverse of wrapUpExpanded: vector t comes back Expanded (entry j replicated over block j)
+// rot(c, t) for t = 0 .. count-1.  The reference walks c = rotate(c, 1) count-1 times (F.cpp:1086-1100); here the set doubles:
+// step 2^b rotates everything produced so far by 2^b in one batched key switch, so rot(c, t) costs popcount(t) key switches
+// (less noise than t of them) and the chain is log2(count) launches deep.
+vector<Ctxt> FHEController::all_shifts(const Ctxt& c, int count) {
+    vector<Ctxt> out = {c};
+    if (!batch_rows) {
+        for (int t = 1; t < count; ++t) out.push_back(rotate(out.back(), 1));
+        return out;
+    }
+    for (int step = 1; step < count; step *= 2) {
+        const int take = std::min(step, count - step);
+        const vector<Ctxt> moved = per_row(vector<Ctxt>(out.begin(), out.begin() + take), [&](const Ctxt& r) { return rotate(r, step); });
+        out.insert(out.end(), moved.begin(), moved.end());
+    }
+    return out;
+}
+
 vector<Ctxt> FHEController::unwrapExpanded(Ctxt c, int inputs_num) {
     // the rotate(c, 1) chain is sequential; the 7-step replication ladders of the picked columns are independent.  The
     // pending rescale of c is taken once up front instead of once per mask (rescaling commutes with rotation).
     c = settle_rows({c})[0];
-    vector<Ctxt> picked;
-    picked.reserve(inputs_num);
-    for (int t = 0; t < inputs_num; ++t) {
-        picked.push_back(mask_mod_n(c, 128, 0, inputs_num * 128));
-        if (t < inputs_num - 1) c = rotate(c, 1);
-    }
-    return per_row(picked, [&](const Ctxt& r) { return repeat(r, 128); });
+    const vector<Ctxt> shifted = all_shifts(c, inputs_num);
+    return per_row(shifted, [&](const Ctxt& r) { return repeat(mask_mod_n(r, 128, 0, inputs_num * 128), 128); });
 }
 
 vector<Ctxt> FHEController::unwrapScoresExpanded(Ctxt c, int inputs_num) {
     c = settle_rows({c})[0];
-    vector<Ctxt> lo, hi;
-    for (int t = 0; t < inputs_num; ++t) {
-        lo.push_back(mask_mod_n(c, 128, 0, inputs_num * 128));
-        hi.push_back(mask_mod_n(c, 128, 64, inputs_num * 128));
-        if (t < inputs_num - 1) c = rotate(c, 1);
-    }
-    lo = per_row(lo, [&](const Ctxt& r) { return repeat(r, 64); });
-    hi = per_row(hi, [&](const Ctxt& r) { return repeat(r, 64); });
+    const vector<Ctxt> shifted = all_shifts(c, inputs_num);
+    vector<Ctxt> lo = per_row(shifted, [&](const Ctxt& r) { return repeat(mask_mod_n(r, 128, 0, inputs_num * 128), 64); });
+    vector<Ctxt> hi = per_row(shifted, [&](const Ctxt& r) { return repeat(mask_mod_n(r, 128, 64, inputs_num * 128), 64); });
     vector<Ctxt> out;
     for (int t = 0; t < inputs_num; ++t) out.push_back(add(lo[t], hi[t]));
     return out;
@@ -694,9 +714,13 @@ vector<Ctxt> FHEController::generate_containers(vector<Ctxt> inputs, const Ptxt&
 }
 
 Ctxt FHEController::wrap_containers(vector<Ctxt> c, int inputs_number) {
-    Ctxt acc = c[0];
-    for (int i = 1; i < inputs_number; ++i) acc = add(rotate(acc, -512), c[i]);
-    return acc;
+    // result = rot(... rot(c[0], -512) + c[1] ..., -512) + c[n-1] = sum_k rot(c[n-1-k], -512 k)
+    vector<Ctxt> items(c.rend() - inputs_number, c.rend());
+    for (int b = 0; (1 << b) < inputs_number; ++b) {
+        int k = -512 * (1 << b);
+        if (batch_rows && !fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
+    }
+    return shifted_sum(items, -512);
 }
 
 /* ------------------------------------------------------------------ masks ------------------------------------------------------------------ */

@@ -158,7 +158,9 @@ public:
     Ctxt pack(const vector<Ctxt>& rows) const;
     vector<Ctxt> unpack(const Ctxt& packed) const;
     vector<Ctxt> per_row(const vector<Ctxt>& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const;
-    vector<Ctxt> settle_rows(const vector<Ctxt>& rows) const;   // pending FLEXIBLEAUTO rescales of many rows, as one batch
+    vector<Ctxt> settle_rows(const vector<Ctxt>& rows) const;
+    Ctxt shifted_sum(vector<Ctxt> items, int stride);          // sum_i rot(items[i], stride * i), tree of batched rotations
+    vector<Ctxt> all_shifts(const Ctxt& c, int count);          // rot(c, t), t < count, by batched doubling   // pending FLEXIBLEAUTO rescales of many rows, as one batch
 
 private:
     void create(int log_ring, int depth, int digits, int first_bits, int scale_bits);
