@@ -100,7 +100,8 @@ void fl_ctx_destroy(fl_ctx* c) {
     delete c;
 }
 int fl_ctx_info(fl_ctx* c, int* info) {
-    FL_TRY({ const Params& P = c->eng->P; info[0] = P.logN; info[1] = P.L; info[2] = P.K; info[3] = P.alpha; info[4] = P.dnum; })
+    FL_TRY({ const Params& P = c->eng->P; info[0] = P.logN; info[1] = P.L; info[2] = P.K; info[3] = P.alpha; info[4] = P.dnum;
+             info[5] = (int)c->eng->pool_allocs; info[6] = (int)c->eng->cache_trims; info[7] = (int)(c->eng->cached_bytes() >> 20); })
 }
 int fl_ctx_moduli(fl_ctx* c, uint64_t* out) { FL_TRY(std::memcpy(out, c->eng->P.q.data(), 8 * c->eng->P.T)) }
 int fl_ctx_roots(fl_ctx* c, uint64_t* out) { FL_TRY(std::memcpy(out, c->eng->P.psi.data(), 8 * c->eng->P.T)) }

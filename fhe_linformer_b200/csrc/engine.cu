@@ -35,6 +35,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     uint64_t keep = ~0ull;
     FLK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 
+    if (const char* ev = std::getenv("FLK_CACHE_GB")) cache_cap_bytes_ = (size_t)std::atol(ev) << 30;
     if (const char* ev = std::getenv("FLK_L2_BUDGET_MB")) l2_budget_bytes = std::atol(ev) << 20;   // tuning knob (bench sweeps it)
     const int Tn = P.T, N = P.N;
     {   // twiddles interleaved with their Shoup companions so one 16-byte load fetches both
@@ -96,6 +97,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
 }
 
 Engine::~Engine() {
+    trim_cache(0);
     cudaStreamSynchronize(stream);
     for (auto& kv : maps_) cudaFree(kv.second);
     for (void* p : owned_) cudaFree(p);
@@ -104,12 +106,48 @@ Engine::~Engine() {
     cudaStreamDestroy(stream);
 }
 
+// Device memory comes from CUDA's stream-ordered pool, fronted by an exact-size cache: a forward pass asks for the same few
+// hundred block sizes over and over, and recycling a block of exactly that size on the one engine stream is free, whereas the
+// pool alone fragments under the mixed sizes and sporadically stalls for 0.2-1.4 s mapping new physical memory
+// (measured: scripts/forward_repeat.py).  Blocks are handed back to the pool only when the cache exceeds its cap.
 u64* Engine::alloc(size_t words) {
+    const size_t bytes = (std::max<size_t>(words, 1) * 8 + 0xFFFF) & ~(size_t)0xFFFF;
     u64* p = nullptr;
-    FLK_CUDA(cudaMallocAsync(&p, std::max<size_t>(words, 1) * 8, stream));
+    // smallest cached block that fits, as long as it wastes at most a quarter (adjacent levels differ by one limb in ~25)
+    auto it = free_blocks_.lower_bound(bytes);
+    while (it != free_blocks_.end() && it->second.empty()) ++it;
+    if (it != free_blocks_.end() && it->first <= bytes + bytes / 4) {
+        p = it->second.back();
+        it->second.pop_back();
+        cached_bytes_ -= it->first;
+        block_size_[p] = it->first;
+        return p;
+    } else {
+        FLK_CUDA(cudaMallocAsync(&p, bytes, stream));
+        ++pool_allocs;
+    }
+    block_size_[p] = bytes;
     return p;
 }
-void Engine::release(u64* p) { if (p) FLK_CUDA(cudaFreeAsync(p, stream)); }
+void Engine::release(u64* p) {
+    if (!p) return;
+    auto it = block_size_.find(p);
+    if (it == block_size_.end()) { FLK_CUDA(cudaFreeAsync(p, stream)); return; }
+    const size_t bytes = it->second;
+    block_size_.erase(it);
+    free_blocks_[bytes].push_back(p);
+    cached_bytes_ += bytes;
+    if (cached_bytes_ > cache_cap_bytes_) trim_cache(cache_cap_bytes_ / 8 * 7);
+}
+void Engine::trim_cache(size_t keep_bytes) {
+    ++cache_trims;
+    for (auto it = free_blocks_.rbegin(); it != free_blocks_.rend() && cached_bytes_ > keep_bytes; ++it)   // largest classes first
+        while (!it->second.empty() && cached_bytes_ > keep_bytes) {
+            cudaFreeAsync(it->second.back(), stream);
+            it->second.pop_back();
+            cached_bytes_ -= it->first;
+        }
+}
 void Engine::upload(u64* dst, const u64* src, size_t words) { FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyHostToDevice, stream)); }
 void Engine::download(u64* dst, const u64* src, size_t words) {
     FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyDeviceToHost, stream));

@@ -83,7 +83,14 @@ public:
     const RsConst& rs() const { return rs_; }
     size_t evk_words() const { return (size_t)P.dnum * 2 * P.T * P.N; }
 
+    void trim_cache(size_t keep_bytes);
+    long pool_allocs = 0, cache_trims = 0;               // allocator statistics (fl_ctx_info slots 5-7)
+    size_t cached_bytes() const { return cached_bytes_; }
+
 private:
+    std::map<size_t, std::vector<u64*>> free_blocks_;    // exact-size cache in front of the stream-ordered pool
+    std::unordered_map<u64*, size_t> block_size_;
+    size_t cached_bytes_ = 0, cache_cap_bytes_ = (size_t)96 << 30;   // of the 180 GB; FLK_CACHE_GB overrides
     std::vector<void*> owned_;
     template <class V> V* to_device(const std::vector<V>& h);
     std::unordered_map<int, KsLevel> ks_;

@@ -41,7 +41,7 @@ const char* fl_last_error(void);
 /* ---- context: GenCryptoContext F.cpp:37 ---- */
 int fl_ctx_create(const fl_params* p, int device, fl_ctx** out);
 void fl_ctx_destroy(fl_ctx* c);
-/* info[0..4] = logN, L, K, alpha, dnum */
+/* info[0..4] = logN, L, K, alpha, dnum; info[5..7] = allocator statistics: pool allocations, cache trims, cached MiB (8 ints) */
 int fl_ctx_info(fl_ctx* c, int* info);
 int fl_ctx_moduli(fl_ctx* c, uint64_t* out /* L+K */);
 int fl_ctx_roots(fl_ctx* c, uint64_t* out /* L+K */);
