@@ -101,21 +101,29 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
         shs[i] = make_uint2(h.lo, h.hi);
     }
     __syncthreads();
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= T.N) return;
-    Split30 y[A];
+    const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;   // two adjacent coefficients per thread: 16-byte accesses, and the
+    if (j >= T.N) return;                                        // conversion constants of a target are fetched once for both
+    Split30 y0[A], y1[A];
 #pragma unroll
-    for (int i = 0; i < A; ++i) y[i] = split30(i < ns ? dcoef[(size_t)b * dco_bs + (size_t)(lo + i) * T.N + j] : 0);
+    for (int i = 0; i < A; ++i) {
+        const ulonglong2 v = i < ns ? *reinterpret_cast<const ulonglong2*>(dcoef + (size_t)b * dco_bs + (size_t)(lo + i) * T.N + j) : make_ulonglong2(0, 0);
+        y0[i] = split30(v.x); y1[i] = split30(v.y);
+    }
     const int tg = gridDim.y, per = (ext + tg - 1) / tg;
     const int t0 = blockIdx.y * per, t1 = min(t0 + per, ext);
     u64* dst = up + (size_t)b * up_bs + (size_t)d * ext * T.N + j;
     for (int t = t0; t < t1; ++t) {
         if (t >= lo && t < hi) continue;
         const RedC rc = load_redc(T, t < l ? t : T.L + (t - l));
-        Acc3 acc{0, 0, 0};
+        Acc3 a0{0, 0, 0}, a1{0, 0, 0};
 #pragma unroll
-        for (int i = 0; i < A; ++i) { const uint2 h = shs[i * ext + t]; mac3(acc, y[i], Split30{h.x, h.y}); }
-        dst[(size_t)t * T.N] = reduce3(acc, rc);
+        for (int i = 0; i < A; ++i) {
+            const uint2 h = shs[i * ext + t];
+            mac3(a0, y0[i], Split30{h.x, h.y});
+            mac3(a1, y1[i], Split30{h.x, h.y});
+        }
+        // the forward NTT that follows takes lazily reduced operands (< 4q)
+        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce3_lazy(a0, rc), reduce3_lazy(a1, rc));
     }
 }
 
@@ -245,20 +253,27 @@ __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict_
         shs[i] = make_uint2(h.lo, h.hi);
     }
     __syncthreads();
-    const int j = blockIdx.x * kThreads + threadIdx.x;
+    const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
     if (j >= T.N) return;
-    Split30 y[KK];
+    Split30 y0[KK], y1[KK];
 #pragma unroll
-    for (int k = 0; k < KK; ++k) y[k] = split30(pcoef[(size_t)b * p_bs + (size_t)p * pstride + (size_t)k * T.N + j]);
+    for (int k = 0; k < KK; ++k) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pcoef + (size_t)b * p_bs + (size_t)p * pstride + (size_t)k * T.N + j);
+        y0[k] = split30(v.x); y1[k] = split30(v.y);
+    }
     const int tg = gridDim.y, per = (l + tg - 1) / tg;
     const int t0 = blockIdx.y * per, t1 = min(t0 + per, l);
     u64* dst = tq + (size_t)b * tq_bs + (size_t)p * l * T.N + j;
     for (int t = t0; t < t1; ++t) {
         const RedC rc = load_redc(T, t);
-        Acc3 acc{0, 0, 0};
+        Acc3 a0{0, 0, 0}, a1{0, 0, 0};
 #pragma unroll
-        for (int k = 0; k < KK; ++k) { const uint2 h = shs[k * l + t]; mac3(acc, y[k], Split30{h.x, h.y}); }
-        dst[(size_t)t * T.N] = reduce3(acc, rc);
+        for (int k = 0; k < KK; ++k) {
+            const uint2 h = shs[k * l + t];
+            mac3(a0, y0[k], Split30{h.x, h.y});
+            mac3(a1, y1[k], Split30{h.x, h.y});
+        }
+        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce3_lazy(a0, rc), reduce3_lazy(a1, rc));   // < 4q: NTT operand
     }
 }
 
@@ -427,7 +442,7 @@ void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, 
 void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s) {
     if (ks.alpha > kAlphaMax) throw std::invalid_argument("digit size above 8 limbs is not supported");
     const int ext = ks.l + t.K, tg = ext >= 16 ? 4 : 1;
-    const dim3 grid(cdiv(t.N, kThreads), tg, ks.beta * batch);
+    const dim3 grid(cdiv(t.N / 2, kThreads), tg, ks.beta * batch);
     const size_t shm = (size_t)ks.alpha * ext * 8;
     switch (ks.alpha) {
 #define FLK_CASE(X) case X: modup_conv_kernel<X><<<grid, kThreads, shm, s>>>(up, dcoef, t, ks, up_bs, dco_bs); break;
@@ -474,7 +489,7 @@ void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u
                          size_t tq_bs, size_t p_bs, cudaStream_t s) {
     if (t.K > kAlphaMax) throw std::invalid_argument("more than 8 P limbs is not supported");
     const int tg = l >= 16 ? 4 : 1;
-    const dim3 grid(cdiv(t.N, kThreads), tg, polys * batch);
+    const dim3 grid(cdiv(t.N / 2, kThreads), tg, polys * batch);
     const size_t shm = (size_t)t.K * l * 8;
     switch (t.K) {
 #define FLK_CASE(X) case X: moddown_conv_kernel<X><<<grid, kThreads, shm, s>>>(tq, pcoef, pstride, t, md, l, polys, tq_bs, p_bs); break;

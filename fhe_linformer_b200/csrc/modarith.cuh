@@ -107,6 +107,13 @@ struct __align__(16) RedC {
 };
 // (a0 + a1 2^30 + a2 2^60) mod q, canonical: the two high accumulators through lazy Shoup products with 2^30, 2^60 mod q,
 // then one single-word Barrett step.  a0 + 8q < 2^64 since q < 2^60.
+// the same, stopping at a value in [0, 4q): enough for operands of the forward NTT, whose lazy butterflies accept it
+__device__ __forceinline__ u64 reduce3_lazy(const Acc3& s, const RedC& k) {
+    const u64 t1 = shoup_lazy4(s.a1, k.c30, k.c30s, k.nq);
+    const u64 t2 = shoup_lazy4(s.a2, k.c60, k.c60s, k.nq);
+    const u64 u = s.a0 + t1 + t2;
+    return u + mulhi_lazy(u, k.mu64) * k.nq;
+}
 __device__ __forceinline__ u64 reduce3(const Acc3& s, const RedC& k) {
     const u64 t1 = shoup_lazy4(s.a1, k.c30, k.c30s, k.nq);
     const u64 t2 = shoup_lazy4(s.a2, k.c60, k.c60s, k.nq);
