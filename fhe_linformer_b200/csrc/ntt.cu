@@ -89,25 +89,28 @@ __device__ __forceinline__ u64 final_reduce(u64 v, u64 q, u64 q4, u64 nq, u64 qi
 constexpr int R1 = 1 << kRadix1Log;
 
 template <bool FWD>
-__global__ void __launch_bounds__(256) ntt_column_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride,
+__global__ void __launch_bounds__(256, 3) ntt_column_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride,
                                                          const u64* __restrict__ post, const u64* __restrict__ post_sh) {
+    // the 15 twiddles of these four stages are the same for every column of a limb: one copy per CTA in shared memory
+    // (broadcast reads) instead of 60 registers per thread
+    __shared__ ulonglong2 stw[R1];
     const int limb = blockIdx.y, m = sel.m[limb];
     const int cols = T.N >> kRadix1Log;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x < R1 - 1) stw[threadIdx.x] = __ldg((FWD ? T.tw2 : T.itw2) + (size_t)m * T.N + 1 + threadIdx.x);   // table entries 1..15 in block order
+    __syncthreads();
     if (c >= cols) return;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + c;
     const u64 q = T.q[m], nq = 0 - q, q4 = q << 2;
     u64 e[R1];
 #pragma unroll
     for (int k = 0; k < R1; ++k) e[k] = a[(size_t)k * cols];
-    ulonglong2 t[R1 - 1];
-    load_tw<kRadix1Log>(t, (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N, 1);
     if (FWD) {
-        if (is_wide(q)) ct_block<kRadix1Log, true>(e, t, nq, q4); else ct_block<kRadix1Log, false>(e, t, nq, q4);
+        if (is_wide(q)) ct_block<kRadix1Log, true>(e, stw, nq, q4); else ct_block<kRadix1Log, false>(e, stw, nq, q4);
 #pragma unroll
-        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 8q (wide) or < 17q (narrow)
+        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 8q (wide) or < 20q (narrow)
     } else {
-        gs_block<kRadix1Log>(e, t, nq, q4);
+        gs_block<kRadix1Log>(e, stw, nq, q4);
         const u64 w = post ? post[m] : T.ninv[m], ws = post ? post_sh[m] : T.ninv_sh[m];
 #pragma unroll
         for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = mul_shoup(e[k], w, ws, q);
