@@ -154,6 +154,16 @@ int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_
     FL_TRY(c->eng->ew(EwOp::Mul, out, ct, pt, l, 2, true))
 }
 
+int fl_raw_ks_digits(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l) { FL_TRY(c->eng->ks_digits(dco, poly, l)) }
+int fl_raw_ks_modup(fl_ctx* c, uint64_t* up, const uint64_t* dco, int l, int first, int count) { FL_TRY(c->eng->ks_modup_part(up, dco, l, first, count)) }
+int fl_raw_ks_inner(fl_ctx* c, uint64_t* acc, const uint64_t* up, const uint64_t* poly, const uint64_t* evk, int l, int first, int count) {
+    FL_TRY(c->eng->ks_inner_part(acc, up, poly, evk, l, first, count))
+}
+int fl_raw_ks_pcoef(fl_ctx* c, uint64_t* acc, int l, int first, int count) { FL_TRY(c->eng->ks_pcoef_part(acc, l, first, count)) }
+int fl_raw_ks_moddown(fl_ctx* c, uint64_t* out, uint64_t* tq, const uint64_t* acc, int l, int first, int count, const uint64_t* add0,
+                      const uint64_t* add1, uint32_t g) {
+    FL_TRY(c->eng->ks_moddown_part(out, tq, acc, l, first, count, add0, add1, g))
+}
 int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse) {
     FL_TRY({
         Engine& e = *c->eng;

@@ -296,6 +296,50 @@ void Engine::rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64*
     }
 }
 
+// ---- limb-sharded key switch: the stages of keyswitch() restricted to limb ranges of the extended basis ----
+// G ranks hold the same input polynomial and split the l + K limbs of Q_l u P between them (sharded.py).  Every stage is
+// limb-wise independent except the two base conversions, which need all source limbs: the digits (cheap, recomputed by every
+// rank) and the P limbs of the accumulators (exchanged over NVLink between ks_pcoef_part and ks_moddown_part).
+void Engine::ks_digits(u64* dco, const u64* c, int l) {
+    const KsLevel& ks = ks_level(l);
+    copy(dco, c, (size_t)l * P.N);
+    launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
+}
+void Engine::ks_modup_part(u64* up, const u64* dco, int l, int first, int count) {
+    const KsLevel& ks = ks_level(l);
+    const int ext = l + P.K;
+    launch_modup_conv(T, ks, up, dco, 1, 0, 0, stream, LimbRange{first, count});
+    LimbSel su; su.n = 0;
+    for (int d = 0; d < ks.beta; ++d) {
+        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
+        for (int t = first; t < first + count; ++t) {
+            if (t >= lo && t < hi) continue;
+            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+        }
+    }
+    launch_ntt(T, up, su, 1, 0, stream);
+}
+void Engine::ks_inner_part(u64* acc, const u64* up, const u64* c, const u64* evk, int l, int first, int count) {
+    launch_inner_product(T, ks_level(l), acc, up, c, evk, 1, 0, 0, 0, stream, LimbRange{first, count});
+}
+void Engine::ks_pcoef_part(u64* acc, int l, int first, int count) {   // first, count: a range of the K special limbs (0-based inside P)
+    const int ext = l + P.K;
+    LimbSel sp; sp.n = 0;
+    for (int p = 0; p < 2; ++p)
+        for (int k = first; k < first + count; ++k) { sp.m[sp.n] = (uint8_t)(P.L + k); sp.pos[sp.n] = (uint8_t)(p * ext + l + k); sp.n++; }
+    launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
+}
+void Engine::ks_moddown_part(u64* out, u64* tq, const u64* acc, int l, int first, int count, const u64* add0, const u64* add1, uint32_t g) {
+    const int N = P.N, ext = l + P.K;
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, 1, 0, 0, stream, LimbRange{first, count});
+    LimbSel sq; sq.n = 0;
+    for (int p = 0; p < 2; ++p)
+        for (int i = first; i < first + count; ++i) { sq.m[sq.n] = (uint8_t)i; sq.pos[sq.n] = (uint8_t)(p * l + i); sq.n++; }
+    launch_ntt(T, tq, sq, 1, 0, stream);
+    FinishArgs fa{out, 0, acc, (size_t)ext * N, 0, tq, 0, add0, 0, add1, 0, nullptr, 0};
+    launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, 1, stream, LimbRange{first, count});
+}
+
 // Hoisted rotate-and-sum: out = (self ? ct : 0) + sum_k sigma_k(ct) for nk rotations of the SAME ciphertexts.  The digit
 // decomposition / ModUp (45 % of a key switch) is done once, the nk evaluation-key inner products accumulate -- each gathered
 // through its automorphism map -- in the extended basis Q_l u P, and a single ModDown brings the sum back (double hoisting,

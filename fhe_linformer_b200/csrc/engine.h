@@ -73,6 +73,12 @@ public:
     void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
     void mul_relin_batch(u64* out, const u64* a, const u64* b, int l, const u64* evk, int B, size_t b_bs);   // a, out: [B][2][l][N]
+    // limb-sharded key switch: one stage each, restricted to [first, first + count) of the extended basis (engine.cu)
+    void ks_digits(u64* dco, const u64* c, int l);
+    void ks_modup_part(u64* up, const u64* dco, int l, int first, int count);
+    void ks_inner_part(u64* acc, const u64* up, const u64* c, const u64* evk, int l, int first, int count);
+    void ks_pcoef_part(u64* acc, int l, int first, int count);
+    void ks_moddown_part(u64* out, u64* tq, const u64* acc, int l, int first, int count, const u64* add0, const u64* add1, uint32_t g);
     // pieces exposed for parity tests
     void modup(u64* out_ext, const u64* c_eval, int l, int digit);     // out: (l+K) limbs eval
     void moddown(u64* out, const u64* in_ext, int l);                  // in: (l+K) limbs eval

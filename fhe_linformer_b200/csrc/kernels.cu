@@ -92,7 +92,7 @@ __device__ __forceinline__ RedC load_redc(const DevTables& T, int m) {
 // grid: (N / 256, target groups, batch * beta); buffers carry a batch stride.
 template <int A>
 __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ up, const u64* __restrict__ dcoef, DevTables T, KsLevel ks,
-                                                              size_t up_bs, size_t dco_bs) {
+                                                              size_t up_bs, size_t dco_bs, LimbRange rg) {
     extern __shared__ uint2 shs[];
     const int d = blockIdx.z % ks.beta, b = blockIdx.z / ks.beta, l = ks.l, ext = l + T.K;
     const int lo = d * A, hi = min(lo + A, l), ns = hi - lo;
@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
         const ulonglong2 v = i < ns ? *reinterpret_cast<const ulonglong2*>(dcoef + (size_t)b * dco_bs + (size_t)(lo + i) * T.N + j) : make_ulonglong2(0, 0);
         y0[i] = split30(v.x); y1[i] = split30(v.y);
     }
-    const int tg = gridDim.y, per = (ext + tg - 1) / tg;
-    const int t0 = blockIdx.y * per, t1 = min(t0 + per, ext);
+    const int tg = gridDim.y, per = (rg.count + tg - 1) / tg;   // targets rg.first .. rg.first + rg.count - 1 (all of them on one GPU)
+    const int t0 = rg.first + blockIdx.y * per, t1 = min(t0 + per, rg.first + rg.count);
     u64* dst = up + (size_t)b * up_bs + (size_t)d * ext * T.N + j;
     for (int t = t0; t < t1; ++t) {
         if (t >= lo && t < hi) continue;
@@ -134,8 +134,8 @@ constexpr int kIpb = 4;
 template <int BETA>
 __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                  const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,
-                                                                 size_t up_bs, size_t c_bs) {
-    const int t = blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * kIpb;
+                                                                 size_t up_bs, size_t c_bs, int t_first) {
+    const int t = t_first + blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * kIpb;
     const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(u64* __restrict__ 
 // grid: (N / 256, target groups, batch * polys); pcoef = P part (coefficient form, pre-scaled) of accumulator (b, p)
 template <int KK>
 __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
-                                                                MdConst md, int l, int polys, size_t tq_bs, size_t p_bs) {
+                                                                MdConst md, int l, int polys, size_t tq_bs, size_t p_bs, LimbRange rg) {
     extern __shared__ uint2 shs[];
     const int p = blockIdx.z % polys, b = blockIdx.z / polys;
     for (int i = threadIdx.x; i < KK * l; i += kThreads) {
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict_
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(pcoef + (size_t)b * p_bs + (size_t)p * pstride + (size_t)k * T.N + j);
         y0[k] = split30(v.x); y1[k] = split30(v.y);
     }
-    const int tg = gridDim.y, per = (l + tg - 1) / tg;
-    const int t0 = blockIdx.y * per, t1 = min(t0 + per, l);
+    const int tg = gridDim.y, per = (rg.count + tg - 1) / tg;
+    const int t0 = rg.first + blockIdx.y * per, t1 = min(t0 + per, rg.first + rg.count);
     u64* dst = tq + (size_t)b * tq_bs + (size_t)p * l * T.N + j;
     for (int t = t0; t < t1; ++t) {
         const RedC rc = load_redc(T, t);
@@ -282,8 +282,9 @@ __global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restric
                                                                   const u64* __restrict__ tq, const u64* __restrict__ add0,
                                                                   const u64* __restrict__ add1, const uint32_t* __restrict__ map, DevTables T,
                                                                   MdConst md, int l, int polys, size_t out_bs, size_t acc_bs, size_t tq_bs,
-                                                                  size_t add0_bs, size_t add1_bs, const u64* __restrict__ plus, size_t plus_bs) {
-    const int i = blockIdx.y, p = blockIdx.z % polys, b = blockIdx.z / polys;
+                                                                  size_t add0_bs, size_t add1_bs, const u64* __restrict__ plus, size_t plus_bs,
+                                                                  int i_first) {
+    const int i = i_first + blockIdx.y, p = blockIdx.z % polys, b = blockIdx.z / polys;
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int src = map ? map[j] : j;
@@ -439,23 +440,29 @@ void launch_tensor(const DevTables& t, u64* d0, u64* d1, u64* d2, const u64* a, 
     tensor_kernel<<<dim3(cdiv((size_t)l * t.N, kThreads), batch), kThreads, 0, s>>>(d0, d1, d2, a, b, t, l, d_bs, a_bs, b_bs);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s) {
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s,
+                       LimbRange rg) {
     if (ks.alpha > kAlphaMax) throw std::invalid_argument("digit size above 8 limbs is not supported");
-    const int ext = ks.l + t.K, tg = ext >= 16 ? 4 : 1;
+    const int ext = ks.l + t.K;
+    if (rg.count < 0) rg = LimbRange{0, ext};
+    if (rg.count == 0) return;
+    const int tg = rg.count >= 16 ? 4 : 1;
     const dim3 grid(cdiv(t.N / 2, kThreads), tg, ks.beta * batch);
     const size_t shm = (size_t)ks.alpha * ext * 8;
     switch (ks.alpha) {
-#define FLK_CASE(X) case X: modup_conv_kernel<X><<<grid, kThreads, shm, s>>>(up, dcoef, t, ks, up_bs, dco_bs); break;
+#define FLK_CASE(X) case X: modup_conv_kernel<X><<<grid, kThreads, shm, s>>>(up, dcoef, t, ks, up_bs, dco_bs, rg); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
 #undef FLK_CASE
     }
     FLK_CUDA(cudaGetLastError());
 }
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
-                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s) {
-    const dim3 grid(cdiv(t.N / 2, kThreads), ks.l + t.K, (batch + kIpb - 1) / kIpb);
+                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange rg) {
+    if (rg.count < 0) rg = LimbRange{0, ks.l + t.K};
+    if (rg.count == 0) return;
+    const dim3 grid(cdiv(t.N / 2, kThreads), rg.count, (batch + kIpb - 1) / kIpb);
     switch (ks.beta) {
-#define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch, acc_bs, up_bs, c_bs); break;
+#define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch, acc_bs, up_bs, c_bs, rg.first); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
 #undef FLK_CASE
         default: throw std::invalid_argument("more than 8 key-switch digits is not supported");
@@ -486,23 +493,27 @@ void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_
     FLK_CUDA(cudaGetLastError());
 }
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
-                         size_t tq_bs, size_t p_bs, cudaStream_t s) {
+                         size_t tq_bs, size_t p_bs, cudaStream_t s, LimbRange rg) {
     if (t.K > kAlphaMax) throw std::invalid_argument("more than 8 P limbs is not supported");
-    const int tg = l >= 16 ? 4 : 1;
+    if (rg.count < 0) rg = LimbRange{0, l};
+    if (rg.count == 0) return;
+    const int tg = rg.count >= 16 ? 4 : 1;
     const dim3 grid(cdiv(t.N / 2, kThreads), tg, polys * batch);
     const size_t shm = (size_t)t.K * l * 8;
     switch (t.K) {
-#define FLK_CASE(X) case X: moddown_conv_kernel<X><<<grid, kThreads, shm, s>>>(tq, pcoef, pstride, t, md, l, polys, tq_bs, p_bs); break;
+#define FLK_CASE(X) case X: moddown_conv_kernel<X><<<grid, kThreads, shm, s>>>(tq, pcoef, pstride, t, md, l, polys, tq_bs, p_bs, rg); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
 #undef FLK_CASE
     }
     FLK_CUDA(cudaGetLastError());
 }
 void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
-                           cudaStream_t s) {
-    moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), l, polys * batch), kThreads, 0, s>>>(a.out, a.acc, a.acc_ps, a.tq, a.add0, a.add1, map, t, md, l,
-                                                                                          polys, a.out_bs, a.acc_bs, a.tq_bs, a.add0_bs, a.add1_bs,
-                                                                                          a.plus, a.plus_bs);
+                           cudaStream_t s, LimbRange rg) {
+    if (rg.count < 0) rg = LimbRange{0, l};
+    if (rg.count == 0) return;
+    moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), rg.count, polys * batch), kThreads, 0, s>>>(a.out, a.acc, a.acc_ps, a.tq, a.add0, a.add1, map, t, md, l,
+                                                                                                 polys, a.out_bs, a.acc_bs, a.tq_bs, a.add0_bs,
+                                                                                                 a.add1_bs, a.plus, a.plus_bs, rg.first);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int n_in, int n_out, cudaStream_t s) {

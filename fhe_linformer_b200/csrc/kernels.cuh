@@ -42,13 +42,21 @@ struct MdConst {          // ModDown constants (level independent)
     const u64* pinv_sh;
 };
 
+// A contiguous range of limbs a launch is restricted to (count < 0: all).  One GPU always takes everything; the limb-sharded
+// key switch (sharded.py) gives every rank its own ranges of the extended basis.
+struct LimbRange {
+    int first, count;
+};
+constexpr LimbRange kAllLimbs{0, -1};
+
 // All key-switch kernels take a batch of ciphertexts (same limb count, same key); *_bs are batch strides in words.
 // up[b][d][t][N] (coefficient form) for all digits d and all extended limbs t outside digit d.
 // dcoef = INTT(c) already scaled by KsLevel::post, [b][l][N].
-void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s);
+void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64* dcoef, int batch, size_t up_bs, size_t dco_bs, cudaStream_t s,
+                       LimbRange targets = kAllLimbs);
 // acc[b][{0,1}][t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[b][t] inside digit d else up[b][d][t]
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
-                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
+                          size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
 // hoisted multi-rotation: acc[b][{0,1}][t][j] = sum_k (sum_d U_d[b][t] evk_k[d][mod(t)])[map_k[j]], nk <= 8 keys with their gather maps
 void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
                                 const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
@@ -58,7 +66,7 @@ void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_
 // tq[b][p][i][N] (coefficient form), i < l, from the scaled INTT of the P part of `polys` accumulators.
 // pcoef = [b][polys][K][N] with poly stride pstride and batch stride p_bs
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
-                         size_t tq_bs, size_t p_bs, cudaStream_t s);
+                         size_t tq_bs, size_t p_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
 // out[b][p][i][j] = ((acc[b][p][i] - tq[b][p][i]) * P^-1 + add_p[b][i])[map ? map[j] : j] + (plus ? plus[b][p][i][j] : 0)
 struct FinishArgs {
     u64* out; size_t out_bs;
@@ -69,7 +77,7 @@ struct FinishArgs {
     const u64* plus; size_t plus_bs;
 };
 void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
-                           cudaStream_t s);
+                           cudaStream_t s, LimbRange limbs = kAllLimbs);
 
 // out[o] = sum_t k[o][t] in[t] over ciphertexts: in [n_in][2][l][N], out [n_out][2][l][N], k [n_out][n_in][l][2] = {residue, Shoup}
 void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int n_in, int n_out, cudaStream_t s);

@@ -76,6 +76,17 @@ int fl_raw_rotate_batch(fl_ctx* c, uint64_t* out, const uint64_t* ct, int l, uin
 int fl_raw_mul_relin(fl_ctx* c, uint64_t* out, const uint64_t* a, const uint64_t* b, int l, const uint64_t* evk);   /* EvalMult(ct,ct) F.cpp:431 */
 int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_t* pt, int l);   /* EvalMult(ct,pt) F.cpp:427 */
 
+/* ---- limb-sharded key switch (optional multi-GPU mode, fhe_linformer_b200/sharded.py): the stages of the hybrid key switch
+ * restricted to a contiguous limb range [first, first + count) of the extended basis Q_l u P.  Work buffers are full size:
+ * dco [l][N], up [beta][l+K][N], acc [2][l+K][N], tq [2][l][N], out [2][l][N].  Between fl_raw_ks_pcoef and
+ * fl_raw_ks_moddown the ranks exchange the P limbs of acc (coefficient form), after fl_raw_ks_moddown the limbs of out. ---- */
+int fl_raw_ks_digits(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l);                                   /* scaled INTT of the digits */
+int fl_raw_ks_modup(fl_ctx* c, uint64_t* up, const uint64_t* dco, int l, int first, int count);                /* ModUp of targets in range */
+int fl_raw_ks_inner(fl_ctx* c, uint64_t* acc, const uint64_t* up, const uint64_t* poly, const uint64_t* evk, int l, int first, int count);
+int fl_raw_ks_pcoef(fl_ctx* c, uint64_t* acc, int l, int first, int count);   /* first, count: range inside the K special limbs */
+int fl_raw_ks_moddown(fl_ctx* c, uint64_t* out, uint64_t* tq, const uint64_t* acc, int l, int first, int count, const uint64_t* add0,
+                      const uint64_t* add1, uint32_t g);
+
 /* ---- the same operations with HOST buffers: H2D copy, kernels, D2H copy (what a host-resident caller pays) ---- */
 int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse);
 int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev);

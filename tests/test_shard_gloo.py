@@ -50,3 +50,17 @@ def test_partition_edges():
     assert sum(len(shard.my_units(1000, r, 3)) for r in range(3)) == 1000
     tot, worst, rate = shard.combine(10, 2.0)                # no process group: identity
     assert (tot, worst, rate) == (10.0, 2.0, 5.0)
+
+
+def test_limb_ranges_of_the_sharded_key_switch_cover_the_extended_basis():
+    """Host logic of sharded.py without a GPU: every limb of Q_l u P is owned by exactly one rank, for ragged splits too."""
+    from types import SimpleNamespace
+    from fhe_linformer_b200 import sharded
+    eng = SimpleNamespace(K=7, N=16, alpha=7)
+    for l in (28, 13, 2, 1):
+        for world in (1, 2, 3, 4, 8):
+            owned = []
+            for r in range(world):
+                st = sharded._RankState(eng, l, r, world, torch.device("cpu"))
+                owned += [t for first, count in st.ranges() for t in range(first, first + count)]
+            assert sorted(owned) == list(range(l + 7)), (l, world)
