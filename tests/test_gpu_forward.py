@@ -102,3 +102,21 @@ def test_key_files_roundtrip_and_resume(setup):
     r = other.ckks.rotate(back, 4)
     assert np.abs(other.ckks.decrypt(r) - np.roll(v, -4)).max() < 1e-8
     other.close()
+
+
+def test_maximum_rows_forward_S256(tmp_path):
+    """The circuit's upper bound, S = 256 rows (two full halves of 128): logits against the slot simulator, and the row-count
+    guards at both ends (the reference simply misbehaves outside 129..256)."""
+    from fhe_linformer_b200 import host, synth
+    from oracle import linformer_sim as ls
+    model = synth.make_model(n_classes=20)
+    sample = synth.make_sample(model, 255, seed=99)
+    dirs = synth.write_files(str(tmp_path), model, sample)
+    fc = host.FHEController(root=str(tmp_path)).generate()
+    logits, stages, S = fc.forward(dirs, dead_work=False)
+    ref = ls.sim_forward(model, sample)
+    assert S == 256
+    assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
+    with pytest.raises(RuntimeError, match="129 <= S <= 256"):
+        fc.forward(dirs, token_limit=100)           # S = 101: below the two-half packing
+    fc.close()

@@ -54,3 +54,15 @@ def test_reference_main_compiles_against_the_veneer():
     r = subprocess.run(["make", "-C", HOST, "reference-main-check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert os.path.exists("/tmp/flb200_refmain/FHE-Linformer")
+
+
+def test_command_line_usage_and_missing_keys(tmp_path):
+    """bin/fhe_linformer: no arguments prints the usage and exits 0 (main.cpp:43-46); loading from a folder without key files
+    prints the reference's message and exits 1 (FHEController.cpp:192-195) -- before any GPU work, so this runs on CPU."""
+    exe = os.path.join(ROOT, "fhe_linformer_b200", "bin", "fhe_linformer")
+    if not os.path.exists(exe):
+        pytest.skip("binary not built")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "Usage" in r.stdout
+    r = subprocess.run([exe, "--verbose", "--root", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1 and "I cannot read serialized data" in r.stderr
