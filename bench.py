@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the encrypted Linformer forward (extra `forward` key)")
     ap.add_argument("--forward-rows", type=int, default=129, help="S = rows of the forward sample (129..256)")
+    ap.add_argument("--forward-logn", type=int, default=15, help="ring of the forward: 15 = the reference's parameters, 16 = its commented-out variant (sparse packing)")
     return ap.parse_args()
 
 
@@ -303,7 +304,7 @@ def run_forward(a, local, rank, world, torch, dist):
     saved = os.dup(1)
     os.dup2(devnull, 1)                       # the controller prints the reference's progress messages on stdout
     try:
-        fc = host.FHEController(device=local, root=root).generate()
+        fc = host.FHEController(device=local, root=root).generate(log_ring=0 if a.forward_logn == 15 else a.forward_logn)
         fc.forward(dirs, dead_work=True)      # warm-up: mask / weight encodings, allocator pool, lazy rotation keys
         fc.ckks.ledger(True); fc.ckks.ledger_reset()
         runs = []
@@ -332,7 +333,7 @@ def run_forward(a, local, rank, world, torch, dist):
     dt, lean = float(t[0].item()), float(t[1].item())
     rot = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
     alg = sum(b for _, b in led.values())
-    return {"seconds_per_sample": dt, "samples_per_s": world / dt, "rows_S": S, "ring": "N=2^15, 28 limbs, dnum 4, 2^14 slots",
+    return {"seconds_per_sample": dt, "samples_per_s": world / dt, "rows_S": S, "ring": "N=2^%d, 28 limbs, dnum 4, 2^14 slots" % a.forward_logn,
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],

@@ -132,8 +132,12 @@ LinStage plan_stage(const Diag& M, int n, int g) {
 }  // namespace
 
 void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
-    const int n = P.N / 2;
-    if (slots != n) throw std::invalid_argument("EvalBootstrapSetup: only full packing (slots = N/2) is implemented");
+    // Full packing (slots = N/2, the reference's N = 2^15 configuration) or sparse packing (slots < N/2, e.g. the 2^14 slots of
+    // the reference at its commented-out N = 2^16): the slot values then live in the subring Y = X^gap, a trace over the
+    // gap conjugates (SubSum, in bootstrap()) projects the raised polynomial onto it, and the same special-FFT matrices
+    // of size `slots` do the rest.
+    const int n = slots;
+    if (n < 2 || n > P.N / 2 || (n & (n - 1))) throw std::invalid_argument("EvalBootstrapSetup: slots must be a power of two <= N/2");
     if (boot_.count(slots)) return;
     auto bp = std::make_shared<BootPrecomp>();
     bp->slots = slots;
@@ -192,7 +196,8 @@ void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
         return out;
     };
     // CtS: U0^-1 z = (t_lo + i t_hi)/sf0; want (t_lo + i t_hi)/(K q0), halved because re/im are taken as ct +- conj(ct)
-    bp->cts = build(true, budget_cts, 0.5 * P.sf[0] / (q0 * bp->K), 0);
+    const int gap = (P.N / 2) / n;   // SubSum multiplies the message by gap: folded into the CoeffsToSlots constant
+    bp->cts = build(true, budget_cts, 0.5 * P.sf[0] / (q0 * bp->K * gap), 0);
     // StC: sin(2 pi t/q0) ~ 2 pi m'/q0 with m' = sf0 2^-corr enc(v)  =>  multiply by q0 2^corr / (2 pi sf0)
     bp->stc = build(false, budget_stc, q0 * std::ldexp(1.0, bp->corr) / (2.0 * M_PI * P.sf[0]), stc_level0);
     for (auto* stages : {&bp->cts, &bp->stc})
@@ -218,6 +223,7 @@ std::vector<int> Scheme::bootstrap_rotations(int slots) {
             for (int b = 1; b < st.n1; ++b) r.push_back(st.g * b);
             for (int gr : st.giant_rot) if (gr) r.push_back(gr);
         }
+    for (int k = slots; k < P.N / 2; k <<= 1) r.push_back(k);   // SubSum of sparse packing
     std::sort(r.begin(), r.end());
     r.erase(std::unique(r.begin(), r.end()), r.end());
     return r;
@@ -268,7 +274,7 @@ Elem Scheme::bootstrap(const Elem& in) {
     auto it = boot_.find(in.slots);
     if (it == boot_.end()) throw std::runtime_error("EvalBootstrap: EvalBootstrapSetup was not called for this slot count");
     BootPrecomp& bp = *it->second;
-    const int N = P.N, n = N / 2, L = P.L;
+    const int N = P.N, n = in.slots, L = P.L;
     Elem ct = in;
     if (ct.deg == 2) {
         if (ct.l < 2) throw std::runtime_error("EvalBootstrap: degree-2 ciphertext at the last level");
@@ -298,6 +304,8 @@ Elem Scheme::bootstrap(const Elem& in) {
         eng.ntt(raised.data(), sel_range(0, L), 2 * B, (size_t)L * N);
         eng.release(x);
     }
+    // ---- SubSum (sparse packing only): trace onto the subring of the slots, raised <- sum of its gap conjugates
+    for (int k = n; k < N / 2; k <<= 1) raised = add(raised, rotate(raised, k));
     // ---- CoeffsToSlots
     Elem c = raised;
     for (auto& st : bp.cts) c = apply_stage(*this, st, c, n);

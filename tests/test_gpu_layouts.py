@@ -175,6 +175,22 @@ def test_batched_bootstrap_chebyshev_and_ct_mult(env):
         assert err(c, p, v) < 1e-5
 
 
+def test_sparse_packing_bootstrap(env):
+    """Bootstrapping with fewer slots than N/2 (the reference's 2^14 slots at its commented-out N = 2^16, F.cpp:12): here
+    2^13 slots in the N = 2^15 ring.  SubSum + the size-2^13 CoeffsToSlots / SlotsToCoeffs matrices."""
+    fc, c, s, rng = env
+    n = 1 << 13
+    c.bootstrap_setup((3, 3), n)
+    c.bootstrap_keygen(n)
+    v = rng.uniform(-1, 1, n)
+    ct = c.encrypt(v, level=24, slots=n)
+    b = c.bootstrap(ct)
+    assert b.slots == n and b.level <= 16
+    assert float(np.abs(c.decrypt(b) - v).max()) < 1e-5
+    sq = c.mult(b, b)                                   # the refreshed ciphertext keeps computing
+    assert float(np.abs(c.decrypt(sq) - v * v).max()) < 1e-5
+
+
 def test_bootstrap_variants_and_scalar_mult(env):
     fc, c, s, rng = env
     v = rng.uniform(-1, 1, s.n)
