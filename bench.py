@@ -264,7 +264,7 @@ def run_b200(a):
         fwd = run_forward(a, local, rank, world, torch, dist)
 
     if rank == 0:
-        launches_per_group = 13         # 4 NTT pass pairs (8) + modup/inner/moddown conv/finish (4) + 1 D2D copy, per batched call
+        launches_per_group = 12         # kernels per batched call: 4 NTT pass pairs (8) + modup / inner product / moddown conv / finish (4); plus 1 D2D copy
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
