@@ -67,6 +67,7 @@ void FHEController::create(int log_ring, int depth, int digits, int first_bits, 
     params_.aux_bits = 60;
     params_.sparse_h = 192;  // SPARSE_TERNARY
     if (const char* ov = std::getenv("FHE_LINFORMER_LOGN")) params_.logN = std::atoi(ov);   // test / bench override only
+    if (const char* ov = std::getenv("FLK_MAX_ROWS")) max_rows_per_batch = std::max(1, std::atoi(ov));
     need(fl_ctx_create(&params_, device, &ctx_), "GenCryptoContext");
 }
 
