@@ -331,7 +331,11 @@ Elem Scheme::bootstrap(const Elem& in) {
         }
         return y;
     };
-    Elem ylo = eval_mod(xlo), yhi = eval_mod(xhi);
+    // both halves go through EvalMod as one batched operand (2 B ciphertexts): same launches, twice the work per launch
+    Elem both = eval_mod(pack({xlo, xhi}));
+    const size_t half = (size_t)B * both.words_each(N);
+    Elem ylo = both, yhi = both;
+    ylo.batch = B; yhi.batch = B; yhi.off = both.off + half;
     Elem y = add(ylo, times_i(yhi, false));
     // ---- SlotsToCoeffs
     for (auto& st : bp.stc) y = apply_stage(*this, st, y, n);
