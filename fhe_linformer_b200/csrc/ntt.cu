@@ -10,7 +10,8 @@
 //                 adjacent threads on adjacent columns (fully coalesced, no shared memory);
 //   chunk pass  : the remaining logN-4 stages on contiguous chunks of 2^(logN-4) words, one CTA per
 //                 chunk, radix-8 register blocks exchanged through XOR-swizzled shared memory, the
-//                 next round's twiddles prefetched (16-byte {w, w'} loads) across the barrier.
+//                 next round's twiddles prefetched (16-byte {w, w'} loads) across the barrier; the
+//                 unit-stride round reads / writes global memory directly with 16-byte accesses.
 // Butterflies are Harvey lazy with Shoup twiddles whose quotient is estimated from three 32x32 partial products
 // (dev::mulhi_lazy: low by at most 2), so a twiddle product lies in [0,4q).  Forward values grow by 4q per stage;
 // for moduli below 2^56 (every Q limb) 65q < 2^64, so the forward transform carries NO conditional subtraction
@@ -190,6 +191,11 @@ struct Rounds {
         if constexpr (FWD && FIRST) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) e[k] = a[tid + k * S::NT];
+        } else if constexpr (!FWD && FIRST) {
+            // the inverse starts with the unit-stride round: a thread's 8 values are contiguous in global memory
+            const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a + tid * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const ulonglong2 v = in[k]; e[2 * k] = v.x; e[2 * k + 1] = v.y; }
         } else {
 #pragma unroll
             for (int h = 0; h < G::G; ++h) lds_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
@@ -214,6 +220,11 @@ struct Rounds {
         if constexpr (!FWD && LAST) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[tid + k * S::NT] = e[k];    // lazy < 4q, consumed by the column pass
+        } else if constexpr (FWD && LAST) {
+            // unit-stride round: the thread's 8 results are contiguous, four 16-byte stores
+            ulonglong2* out = reinterpret_cast<ulonglong2*>(a + tid * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k] = make_ulonglong2(e[2 * k], e[2 * k + 1]);
         } else {
 #pragma unroll
             for (int h = 0; h < G::G; ++h) sts_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
@@ -222,21 +233,6 @@ struct Rounds {
         if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q4, qinv64, wide);
     }
 };
-
-template <int S2, int K>
-__device__ __forceinline__ void copy_in(u64* sm, const u64* __restrict__ a, int tid, const SBase& b) {
-    if constexpr (K < 8) {
-        sm[b.at<(K << (S2 - 3))>()] = a[tid + K * Sched<S2>::NT];
-        copy_in<S2, K + 1>(sm, a, tid, b);
-    }
-}
-template <int S2, int K>
-__device__ __forceinline__ void copy_out(u64* __restrict__ a, const u64* sm, int tid, const SBase& b) {
-    if constexpr (K < 8) {
-        a[tid + K * Sched<S2>::NT] = sm[b.at<(K << (S2 - 3))>()];
-        copy_out<S2, K + 1>(a, sm, tid, b);
-    }
-}
 
 template <int S2, bool FWD>
 __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kernel(u64* __restrict__ data, DevTables T, LimbSel sel,
@@ -252,12 +248,7 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kern
     const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
     ulonglong2 tw[7];
     Rounds<S2, FWD, 0>::load_twiddles(tw, tab, tid, chunk, T.logN);
-    if constexpr (!FWD) {
-        copy_in<S2, 0>(sm, a, tid, SBase(tid));
-        __syncthreads();
-    }
     Rounds<S2, FWD, 0>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, wide);
-    if constexpr (FWD) copy_out<S2, 0>(a, sm, tid, SBase(tid));
 }
 
 template <int S2, bool FWD>
