@@ -11,7 +11,9 @@
 //   chunk pass  : the remaining logN-4 stages on contiguous chunks of 2^(logN-4) words, one CTA per
 //                 chunk, radix-8 register blocks exchanged through XOR-swizzled shared memory, the
 //                 next round's twiddles prefetched (16-byte {w, w'} loads) across the barrier; the
-//                 unit-stride round reads / writes global memory directly with 16-byte accesses.
+//                 unit-stride round reads / writes global memory directly with 16-byte accesses, and the
+//                 barrier between two rounds only spans the threads that exchange values (CTA, then a
+//                 named barrier per 64 threads, then a warp).
 // Butterflies are Harvey lazy with Shoup twiddles whose quotient is estimated from three 32x32 partial products
 // (dev::mulhi_lazy: low by at most 2), so a twiddle product lies in [0,4q).  Forward values grow by 4q per stage;
 // for moduli below 2^56 (every Q limb) 65q < 2^64, so the forward transform carries NO conditional subtraction
@@ -228,7 +230,14 @@ struct Rounds {
         } else {
 #pragma unroll
             for (int h = 0; h < G::G; ++h) sts_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
-            __syncthreads();
+            // A round only exchanges values inside aligned groups of 2^max(ULOG, ULOG_next) threads (the thread that reads
+            // index hi' U + lo' + k U/8 next round finds it written by threads (hi'/8) U + lo' + k U/8 of this round), so the
+            // barrier shrinks with the stride: whole CTA, then a named barrier per group, then a warp.
+            constexpr int NEXT_ULOG = Rounds<S2, FWD, R + 1>::ULOG;
+            constexpr int SCOPE = 1 << (ULOG > NEXT_ULOG ? ULOG : NEXT_ULOG);
+            if constexpr (SCOPE >= S::NT) __syncthreads();
+            else if constexpr (SCOPE <= 32) __syncwarp();
+            else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / SCOPE), "n"(SCOPE) : "memory");
         }
         if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q4, qinv64, wide);
     }
