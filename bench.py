@@ -53,7 +53,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_load = index, [], None, None
 
     def start(self):
         try:
@@ -66,23 +66,36 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a few hundred ms to produce its first line: wait for it so a short timed region is still covered."""
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Clocks over the samples taken inside [t_begin, t_end] (the timed region); when the region is shorter than the
+        sampling period, over the GPU-busy window that started with the warm-up steps of the same workload (`window`)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        ok = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        inside = [(t, r) for t, r in ok if t_begin is not None and t_begin - 0.05 <= t <= t_end + 0.12]
+        window = "timed region"
+        if not inside:
+            inside, window = [(t, r) for t, r in ok if self.t_load is None or t >= self.t_load], "warm-up + timed region (timed region shorter than the sampling period)"
+        sm = sorted(float(r[1]) for _, r in inside)
+        mx = [float(r[2]) for _, r in inside if r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        for _, r in inside:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def cpu_rotations(o, l, count, seed=0, warm=True):
@@ -170,21 +183,25 @@ def run_b200(a):
         if world > 1:
             dist.barrier()
 
-    for _ in range(a.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        sampler.wait_first()
+        sampler.t_load = time.time()
+    for _ in range(a.warmup):
+        step()
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     ev0.record(stream)
     for _ in range(a.steps):
         step()
     ev1.record(stream)
     e.sync()
+    t_end = time.time()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
     from fhe_linformer_b200 import shard
     units, worst_s, value = shard.combine(B * a.steps, ms * 1e-3, device="cuda")     # SUM of rotations / MAX device time
     ms = worst_s * 1e3
