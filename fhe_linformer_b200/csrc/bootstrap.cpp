@@ -9,6 +9,7 @@
 //     (sparse-secret range K = 28; R = 4, degree 31: 9 levels).  Total depth 3 + 9 + 3 = 15 incl. the pending rescale.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 
@@ -269,7 +270,22 @@ Elem apply_stage(Scheme& s, LinStage& st, const Elem& in_ct, int n) {
 }
 }  // namespace
 
+namespace {
+struct PhaseTimer {   // FLK_BOOT_TIMING=1: GPU milliseconds of the bootstrap phases on stderr
+    bool on; cudaStream_t s; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    explicit PhaseTimer(cudaStream_t st) : on(std::getenv("FLK_BOOT_TIMING") != nullptr), s(st) { mark("start"); }
+    void mark(const char* name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); ev.push_back({name, e}); }
+    ~PhaseTimer() {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        for (size_t i = 1; i < ev.size(); ++i) { float ms; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); std::fprintf(stderr, "  boot %-10s %7.2f ms\n", ev[i].first, ms); }
+        for (auto& e : ev) cudaEventDestroy(e.second);
+    }
+};
+}  // namespace
+
 Elem Scheme::bootstrap(const Elem& in) {
+    PhaseTimer pt(eng.stream);
     if (in.ncomp != 2) throw std::invalid_argument("EvalBootstrap: ciphertext expected");
     auto it = boot_.find(in.slots);
     if (it == boot_.end()) throw std::runtime_error("EvalBootstrap: EvalBootstrapSetup was not called for this slot count");
@@ -304,11 +320,13 @@ Elem Scheme::bootstrap(const Elem& in) {
         eng.ntt(raised.data(), sel_range(0, L), 2 * B, (size_t)L * N);
         eng.release(x);
     }
+    pt.mark("modraise");
     // ---- SubSum (sparse packing only): trace onto the subring of the slots, raised <- sum of its gap conjugates
     for (int k = n; k < N / 2; k <<= 1) raised = add(raised, rotate(raised, k));
     // ---- CoeffsToSlots
     Elem c = raised;
     for (auto& st : bp.cts) c = apply_stage(*this, st, c, n);
+    pt.mark("cts");
     // real / imaginary coefficient halves: x_lo = c + conj(c), x_hi = -i (c - conj(c))   (the 1/2 is folded into CtS)
     Elem cc = conjugate(c);
     Elem xlo = add(c, cc);
@@ -337,9 +355,11 @@ Elem Scheme::bootstrap(const Elem& in) {
     Elem ylo = both, yhi = both;
     ylo.batch = B; yhi.batch = B; yhi.off = both.off + half;
     Elem y = add(ylo, times_i(yhi, false));
+    pt.mark("evalmod");
     // ---- SlotsToCoeffs
     for (auto& st : bp.stc) y = apply_stage(*this, st, y, n);
     if (post_fix != 1.0) y = mult_const(y, post_fix);
+    pt.mark("stc");
     return y;
 }
 

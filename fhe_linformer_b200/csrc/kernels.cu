@@ -303,12 +303,13 @@ __global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restric
 // out[o] = sum_t k[o][t] * in[t], limb-wise.  A thread owns one coefficient of one limb of one polynomial for kOt outputs, so
 // every input word is read n_out / kOt times.  k: [n_out][n_in][l] residues with Shoup companions ([.][.][.][2]).
 constexpr int kOt = 8;
+// rows = polynomials x limbs of one operand (2 l for a ciphertext, 2 l B for a batched one): limb = row mod l
 __global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out, const u64* __restrict__ in, const ulonglong2* __restrict__ k,
-                                                           DevTables T, int l, int n_in, int n_out) {
+                                                           DevTables T, int l, int rows, int n_in, int n_out) {
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int limb = blockIdx.y % l, o0 = blockIdx.z * kOt;
-    const size_t poly_off = (size_t)blockIdx.y * T.N + j, ct = (size_t)2 * l * T.N;
+    const size_t poly_off = (size_t)blockIdx.y * T.N + j, ct = (size_t)rows * T.N;
     const u64 q = T.q[limb];
     u64 acc[kOt];
 #pragma unroll
@@ -516,9 +517,9 @@ void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishAr
                                                                                                  a.add1_bs, a.plus, a.plus_bs, rg.first);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int n_in, int n_out, cudaStream_t s) {
-    lincomb_kernel<<<dim3(cdiv(t.N, kThreads), 2 * l, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, reinterpret_cast<const ulonglong2*>(k), t, l,
-                                                                                                n_in, n_out);
+void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s) {
+    lincomb_kernel<<<dim3(cdiv(t.N, kThreads), rows, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, reinterpret_cast<const ulonglong2*>(k), t, l,
+                                                                                               rows, n_in, n_out);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {

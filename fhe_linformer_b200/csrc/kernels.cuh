@@ -79,8 +79,9 @@ struct FinishArgs {
 void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
                            cudaStream_t s, LimbRange limbs = kAllLimbs);
 
-// out[o] = sum_t k[o][t] in[t] over ciphertexts: in [n_in][2][l][N], out [n_out][2][l][N], k [n_out][n_in][l][2] = {residue, Shoup}
-void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int n_in, int n_out, cudaStream_t s);
+// out[o] = sum_t k[o][t] in[t] over operands of `rows` limb rows each (2 l for a ciphertext, 2 l B for a batched one):
+// in [n_in][rows][N], out [n_out][rows][N], k [n_out][n_in][l][2] = {residue, Shoup}
+void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s);
 
 // ---- rescale ----
 struct RsConst {

@@ -35,14 +35,44 @@ int poly_degree(const std::vector<double>& c) {
 
 // sum_{i<=upto} c[i] T[i]; T[0] is the constant 1 (T[0] unused).  Returns an invalid Elem when everything is zero
 // except possibly c[0], which the caller adds as a constant.
+// sum_{1 <= i <= upto} c[i] T[i] as ONE kernel (weighted_sum) instead of a scalar multiplication, a rescale and an addition per
+// term: the terms a combination uses are brought to the deepest level among them (never deeper, so no level is wasted) and
+// to one scale -- OpenFHE's EvalChebyshevSeriesPS aligns levels the same way before its EvalLinearWSum.  `settled` holds
+// T[i] after its pending rescale, `aligned` caches (i, target limbs) -> adjusted copy, so each polynomial is adjusted once
+// per target level rather than once per use.
 Elem Scheme::inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto) {
-    Elem acc;
+    std::vector<int> idx;
+    std::vector<double> w;
     for (int i = 1; i <= upto && i < (int)c.size(); ++i) {
         if (negligible(c[i])) continue;
-        Elem t = mult_const(T[i], c[i]);
-        acc = acc.valid() ? add(acc, t) : t;
+        idx.push_back(i);
+        w.push_back(c[i]);
     }
-    return acc;
+    if (idx.empty()) return Elem();
+    if (ps_settled_.size() != T.size()) { ps_settled_.assign(T.size(), Elem()); ps_aligned_.clear(); }
+    int deepest = idx[0];
+    for (int i : idx) {
+        if (!ps_settled_[i].valid()) {
+            ps_settled_[i] = T[i];
+            if (ps_settled_[i].deg == 2) rescale_inplace(ps_settled_[i]);
+        }
+        if (ps_settled_[i].l < ps_settled_[deepest].l) deepest = i;
+    }
+    const Elem& ref = ps_settled_[deepest];
+    std::vector<Elem> terms;
+    for (int i : idx) {
+        const Elem& si = ps_settled_[i];
+        if (si.l == ref.l && si.scale == ref.scale) { terms.push_back(si); continue; }
+        auto key = std::make_pair(i, ref.l);
+        auto it = ps_aligned_.find(key);
+        if (it == ps_aligned_.end()) {
+            Elem a = si, r = ref;
+            adjust_pair(a, r);
+            it = ps_aligned_.emplace(key, a).first;
+        }
+        terms.push_back(it->second);
+    }
+    return weighted_sum(terms, w);
 }
 
 // Chebyshev series sum c[i] T_i(x) (true coefficients, c[0] not halved), x already mapped to [-1,1].
@@ -71,6 +101,7 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
         p = add(p, p);
         Gs[j] = add_const(p, -1.0);
     }
+    ps_settled_.clear(); ps_aligned_.clear();   // per-evaluation caches of inner_linear
     // recursive split p = q T_g + r
     struct Rec {
         Scheme* s; const std::vector<Elem>& T; const std::vector<Elem>& Gs; int k;
@@ -104,6 +135,7 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
     } rec{this, T, Gs, k};
     double c0 = 0;
     Elem res = rec.run(c, m, c0);
+    ps_settled_.clear(); ps_aligned_.clear();
     if (!res.valid()) res = mult_const(x, 0.0);
     return negligible(c0) ? res : add_const(res, c0);
 }

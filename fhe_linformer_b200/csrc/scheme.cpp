@@ -337,14 +337,8 @@ Elem Scheme::encode_at(const cplx* vals, int n, int l, double scale, int slots, 
     const int Nh = P.N / 2;
     if (slots < 1 || slots > Nh || (slots & (slots - 1))) throw std::invalid_argument("encode: slots must be a power of two <= N/2");
     DevFft& f = dev_fft(slots);
-    // pinned staging ring: a slot is reused only after the copy that read it has completed
-    if (!stage_) {
-        FLK_CUDA(cudaMallocHost(&stage_, kStageSlots * (size_t)2 * Nh * sizeof(double)));
-        for (auto& ev : stage_ev_) FLK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    }
-    const int slot = stage_next_++ % kStageSlots;
-    FLK_CUDA(cudaEventSynchronize(stage_ev_[slot]));
-    double* h = stage_ + (size_t)slot * 2 * Nh;
+    int slot;
+    double* h = stage_slot(slot);
     const int m = std::min(n, slots);
     for (int i = 0; i < m; ++i) { h[i] = vals[i].real(); h[slots + i] = vals[i].imag(); }
     for (int i = m; i < slots; ++i) { h[i] = 0.0; h[slots + i] = 0.0; }
@@ -356,6 +350,27 @@ Elem Scheme::encode_at(const cplx* vals, int n, int l, double scale, int slots, 
     eng.ntt(e.data(), sel_range(0, l));
     eng.release((u64*)d);
     return e;
+}
+
+// pinned staging ring for small host -> device uploads: a slot is reused only after the copy that read it has completed, so
+// the host never waits for the device in the steady state
+double* Scheme::stage_slot(int& slot) {
+    const size_t each = (size_t)P.N;   // doubles per slot (2 x N/2 slot values)
+    if (!stage_) {
+        FLK_CUDA(cudaMallocHost(&stage_, kStageSlots * each * sizeof(double)));
+        for (auto& ev : stage_ev_) FLK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    slot = stage_next_++ % kStageSlots;
+    FLK_CUDA(cudaEventSynchronize(stage_ev_[slot]));
+    return stage_ + (size_t)slot * each;
+}
+void Scheme::upload_small(u64* dst, const u64* src, size_t words) {
+    if (words > (size_t)P.N) { eng.upload(dst, src, words); eng.sync(); return; }
+    int slot;
+    u64* h = reinterpret_cast<u64*>(stage_slot(slot));
+    std::memcpy(h, src, words * 8);
+    FLK_CUDA(cudaMemcpyAsync(dst, h, words * 8, cudaMemcpyHostToDevice, eng.stream));
+    FLK_CUDA(cudaEventRecord(stage_ev_[slot], eng.stream));
 }
 
 Scheme::DevFft& Scheme::dev_fft(int slots) {
@@ -644,10 +659,37 @@ Elem Scheme::linear_wsum(const Elem& in_raw, const double* w, int n_out) {
     u64* kd = eng.alloc(k.size());
     eng.upload(kd, k.data(), k.size());
     Elem r = make(2, l, in.deg + 1, in.scale * sf, in.slots, n_out);
-    launch_lincomb(eng.T, r.data(), in.data(), kd, l, n_in, n_out, eng.stream);
+    launch_lincomb(eng.T, r.data(), in.data(), kd, l, 2 * l, n_in, n_out, eng.stream);
     eng.sync();   // k is a host temporary
     eng.release(kd);
     if (eng.ledger_on) eng.ledger.add("linear_wsum", l, (double)(n_in + n_out) * 16.0 * l * P.N);
+    return r;
+}
+
+// sum_i w[i] * terms[i] for terms of identical level / degree 1 / scale (each possibly a batched operand): one kernel.
+// The result is one degree deeper, like EvalMult by a scalar.
+Elem Scheme::weighted_sum(const std::vector<Elem>& terms, const std::vector<double>& w) {
+    const Elem& f = terms.at(0);
+    const int n_in = (int)terms.size(), l = f.l, rows = 2 * l * f.batch;
+    const size_t each = (size_t)rows * P.N;
+    const double sf = P.sf[level_of(f)];
+    std::vector<u64> k((size_t)n_in * l * 2);
+    for (int t = 0; t < n_in; ++t) {
+        if (terms[t].l != l || terms[t].deg != 1 || terms[t].scale != f.scale || terms[t].batch != f.batch) throw std::invalid_argument("weighted_sum: misaligned terms");
+        const i128 v = (i128)std::rint(w[t] * sf);
+        for (int i = 0; i < l; ++i) {
+            i128 r = v % (i128)P.q[i];
+            if (r < 0) r += P.q[i];
+            k[((size_t)t * l + i) * 2] = (u64)r; k[((size_t)t * l + i) * 2 + 1] = nt::shoup((u64)r, P.q[i]);
+        }
+    }
+    u64* kd = eng.alloc(k.size());
+    u64* in = eng.alloc(each * n_in);
+    for (int t = 0; t < n_in; ++t) eng.copy(in + (size_t)t * each, terms[t].data(), each);
+    upload_small(kd, k.data(), k.size());
+    Elem r = make(2, l, 2, f.scale * sf, f.slots, f.batch);
+    launch_lincomb(eng.T, r.data(), in, kd, l, rows, n_in, 1, eng.stream);
+    eng.release(kd); eng.release(in);
     return r;
 }
 

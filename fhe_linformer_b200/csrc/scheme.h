@@ -95,6 +95,7 @@ public:
     // EvalLinearWSum: out[o] = sum_t w[o * n_in + t] * in[t] for a batched operand `in` (n_in ciphertexts); result is a batch
     // of n_out ciphertexts one degree deeper.  The encrypted Linformer E / F projection is one such call.
     Elem linear_wsum(const Elem& in, const double* w, int n_out);
+    Elem weighted_sum(const std::vector<Elem>& terms, const std::vector<double>& w);   // aligned terms, one kernel
     Elem square(const Elem& a) { return mult(a, a); }
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);
@@ -146,6 +147,8 @@ private:
     void sample_dev_to_eval(u64* dst, u64 seed, int kind, const LimbSel& sel);   // kind 0 ternary, 1 Gaussian (device sampler + NTT)
     struct DevFft { uint32_t* rot; double* cre; double* cim; };               // special-FFT tables of one slot count, on the device
     DevFft& dev_fft(int slots);
+    double* stage_slot(int& slot);                                   // next free slot of the pinned staging ring
+    void upload_small(u64* dst, const u64* src, size_t words);        // host -> device through the ring, no synchronisation
     void encode_coeffs(const cplx* vals, int n, int slots, double scale, std::vector<i128>& co) const;
     void coeffs_to_dev(u64* dst, const std::vector<i128>& co, int l);
     ScalarSet scalar_set(i128 k, int l) const;
@@ -153,6 +156,8 @@ private:
     // evaluation helpers
     Elem cheby_ps(const Elem& x, const std::vector<double>& c);
     Elem inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto);
+    std::vector<Elem> ps_settled_;                          // inner_linear caches, valid during one cheby_ps evaluation
+    std::map<std::pair<int, int>, Elem> ps_aligned_;
 
     std::map<int, DevFft> dev_fft_;
     static constexpr int kStageSlots = 8;
