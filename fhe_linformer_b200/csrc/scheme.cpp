@@ -736,23 +736,33 @@ Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
     };
     for (int i = 0; i < steps;) {
         const int k = stride * (1 << i);
+        if (!key_of(k)) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(k));
+        // g doubling steps at once: r + sum_{t = 1 .. 2^g - 1} rot(r, t k), all rotations hoisted on one ModUp / one ModDown.
+        // Pairs (three rotations) are the sweet spot; an odd tail is taken as a triple (seven rotations) instead of 2 + 1.
+        int g = 1;
+        if (!no_hoist) {
+            auto have = [&](int gg) {
+                for (int t = 1; t < (1 << gg); ++t)
+                    if (!key_of(t * k)) return false;
+                return true;
+            };
+            const int left = steps - i;
+            if (left == 3 && have(3)) g = 3;
+            else if (left >= 2 && have(2)) g = 2;
+        }
+        const int nk = (1 << g) - 1;
+        uint32_t gs[8];
+        const u64* evks[8];
+        for (int t = 1; t <= nk; ++t) { gs[t - 1] = P.galois_for_rotation(t * k); evks[t - 1] = key_of(t * k); }
         Elem nx = make(2, r.l, r.deg, r.scale, r.slots, r.batch);
-        const u64* k1 = key_of(k);
-        if (!k1) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(k));
-        const u64* k2 = i + 1 < steps ? key_of(2 * k) : nullptr;
-        const u64* k3 = i + 1 < steps ? key_of(3 * k) : nullptr;
-        const bool pair = !no_hoist && k2 && k3;
-        // two doubling steps at once: r + rot(r,k) + rot(r,2k) + rot(r,3k), the three rotations hoisted on one ModUp / ModDown
-        const uint32_t gs[3] = {P.galois_for_rotation(k), P.galois_for_rotation(2 * k), P.galois_for_rotation(3 * k)};
-        const u64* evks[3] = {k1, k2, k3};
         for (int b0 = 0, mb = max_batch(r.l); b0 < r.batch; b0 += mb) {
             const size_t o = (size_t)b0 * r.words_each(P.N);
             const int nb = std::min(mb, r.batch - b0);
-            if (pair) eng.rotate_sum_batch(nx.data() + o, r.data() + o, r.l, gs, evks, 3, nb, true);
-            else eng.rotate_batch(nx.data() + o, r.data() + o, r.l, gs[0], k1, nb, true);
+            if (g > 1) eng.rotate_sum_batch(nx.data() + o, r.data() + o, r.l, gs, evks, nk, nb, true);
+            else eng.rotate_batch(nx.data() + o, r.data() + o, r.l, gs[0], evks[0], nb, true);
         }
         r = nx;
-        i += pair ? 2 : 1;
+        i += g;
     }
     return steps == 0 ? clone(a) : r;
 }

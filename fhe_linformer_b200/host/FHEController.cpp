@@ -433,9 +433,18 @@ Ctxt FHEController::ladder(const Ctxt& in, int slots, int stride) {
     for (int i = 0; i < steps; ++i) {
         int k = stride * (1 << i);
         if (!fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
-        // the engine takes two doubling steps at once (r + rot(r,k) + rot(r,2k) + rot(r,3k), hoisted) when the 3k key exists
-        int k3 = 3 * k;
-        if (hoist_ladders && i % 2 == 0 && i + 1 < steps && !fl_has_rot_key(ctx_, k3)) need(fl_gen_rot_keys(ctx_, &k3, 1), "EvalRotateKeyGen");
+    }
+    // the engine takes two doubling steps per hoisted key switch (r + rot(r,k) + rot(r,2k) + rot(r,3k)) when the 3k key exists,
+    // and an odd tail of three steps as one (rotations k .. 7k): generate those extra keys on first use
+    if (hoist_ladders) {
+        for (int i = 0; i < steps;) {
+            const int k = stride * (1 << i), g = steps - i == 3 ? 3 : (steps - i >= 2 ? 2 : 1);
+            for (int t = 3; t < (1 << g); ++t) {
+                int kt = t * k;
+                if (!fl_has_rot_key(ctx_, kt)) need(fl_gen_rot_keys(ctx_, &kt, 1), "EvalRotateKeyGen");
+            }
+            i += g;
+        }
     }
     fl_elem* e = nullptr;
     need(fl_rotsum(ctx_, in->handle(), steps, stride, &e), "EvalRotate ladder");
