@@ -8,7 +8,7 @@
  * algorithms are the published ones: Cheon-Han-Kim-Kim-Song full-RNS CKKS, Han-Ki hybrid key
  * switching, Harvey/Shoup NTT butterflies.
  *
- * Build: see oracle/Makefile (gcc -O3 -march=native -fopenmp -ffp-contract=off).
+ * Build: see oracle/Makefile (gcc -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off).
  */
 #include "ckks_oracle.h"
 #include <math.h>
