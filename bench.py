@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the encrypted Linformer forward (extra `forward` key)")
     ap.add_argument("--forward-rows", type=int, default=129, help="S = rows of the forward sample (129..256)")
+    ap.add_argument("--no-forward-n16", action="store_true", help="skip the extra forward at the reference's commented-out ring N=2^16")
     ap.add_argument("--forward-logn", type=int, default=15, help="ring of the forward: 15 = the reference's parameters, 16 = its commented-out variant (sparse packing)")
     return ap.parse_args()
 
@@ -341,6 +342,16 @@ def run_forward(a, local, rank, world, torch, dist):
             lean_runs.append(time.perf_counter() - t1)
         lean = sorted(lean_runs)[1]
         fc.close()
+        n16 = None
+        if a.forward_logn == 15 and not a.no_forward_n16:
+            # the same sample at the ring the reference leaves commented out (F.cpp:12): 2^14 slots become sparse packing
+            fc16 = host.FHEController(device=local, root=root).generate(log_ring=16)
+            fc16.forward(dirs, dead_work=True)
+            t2 = time.perf_counter()
+            logits16, _, _ = fc16.forward(dirs, dead_work=True)
+            n16 = {"seconds_per_sample": time.perf_counter() - t2, "ring": "N=2^16, 28 limbs, dnum 4, 2^14 slots (sparse packing)",
+                   "predicted_class": int(np.argmax(logits16)), "max_logit_difference_to_N15": float(np.abs(logits16 - logits).max())}
+            fc16.close()
     finally:
         os.dup2(saved, 1)
         os.close(devnull); os.close(saved)
@@ -354,6 +365,7 @@ def run_forward(a, local, rank, world, torch, dist):
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
+            "n16": n16,
             "note": "text files -> encode/encrypt -> encoder1 -> pooler -> classifier -> decrypt, wall clock incl. host encode; "
                     "lean = same logits without the operations main.cpp issues but never reads"}
 
