@@ -56,10 +56,11 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
         std::vector<u64> rc((size_t)Tn * 8, 0);
         for (int m = 0; m < Tn; ++m) {
             const u64 qq = P.q[m];
-            if (qq >> 60) throw std::invalid_argument("moduli must be below 2^60");
+            if ((qq >> 60) || qq < (1ull << 31)) throw std::invalid_argument("moduli must lie between 2^31 and 2^60");
             const u64 c30 = (1ull << 30) % qq, c60 = (1ull << 60) % qq;
             u64* r = &rc[(size_t)m * 8];
             r[0] = qq; r[1] = 0 - qq; r[2] = P.mu_hi[m]; r[3] = c30; r[4] = nt::shoup(c30, qq); r[5] = c60; r[6] = nt::shoup(c60, qq);
+            r[7] = (u64)(((unsigned __int128)1 << 94) / qq);
         }
         T.redc = to_device(rc);
     }
@@ -69,19 +70,22 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     {
         std::vector<int> sm(P.K);
         for (int k = 0; k < P.K; ++k) sm[k] = P.L + k;
-        std::vector<u64> hatinv(P.K), post(Tn, 0), post_sh(Tn, 0), phm((size_t)P.K * P.L), pinv(P.L), pinv_sh(P.L);
+        std::vector<u64> hatinv(P.K), post(Tn, 0), post_sh(Tn, 0), phm((size_t)P.K * P.L), phm30(phm.size()), pinv(P.L), pinv_sh(P.L);
         P.conv_hatinv(sm.data(), P.K, hatinv.data());
         for (int k = 0; k < P.K; ++k) {
             u64 qq = P.q[P.L + k];
             post[P.L + k] = nt::mulmod(P.ninv[P.L + k], hatinv[k], qq);
             post_sh[P.L + k] = nt::shoup(post[P.L + k], qq);
-            for (int i = 0; i < P.L; ++i) phm[(size_t)k * P.L + i] = P.conv_hat_mod(sm.data(), P.K, k, P.q[i]);
+            for (int i = 0; i < P.L; ++i) {
+                phm[(size_t)k * P.L + i] = P.conv_hat_mod(sm.data(), P.K, k, P.q[i]);
+                phm30[(size_t)k * P.L + i] = nt::mulmod(phm[(size_t)k * P.L + i], (1ull << 30) % P.q[i], P.q[i]);
+            }
         }
         for (int i = 0; i < P.L; ++i) {
             pinv[i] = nt::invmod(P.P_mod(P.q[i]), P.q[i]);
             pinv_sh[i] = nt::shoup(pinv[i], P.q[i]);
         }
-        md_.post = to_device(post); md_.post_sh = to_device(post_sh); md_.phm = to_device(phm);
+        md_.post = to_device(post); md_.post_sh = to_device(post_sh); md_.phm = to_device(phm); md_.phm30 = to_device(phm30);
         md_.pinv = to_device(pinv); md_.pinv_sh = to_device(pinv_sh);
     }
     // rescale constants (A.7)
@@ -186,7 +190,7 @@ const KsLevel& Engine::ks_level(int l) {
     if (it != ks_.end()) return it->second;
     if (l < 1 || l > P.L) throw std::invalid_argument("key switch: limb count out of range");
     const int beta = P.beta(l), ext = l + P.K, a = P.alpha;
-    std::vector<u64> post(P.T, 0), post_sh(P.T, 0), hm((size_t)beta * a * ext, 0);
+    std::vector<u64> post(P.T, 0), post_sh(P.T, 0), hm((size_t)beta * a * ext, 0), hm30(hm.size(), 0);
     for (int d = 0; d < beta; ++d) {
         const int lo = d * a, hi = std::min(lo + a, l), ns = hi - lo;
         std::vector<int> sm(ns);
@@ -197,12 +201,16 @@ const KsLevel& Engine::ks_level(int l) {
             const int m = lo + i;
             post[m] = nt::mulmod(P.ninv[m], hatinv[i], P.q[m]);
             post_sh[m] = nt::shoup(post[m], P.q[m]);
-            for (int t = 0; t < ext; ++t)
-                hm[((size_t)d * a + i) * ext + t] = P.conv_hat_mod(sm.data(), ns, i, P.q[P.mod_index_ext(l, t)]);
+            for (int t = 0; t < ext; ++t) {
+                const u64 qt = P.q[P.mod_index_ext(l, t)];
+                const u64 h = P.conv_hat_mod(sm.data(), ns, i, qt);
+                hm[((size_t)d * a + i) * ext + t] = h;
+                hm30[((size_t)d * a + i) * ext + t] = nt::mulmod(h, (1ull << 30) % qt, qt);
+            }
         }
     }
     KsLevel k;
-    k.post = to_device(post); k.post_sh = to_device(post_sh); k.hm = to_device(hm);
+    k.post = to_device(post); k.post_sh = to_device(post_sh); k.hm = to_device(hm); k.hm30 = to_device(hm30);
     k.l = l; k.beta = beta; k.alpha = a;
     return ks_.emplace(l, k).first->second;
 }

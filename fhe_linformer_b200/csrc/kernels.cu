@@ -93,12 +93,12 @@ __device__ __forceinline__ RedC load_redc(const DevTables& T, int m) {
 template <int A>
 __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ up, const u64* __restrict__ dcoef, DevTables T, KsLevel ks,
                                                               size_t up_bs, size_t dco_bs, LimbRange rg) {
-    extern __shared__ uint2 shs[];
+    extern __shared__ uint4 shs[];
     const int d = blockIdx.z % ks.beta, b = blockIdx.z / ks.beta, l = ks.l, ext = l + T.K;
     const int lo = d * A, hi = min(lo + A, l), ns = hi - lo;
     for (int i = threadIdx.x; i < A * ext; i += kThreads) {
-        const Split30 h = split30(ks.hm[(size_t)d * A * ext + i]);
-        shs[i] = make_uint2(h.lo, h.hi);
+        const Split30 h = split30(ks.hm[(size_t)d * A * ext + i]), g = split30(ks.hm30[(size_t)d * A * ext + i]);
+        shs[i] = make_uint4(h.lo, h.hi, g.lo, g.hi);
     }
     __syncthreads();
     const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;   // two adjacent coefficients per thread: 16-byte accesses, and the
@@ -115,15 +115,15 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
     for (int t = t0; t < t1; ++t) {
         if (t >= lo && t < hi) continue;
         const RedC rc = load_redc(T, t < l ? t : T.L + (t - l));
-        Acc3 a0{0, 0, 0}, a1{0, 0, 0};
+        Acc2 a0{0, 0}, a1{0, 0};
 #pragma unroll
         for (int i = 0; i < A; ++i) {
-            const uint2 h = shs[i * ext + t];
-            mac3(a0, y0[i], Split30{h.x, h.y});
-            mac3(a1, y1[i], Split30{h.x, h.y});
+            const uint4 h = shs[i * ext + t];
+            mac2(a0, y0[i], h);
+            mac2(a1, y1[i], h);
         }
-        // the forward NTT that follows takes lazily reduced operands (< 4q)
-        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce3_lazy(a0, rc), reduce3_lazy(a1, rc));
+        // the forward NTT that follows takes lazily reduced operands (< 8q)
+        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce2_lazy(a0.b0, a0.b1, rc), reduce2_lazy(a1.b0, a1.b1, rc));
     }
 }
 
@@ -246,11 +246,11 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(u64* __restrict__ 
 template <int KK>
 __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
                                                                 MdConst md, int l, int polys, size_t tq_bs, size_t p_bs, LimbRange rg) {
-    extern __shared__ uint2 shs[];
+    extern __shared__ uint4 shs[];
     const int p = blockIdx.z % polys, b = blockIdx.z / polys;
     for (int i = threadIdx.x; i < KK * l; i += kThreads) {
-        const Split30 h = split30(md.phm[(size_t)(i / l) * T.L + (i % l)]);
-        shs[i] = make_uint2(h.lo, h.hi);
+        const Split30 h = split30(md.phm[(size_t)(i / l) * T.L + (i % l)]), g = split30(md.phm30[(size_t)(i / l) * T.L + (i % l)]);
+        shs[i] = make_uint4(h.lo, h.hi, g.lo, g.hi);
     }
     __syncthreads();
     const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
@@ -266,14 +266,14 @@ __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict_
     u64* dst = tq + (size_t)b * tq_bs + (size_t)p * l * T.N + j;
     for (int t = t0; t < t1; ++t) {
         const RedC rc = load_redc(T, t);
-        Acc3 a0{0, 0, 0}, a1{0, 0, 0};
+        Acc2 a0{0, 0}, a1{0, 0};
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
-            const uint2 h = shs[k * l + t];
-            mac3(a0, y0[k], Split30{h.x, h.y});
-            mac3(a1, y1[k], Split30{h.x, h.y});
+            const uint4 h = shs[k * l + t];
+            mac2(a0, y0[k], h);
+            mac2(a1, y1[k], h);
         }
-        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce3_lazy(a0, rc), reduce3_lazy(a1, rc));   // < 4q: NTT operand
+        *reinterpret_cast<ulonglong2*>(dst + (size_t)t * T.N) = make_ulonglong2(reduce2_lazy(a0.b0, a0.b1, rc), reduce2_lazy(a1.b0, a1.b1, rc));   // < 5q: NTT operand
     }
 }
 
@@ -449,7 +449,7 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
     if (rg.count == 0) return;
     const int tg = rg.count >= 16 ? 4 : 1;
     const dim3 grid(cdiv(t.N / 2, kThreads), tg, ks.beta * batch);
-    const size_t shm = (size_t)ks.alpha * ext * 8;
+    const size_t shm = (size_t)ks.alpha * ext * 16;
     switch (ks.alpha) {
 #define FLK_CASE(X) case X: modup_conv_kernel<X><<<grid, kThreads, shm, s>>>(up, dcoef, t, ks, up_bs, dco_bs, rg); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
@@ -500,7 +500,7 @@ void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u
     if (rg.count == 0) return;
     const int tg = rg.count >= 16 ? 4 : 1;
     const dim3 grid(cdiv(t.N / 2, kThreads), tg, polys * batch);
-    const size_t shm = (size_t)t.K * l * 8;
+    const size_t shm = (size_t)t.K * l * 16;
     switch (t.K) {
 #define FLK_CASE(X) case X: moddown_conv_kernel<X><<<grid, kThreads, shm, s>>>(tq, pcoef, pstride, t, md, l, polys, tq_bs, p_bs, rg); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)

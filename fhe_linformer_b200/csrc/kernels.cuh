@@ -32,12 +32,14 @@ struct KsLevel {          // device constants for key switching at l active limb
     const u64* post;      // [T] by modulus: N^-1 * (Q_d/q_m)^-1 mod q_m   (INTT post-scale)
     const u64* post_sh;
     const u64* hm;        // [beta][alpha][l+K]: (Q_d/q_{d*alpha+i}) mod q_ext(t)
+    const u64* hm30;      // the same constants times 2^30 (mod q_ext(t)): the high 30-bit half of a source residue multiplies these
     int l, beta, alpha;
 };
 struct MdConst {          // ModDown constants (level independent)
     const u64* post;      // [T] by modulus (P limbs): N^-1 * (P/p_k)^-1 mod p_k
     const u64* post_sh;
     const u64* phm;       // [K][L]: (P/p_k) mod q_i
+    const u64* phm30;     // [K][L]: (P/p_k) 2^30 mod q_i
     const u64* pinv;      // [L] P^-1 mod q_i
     const u64* pinv_sh;
 };

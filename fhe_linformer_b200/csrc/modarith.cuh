@@ -98,29 +98,47 @@ __device__ __forceinline__ u64 shoup_lazy4(u64 a, u64 w, u64 ws, u64 nq) {
         : "=l"(r) : "l"(a), "l"(w), "l"(ws), "l"(nq));
     return r;
 }
-// per-modulus constants of the accumulator reduction
+// per-modulus constants of the accumulator reductions
 struct __align__(16) RedC {
     u64 q, nq, mu64;        // mu64 = floor(2^64 / q)
     u64 c30, c30s;          // 2^30 mod q and its Shoup companion
     u64 c60, c60s;          // 2^60 mod q
-    u64 pad;
+    u64 mu94;               // floor(2^94 / q)  (q > 2^30)
 };
-// (a0 + a1 2^30 + a2 2^60) mod q, canonical: the two high accumulators through lazy Shoup products with 2^30, 2^60 mod q,
-// then one single-word Barrett step.  a0 + 8q < 2^64 since q < 2^60.
-// the same, stopping at a value in [0, 4q): enough for operands of the forward NTT, whose lazy butterflies accept it
-__device__ __forceinline__ u64 reduce3_lazy(const Acc3& s, const RedC& k) {
-    const u64 t1 = shoup_lazy4(s.a1, k.c30, k.c30s, k.nq);
-    const u64 t2 = shoup_lazy4(s.a2, k.c60, k.c60s, k.nq);
-    const u64 u = s.a0 + t1 + t2;
-    return u + mulhi_lazy(u, k.mu64) * k.nq;
+// Two-accumulator sums X = b0 + b1 2^30 < 2^94 (b1 + (b0 >> 30) < 2^64): one Barrett step on the top 64 bits.
+// floor(X / 2^30) = b1 + (b0 >> 30) exactly; qhat = hi64(that * floor(2^94/q)) from three partial products is
+// floor(X/q) - e with e in 0..4, so X - qhat q (computed modulo 2^64) lies in [0, 5q): 6 IMAD-class + ~12 ALU instructions
+// against 24 + 14 for the three-accumulator form below.
+struct Acc2 {
+    u64 b0, b1;
+};
+// acc += y * h with y as 30-bit halves and the constant given twice: h = (h.x, h.y) and h 2^30 mod q = (h.z, h.w), all 30-bit
+// halves.  Up to 8 terms (16 products below 2^60 per accumulator) fit without carries.
+__device__ __forceinline__ void mac2(Acc2& s, Split30 y, uint4 h) {
+    wmad(s.b0, y.lo, h.x);
+    wmad(s.b1, y.lo, h.y);
+    wmad(s.b0, y.hi, h.z);
+    wmad(s.b1, y.hi, h.w);
 }
-__device__ __forceinline__ u64 reduce3(const Acc3& s, const RedC& k) {
-    const u64 t1 = shoup_lazy4(s.a1, k.c30, k.c30s, k.nq);
-    const u64 t2 = shoup_lazy4(s.a2, k.c60, k.c60s, k.nq);
-    const u64 u = s.a0 + t1 + t2;
-    u64 r = u + mulhi_lazy(u, k.mu64) * k.nq;      // Barrett quotient low by at most 3: r < 4q
+__device__ __forceinline__ u64 reduce2_lazy(u64 b0, u64 b1, const RedC& k) {    // [0, 5q)
+    const u64 xh = b1 + (b0 >> 30);
+    const u64 xl = b0 + (b1 << 30);
+    return xl + mulhi_lazy(xh, k.mu94) * k.nq;
+}
+__device__ __forceinline__ u64 reduce2(u64 b0, u64 b1, const RedC& k) {         // canonical
+    u64 r = reduce2_lazy(b0, b1, k);
+    r = csub_s(r, k.q << 2);
     r = csub_s(r, k.q << 1);
     return csub_s(r, k.q);
+}
+// (a0 + a1 2^30 + a2 2^60) mod q for sums of up to 8 products (mac3): the top accumulator is folded through a lazy Shoup
+// product with 2^60 mod q (< 4q < 2^62, so a0 + it stays below 2^64), the rest is the two-accumulator step above
+// (a1 + ((a0 + fold) >> 30) < 2^64 because a1 <= 16 (2^30 - 1)^2).
+__device__ __forceinline__ u64 reduce3_lazy(const Acc3& s, const RedC& k) {
+    return reduce2_lazy(s.a0 + shoup_lazy4(s.a2, k.c60, k.c60s, k.nq), s.a1, k);
+}
+__device__ __forceinline__ u64 reduce3(const Acc3& s, const RedC& k) {
+    return reduce2(s.a0 + shoup_lazy4(s.a2, k.c60, k.c60s, k.nq), s.a1, k);
 }
 
 // Harvey lazy butterflies.  Cooley-Tukey (forward): x,y in [0,4q) -> [0,4q)
