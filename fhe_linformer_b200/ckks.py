@@ -27,6 +27,10 @@ _SIGS = {
     "fl_eval_chebyshev": (ci, [vp, vp, vp, ci, dbl, dbl, C.POINTER(vp)]),
     "fl_chebyshev_coefficients": (ci, [CHEB_FN, vp, dbl, dbl, ci, vp]),
     "fl_bootstrap_setup": (ci, [vp, ci, ci, ci]), "fl_bootstrap_keygen": (ci, [vp, ci]), "fl_bootstrap": (ci, [vp, vp, C.POINTER(vp)]),
+    "fl_lt_create": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(vp)]), "fl_lt_rotations": (ci, [vp, vp, vp, ci]),
+    "fl_lt_shape": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
+    "fl_lt_apply": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_lt_apply_plain": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_lt_free": (None, [vp]),
+    "fl_batch_pack": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_batch_slice": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_elem_batch": (ci, [vp]),
     "fl_elem_level": (ci, [vp]), "fl_elem_limbs": (ci, [vp]), "fl_elem_deg": (ci, [vp]), "fl_elem_slots": (ci, [vp]), "fl_elem_ncomp": (ci, [vp]),
     "fl_elem_scale": (dbl, [vp]), "fl_elem_clone": (ci, [vp, vp, C.POINTER(vp)]), "fl_elem_free": (None, [vp]),
     "fl_elem_export": (ci, [vp, vp, vp]), "fl_elem_import": (ci, [vp, vp, ci, ci, ci, dbl, ci, C.POINTER(vp)]),
@@ -34,6 +38,35 @@ _SIGS = {
     "fl_prof_enable": (ci, [vp, ci]), "fl_prof_dump": (ci, [vp, C.c_char_p, C.c_size_t]),
     "fl_ledger_enable": (ci, [vp, ci]), "fl_ledger_reset": (ci, [vp]), "fl_ledger_dump": (ci, [vp, C.c_char_p, C.c_size_t]),
 }
+
+
+class LinearTransform:
+    """BSGS plan of a diagonal matrix (fl_lt*): rotations() lists the keys it needs, apply() is the double-hoisted product."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h is not None:
+                self.ctx.lib.fl_lt_free(self.h)
+        except Exception:
+            pass
+        self.h = None
+
+    def rotations(self):
+        out = np.zeros(64, np.int32)
+        n = self.ctx.lib.fl_lt_rotations(self.ctx.h, self.h, _ptr(out), 64)
+        return [int(k) for k in out[:n]]
+
+    @property
+    def shape(self):
+        a, b, g, d = ci(), ci(), ci(), ci()
+        self.ctx.lib.fl_lt_shape(self.h, C.byref(a), C.byref(b), C.byref(g), C.byref(d))
+        return {"n1": a.value, "n2": b.value, "stride": g.value, "diagonals": d.value}
+
+    def apply(self, ct): return self.ctx._out(self.ctx.lib.fl_lt_apply, self.h, ct.h)
+    def apply_plain(self, ct): return self.ctx._out(self.ctx.lib.fl_lt_apply_plain, self.h, ct.h)
 
 
 class Elem:
@@ -138,6 +171,8 @@ class CKKS(Engine):
         arr = (vp * len(v))(*[e.h for e in v]); return self._out(fn, arr, len(v))
     def add_many(self, v): return self._many(self.lib.fl_add_many, v)
     def mult_many(self, v): return self._many(self.lib.fl_mul_many, v)
+    def pack(self, v): return self._many(self.lib.fl_batch_pack, v)                 # ciphertexts of equal level / scale as one batched operand
+    def unpack(self, b): return [self._out(self.lib.fl_batch_slice, b.h, i) for i in range(self.lib.fl_elem_batch(b.h))]
     def rotate(self, a, k): return self._out(self.lib.fl_rotate, a.h, int(k))
     def conjugate(self, a): return self._out(self.lib.fl_conjugate, a.h)
     def rescale(self, a): return self._out(self.lib.fl_rescale, a.h)
@@ -157,6 +192,17 @@ class CKKS(Engine):
 
     def eval_chebyshev_function(self, f, x, a, b, degree):   # EvalChebyshevFunction(f, ct, a, b, degree)
         return self.eval_chebyshev(x, self.chebyshev_coefficients(f, a, b, degree), a, b)
+
+    # BSGS diagonal ct x pt matrix product (fl_lt_*)
+    def linear_transform(self, diagonals, slots=None, level=-1, max_baby=0):
+        """diagonals: {shift: vector[slots]} with (M v)[p] = sum_d diag_d[p] v[(p + d) mod slots]; returns a LinearTransform plan."""
+        slots = slots or self.N // 2
+        shifts = np.ascontiguousarray(sorted(diagonals), np.int32)
+        d = np.stack([np.asarray(diagonals[int(k)], np.complex128) for k in shifts])
+        re, im = np.ascontiguousarray(d.real), np.ascontiguousarray(d.imag)
+        h = vp()
+        self._ck(self.lib.fl_lt_create(self.h, _ptr(shifts), len(shifts), _ptr(re), _ptr(im), slots, level, max_baby, C.byref(h)))
+        return LinearTransform(self, h)
 
     def bootstrap_setup(self, budget=(3, 3), slots=None): self._ck(self.lib.fl_bootstrap_setup(self.h, budget[0], budget[1], slots or self.N // 2))
     def bootstrap_keygen(self, slots=None): self._ck(self.lib.fl_bootstrap_keygen(self.h, slots or self.N // 2))

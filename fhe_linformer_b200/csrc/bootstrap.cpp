@@ -81,56 +81,12 @@ Diag butterfly(int n, int len, bool inverse) {
 
 }  // namespace
 
-struct LinStage {
-    int g = 1, n1 = 1, n2 = 1, off = 0, cnt = 0, level = 0;
-    std::vector<int> giant_rot;                    // rotation amount of giant step j (may be 0)
-    std::vector<std::vector<Elem>> pt;             // [j][b], invalid Elem = zero diagonal
-    std::vector<std::vector<std::vector<cplx>>> host;   // pre-rotated diagonals (kept for re-encoding at another level)
-};
-
 struct BootPrecomp {
     int slots = 0, K = 28, R = 4, cheb_deg = 31, corr = 0;
-    std::vector<LinStage> cts, stc;
+    std::vector<LinTrans> cts, stc;   // one BSGS linear transform per collapsed group of special-FFT stages (lintrans.cpp)
     std::vector<double> cheb;
     ScalarSet zeta;       // psi^(N/2) per Q limb (multiplication by i)
 };
-
-namespace {
-
-// split the merged matrix into the BSGS plan and pre-rotate its diagonals
-LinStage plan_stage(const Diag& M, int n, int g) {
-    LinStage st;
-    st.g = g;
-    int lo = 0, hi = 0;
-    std::map<int, const std::vector<cplx>*> byidx;
-    for (auto& kv : M) {
-        int d = kv.first;
-        if (d > n / 2) d -= n;                       // signed shift in (-n/2, n/2]
-        if (d % g) throw std::runtime_error("bootstrap: unexpected diagonal stride");
-        const int i = d / g;
-        lo = std::min(lo, i); hi = std::max(hi, i);
-        byidx[i] = &kv.second;
-    }
-    st.off = -lo;
-    st.cnt = hi - lo + 1;
-    st.n1 = 1;
-    while (st.n1 * st.n1 < st.cnt) st.n1 <<= 1;
-    st.n2 = (st.cnt + st.n1 - 1) / st.n1;
-    st.giant_rot.resize(st.n2);
-    st.host.assign(st.n2, std::vector<std::vector<cplx>>(st.n1));
-    for (int j = 0; j < st.n2; ++j) {
-        const int gr = g * (st.n1 * j - st.off);
-        st.giant_rot[j] = gr;
-        for (int b = 0; b < st.n1; ++b) {
-            auto it = byidx.find(st.n1 * j + b - st.off);
-            if (it == byidx.end()) continue;
-            st.host[j][b] = rot_vec(*it->second, -gr);      // P_{j,b} = Rot_{-giant}(D_i)
-        }
-    }
-    return st;
-}
-
-}  // namespace
 
 void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
     // Full packing (slots = N/2, the reference's N = 2^15 configuration) or sparse packing (slots < N/2, e.g. the 2^14 slots of
@@ -171,7 +127,7 @@ void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
     while ((1 << D) < bp->cheb_deg + 1) ++D;
     const int stc_level0 = budget_cts + D + 1 + bp->R;   // Chebyshev: D levels + 1 for the scalar coefficients
     auto build = [&](bool to_slots, int budget, double total_const, int level0) {
-        std::vector<LinStage> out;
+        std::vector<LinTrans> out;
         // application order: CtS applies B_logn^-1 first ... B_1^-1 last; StC applies B_1 first ... B_logn last
         std::vector<int> order;
         for (int s = 1; s <= logn; ++s) order.push_back(s);
@@ -181,17 +137,16 @@ void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
         for (int b = 0; b < budget; ++b) {
             const int cntf = (logn - pos + (budget - b) - 1) / (budget - b);
             Diag M;
-            int smin = 1 << 30;
             for (int t = 0; t < cntf; ++t) {
                 const int s = order[pos + t];
-                smin = std::min(smin, s);
                 Diag Bf = butterfly(n, 1 << s, to_slots);
                 M = M.empty() ? Bf : compose(Bf, M, n);
             }
             pos += cntf;
             for (auto& kv : M) for (auto& v : kv.second) v *= per_stage;
-            LinStage st = plan_stage(M, n, 1 << (smin - 1));
-            st.level = level0 + b;
+            std::map<int, std::vector<cplx>> dm(M.begin(), M.end());
+            LinTrans st = lintrans_plan(dm, n);
+            lintrans_encode(st, level0 + b);
             out.push_back(std::move(st));
         }
         return out;
@@ -201,13 +156,6 @@ void Scheme::bootstrap_setup(int budget_cts, int budget_stc, int slots) {
     bp->cts = build(true, budget_cts, 0.5 * P.sf[0] / (q0 * bp->K * gap), 0);
     // StC: sin(2 pi t/q0) ~ 2 pi m'/q0 with m' = sf0 2^-corr enc(v)  =>  multiply by q0 2^corr / (2 pi sf0)
     bp->stc = build(false, budget_stc, q0 * std::ldexp(1.0, bp->corr) / (2.0 * M_PI * P.sf[0]), stc_level0);
-    for (auto* stages : {&bp->cts, &bp->stc})
-        for (auto& st : *stages) {
-            st.pt.assign(st.n2, std::vector<Elem>(st.n1));
-            for (int j = 0; j < st.n2; ++j)
-                for (int b = 0; b < st.n1; ++b)
-                    if (!st.host[j][b].empty()) st.pt[j][b] = encode(st.host[j][b].data(), n, st.level, n, 1);
-        }
     for (int i = 0; i < P.L; ++i) {
         const u64 z = nt::powmod(P.psi[i], (u64)P.N / 2, P.q[i]);
         bp->zeta.c[i] = z; bp->zeta.c_sh[i] = nt::shoup(z, P.q[i]);
@@ -220,10 +168,8 @@ std::vector<int> Scheme::bootstrap_rotations(int slots) {
     if (it == boot_.end()) throw std::runtime_error("EvalBootstrapKeyGen: call EvalBootstrapSetup first");
     std::vector<int> r;
     for (auto* stages : {&it->second->cts, &it->second->stc})
-        for (auto& st : *stages) {
-            for (int b = 1; b < st.n1; ++b) r.push_back(st.g * b);
-            for (int gr : st.giant_rot) if (gr) r.push_back(gr);
-        }
+        for (auto& st : *stages)
+            for (int k : lintrans_rotations(st)) r.push_back(k);
     for (int k = slots; k < P.N / 2; k <<= 1) r.push_back(k);   // SubSum of sparse packing
     std::sort(r.begin(), r.end());
     r.erase(std::unique(r.begin(), r.end()), r.end());
@@ -237,36 +183,10 @@ void Scheme::bootstrap_keygen(int slots) {
 }
 
 namespace {
-Elem apply_stage(Scheme& s, LinStage& st, const Elem& in_ct, int n) {
-    Elem ct = in_ct;
-    if (ct.deg == 2) s.rescale_inplace(ct);
-    const int lvl = s.level_of(ct);
-    if (lvl != st.level) {       // re-encode the diagonals at the level the ciphertext actually has
-        for (int j = 0; j < st.n2; ++j)
-            for (int b = 0; b < st.n1; ++b)
-                if (!st.host[j][b].empty()) st.pt[j][b] = s.encode(st.host[j][b].data(), n, lvl, n, 1);
-        st.level = lvl;
-    }
-    std::vector<Elem> baby(st.n1);
-    baby[0] = ct;
-    for (int b = 1; b < st.n1; ++b) {
-        bool needed = false;
-        for (int j = 0; j < st.n2; ++j) needed |= st.pt[j][b].valid();
-        if (needed) baby[b] = s.rotate(ct, st.g * b);
-    }
-    Elem acc;
-    for (int j = 0; j < st.n2; ++j) {
-        Elem inner;
-        for (int b = 0; b < st.n1; ++b) {
-            if (!st.pt[j][b].valid()) continue;
-            Elem t = s.mult(baby[b], st.pt[j][b]);
-            inner = inner.valid() ? s.add(inner, t) : t;
-        }
-        if (!inner.valid()) continue;
-        if (st.giant_rot[j]) inner = s.rotate(inner, st.giant_rot[j]);
-        acc = acc.valid() ? s.add(acc, inner) : inner;
-    }
-    return acc;
+// FLK_BOOT_PLAIN=1: evaluate the transforms one EvalRotate / EvalMult / EvalAdd at a time (the checker path of lintrans.cpp)
+Elem apply_stage(Scheme& s, LinTrans& st, const Elem& ct, int) {
+    static const bool plain = [] { const char* e = std::getenv("FLK_BOOT_PLAIN"); return e && e[0] == '1'; }();
+    return plain ? s.lintrans_apply_plain(st, ct) : s.lintrans_apply(st, ct);
 }
 }  // namespace
 

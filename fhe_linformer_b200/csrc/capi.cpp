@@ -267,6 +267,35 @@ int fl_eval_chebyshev(fl_ctx* c, const fl_ct* x, const double* coeffs, int n, do
 int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree, double* out) {
     FL_TRY0({ auto v = Scheme::chebyshev_coefficients(f, user, a, b, degree); std::memcpy(out, v.data(), 8 * v.size()); })
 }
+struct fl_lt {
+    LinTrans t;
+};
+int fl_lt_create(fl_ctx* c, const int* shifts, int ndiag, const double* re, const double* im, int slots, int level, int max_baby, fl_lt** out) {
+    FL_TRY({
+        std::map<int, std::vector<cplx>> d;
+        for (int k = 0; k < ndiag; ++k) {
+            std::vector<cplx> v(slots);
+            for (int p = 0; p < slots; ++p) v[p] = cplx(re[(size_t)k * slots + p], im ? im[(size_t)k * slots + p] : 0.0);
+            d[shifts[k]] = std::move(v);
+        }
+        auto* h = new fl_lt{c->sch->lintrans_plan(d, slots, max_baby)};
+        if (level >= 0) c->sch->lintrans_encode(h->t, level);
+        *out = h;
+    })
+}
+int fl_lt_rotations(fl_ctx* c, const fl_lt* t, int* out, int cap) {
+    const std::vector<int> r = c->sch->lintrans_rotations(t->t);
+    for (int i = 0; i < (int)r.size() && i < cap; ++i) out[i] = r[i];
+    return (int)r.size();
+}
+int fl_lt_shape(const fl_lt* t, int* n1, int* n2, int* stride, int* ndiag) {
+    *n1 = t->t.n1; *n2 = t->t.n2; *stride = t->t.g; *ndiag = t->t.ndiag;
+    return 0;
+}
+int fl_lt_apply(fl_ctx* c, fl_lt* t, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->lintrans_apply(t->t, a->e))) }
+int fl_lt_apply_plain(fl_ctx* c, fl_lt* t, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->lintrans_apply_plain(t->t, a->e))) }
+void fl_lt_free(fl_lt* t) { delete t; }
+
 int fl_bootstrap_setup(fl_ctx* c, int b0, int b1, int slots) { FL_TRY(c->sch->bootstrap_setup(b0, b1, slots)) }
 int fl_bootstrap_keygen(fl_ctx* c, int slots) { FL_TRY(c->sch->bootstrap_keygen(slots)) }
 int fl_bootstrap(fl_ctx* c, const fl_ct* a, fl_ct** out) { FL_TRY(*out = wrap(c->sch->bootstrap(a->e))) }

@@ -115,7 +115,7 @@ __device__ __forceinline__ void double_to_u128(double v, bool& neg, u64& lo, u64
 
 // coefficient i * gap <- rint(re[bitrev(i)] / n * scale), coefficient N/2 + i * gap <- same for im; reduced into every limb
 __global__ void __launch_bounds__(kThreads) encode_finish_kernel(u64* __restrict__ dst, const double* __restrict__ re, const double* __restrict__ im,
-                                                                 int slots, int log_slots, int gap, double scale, DevTables T, int l) {
+                                                                 int slots, int log_slots, int gap, double scale, DevTables T, int l, int kext) {
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= 2 * slots) return;
     const int i = t < slots ? t : t - slots;
@@ -125,9 +125,10 @@ __global__ void __launch_bounds__(kThreads) encode_finish_kernel(u64* __restrict
     bool neg; u64 lo, hi;
     double_to_u128(v, neg, lo, hi);
     const size_t pos = (size_t)(t < slots ? 0 : T.N / 2) + (size_t)i * gap;
-    for (int k = 0; k < l; ++k) {
-        const u64 q = T.q[k];
-        u64 r = barrett128(U128{lo, hi}, q, T.mu_lo[k], T.mu_hi[k]);
+    for (int k = 0; k < l + kext; ++k) {            // kext > 0: also the first kext special limbs (extended-basis plaintexts)
+        const int m = k < l ? k : T.L + (k - l);
+        const u64 q = T.q[m];
+        u64 r = barrett128(U128{lo, hi}, q, T.mu_lo[m], T.mu_hi[m]);
         if (neg && r) r = q - r;
         dst[(size_t)k * T.N + pos] = r;
     }
@@ -150,15 +151,15 @@ void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const 
     FLK_CUDA(cudaGetLastError());
 }
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,
-                   const double* cim, cudaStream_t s) {
+                   const double* cim, cudaStream_t s, int kext) {
     int log_slots = 0;
     while ((1 << log_slots) < slots) ++log_slots;
     int len = slots;
     for (; len > kFftBlock; len >>= 1) fft_inv_stage_kernel<<<cdiv(slots / 2, kThreads), kThreads, 0, s>>>(re, im, slots, len, rot, cre, cim);
     if (len >= 2) fft_inv_block_kernel<<<slots / len, std::max(32, std::min(len / 2, kFftBlock / 2)), 0, s>>>(re, im, slots, len, rot, cre, cim);
     const int gap = (t.N / 2) / slots;
-    if (gap > 1) FLK_CUDA(cudaMemsetAsync(dst, 0, (size_t)l * t.N * 8, s));
-    encode_finish_kernel<<<cdiv((size_t)2 * slots, kThreads), kThreads, 0, s>>>(dst, re, im, slots, log_slots, gap, scale, t, l);
+    if (gap > 1) FLK_CUDA(cudaMemsetAsync(dst, 0, (size_t)(l + kext) * t.N * 8, s));
+    encode_finish_kernel<<<cdiv((size_t)2 * slots, kThreads), kThreads, 0, s>>>(dst, re, im, slots, log_slots, gap, scale, t, l, kext);
     FLK_CUDA(cudaGetLastError());
 }
 

@@ -84,6 +84,8 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
         for (int i = 0; i < P.L; ++i) {
             pinv[i] = nt::invmod(P.P_mod(P.q[i]), P.q[i]);
             pinv_sh[i] = nt::shoup(pinv[i], P.q[i]);
+            pmod_.c[i] = P.P_mod(P.q[i]);
+            pmod_.c_sh[i] = nt::shoup(pmod_.c[i], P.q[i]);
         }
         md_.post = to_device(post); md_.post_sh = to_device(post_sh); md_.phm = to_device(phm); md_.phm30 = to_device(phm30);
         md_.pinv = to_device(pinv); md_.pinv_sh = to_device(pinv_sh);
@@ -398,6 +400,127 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
         while ((1 << s_steps) - 1 < nk) ++s_steps;
         ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B * s_steps);
         ledger.add("add", l, 48.0 * l * P.N, B * s_steps);
+    }
+}
+
+void Engine::modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l) {
+    const KsLevel& ks = ks_level(l);
+    const int N = P.N, ext = l + P.K, beta = ks.beta;
+    const size_t dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N;
+    u64* dco = alloc(dco_bs * Bn);
+    if (Bn == 1) copy(dco, c, dco_bs);
+    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, c, c_bs * 8, dco_bs * 8, Bn, cudaMemcpyDeviceToDevice, stream));
+    launch_intt(T, dco, sel_range(0, l), Bn, dco_bs, ks.post, ks.post_sh, stream);
+    launch_modup_conv(T, ks, up, dco, Bn, up_bs, dco_bs, stream);
+    LimbSel su; su.n = 0;
+    for (int d = 0; d < beta; ++d) {
+        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
+        for (int t = 0; t < ext; ++t) {
+            if (t >= lo && t < hi) continue;
+            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+        }
+    }
+    launch_ntt(T, up, su, Bn, up_bs, stream);
+    release(dco);
+}
+
+void Engine::moddown_acc(u64* out, size_t out_bs, u64* acc, int Bn, int l, const u64* add0, size_t add0_bs, const u64* add1, size_t add1_bs,
+                         const u64* plus, size_t plus_bs, uint32_t g) {
+    const int N = P.N, K = P.K, ext = l + K;
+    const size_t acc_bs = (size_t)2 * ext * N, tq_bs = (size_t)2 * l * N;
+    LimbSel sp; sp.n = 2 * K;
+    for (int p = 0; p < 2; ++p)
+        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+    launch_intt(T, acc, sp, Bn, acc_bs, md_.post, md_.post_sh, stream);
+    u64* tq = alloc(tq_bs * Bn);
+    launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, Bn, tq_bs, acc_bs, stream);
+    LimbSel sq; sq.n = 2 * l;
+    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    launch_ntt(T, tq, sq, Bn, tq_bs, stream);
+    FinishArgs fa{out, out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, add0, add0_bs, add1, add1_bs, plus, plus_bs};
+    launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, Bn, stream);
+    release(tq);
+}
+
+// BSGS diagonal linear transform with double hoisting (the ct x pt matrix product of CoeffsToSlots / SlotsToCoeffs and of the
+// packed linear layers).  Against n1 - 1 + r separate rotations (r = rotating giant steps) it runs 1 + r ModUps instead of
+// n1 - 1 + r and n2 + 1 ModDowns instead of n1 - 1 + r, and the n1 n2 plaintext products + sums become one kernel that
+// streams each plaintext diagonal once per batch.
+void Engine::linear_transform(u64* out, const u64* ct, int B, const LtPlan& p) {
+    if (B <= 0) return;
+    const int l = p.l, n1 = p.n1, n2 = p.n2;
+    const KsLevel& ks = ks_level(l);
+    const int N = P.N, ext = l + P.K, beta = ks.beta;
+    const size_t cs = (size_t)2 * l * N, dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N, acc_bs = (size_t)2 * ext * N;
+    const u64* c1 = ct + (size_t)l * N;
+    // u_0 = P * ct on the Q limbs
+    u64* pc = alloc(cs * B);
+    launch_mul_scalar(T, pc, ct, pmod_, sel_range(0, l), 2 * B, stream);
+    // baby steps: one ModUp, one key inner product per rotation, no ModDown
+    BsgsArgs a{};
+    a.n1 = n1; a.n2 = n2;
+    for (int j = 0; j < n2; ++j) a.mask[j] = p.mask[j];
+    uint32_t used = 0;
+    for (int j = 0; j < n2; ++j) used |= p.mask[j];
+    u64* accb = nullptr;
+    int nb = 0;
+    if (used >> 1) {
+        u64* up = alloc(up_bs * B);
+        modup_batch(up, c1, cs, B, l);
+        accb = alloc(acc_bs * B * (size_t)(n1 - 1));
+        for (int i = 1; i < n1; ++i) {
+            if (!((used >> i) & 1u)) continue;
+            u64* dst = accb + (size_t)(i - 1) * B * acc_bs;
+            launch_inner_product(T, ks, dst, up, c1, p.baby_evk[i], B, acc_bs, up_bs, cs, stream);
+            a.accb[i] = dst; a.map[i] = automorph_map(p.baby_g[i]);
+            ++nb;
+        }
+        release(up);
+    }
+    u64* W = alloc(acc_bs * B * (size_t)n2);
+    launch_bsgs_inner(T, W, p.pts, pc, a, l, B, acc_bs, cs, stream);
+    if (accb) release(accb);
+    release(pc);
+    // one ModDown per giant step (all of them as one batch)
+    int r = 0;
+    for (int j = 0; j < n2; ++j) if (p.giant_g[j] != 1) ++r;
+    const bool ident = r < n2;     // the non-rotating giant step is the last one
+    if (r == 0) {
+        moddown_acc(out, cs, W, B, l, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+        release(W);
+    } else {
+        u64* w = alloc(cs * B * (size_t)n2);
+        moddown_acc(w, cs, W, B * n2, l, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+        release(W);
+        // giant steps: different operands, different rotations -- batched ModUp, one inner product each, summed through their
+        // automorphism maps in the extended basis, a single ModDown
+        u64* up2 = alloc(up_bs * B * (size_t)r);
+        modup_batch(up2, w + (size_t)l * N, cs, B * r, l);
+        u64* acc2 = alloc(acc_bs * B * (size_t)r);
+        GatherArgs gz{}, g0{};
+        gz.n = g0.n = r;
+        for (int j = 0; j < r; ++j) {
+            const u64* wj = w + (size_t)j * B * cs;
+            launch_inner_product(T, ks, acc2 + (size_t)j * B * acc_bs, up2 + (size_t)j * B * up_bs, wj + (size_t)l * N, p.giant_evk[j], B, acc_bs, up_bs, cs,
+                                 stream);
+            gz.src[j] = acc2 + (size_t)j * B * acc_bs; g0.src[j] = wj;
+            gz.map[j] = g0.map[j] = automorph_map(p.giant_g[j]);
+        }
+        release(up2);
+        u64* Z = alloc(acc_bs * B);
+        launch_gather_multi(T, Z, gz, l, ext, 2 * ext, B, acc_bs, acc_bs, stream);
+        u64* s0 = alloc(dco_bs * B);
+        launch_gather_multi(T, s0, g0, l, l, l, B, dco_bs, cs, stream);
+        release(acc2);
+        moddown_acc(out, cs, Z, B, l, s0, dco_bs, nullptr, 0, ident ? w + (size_t)r * B * cs : nullptr, cs, 0);
+        release(Z); release(s0); release(w);
+    }
+    if (ledger_on) {
+        // the reference's census of the same transform: one EvalRotate per baby / giant rotation, one ct x pt product and one
+        // addition per diagonal
+        ledger.add("rotate", l, (4.0 * l + 2.0 * P.beta(l) * (l + P.K)) * 8.0 * P.N, B * (nb + r));
+        ledger.add("mul_plain", l, 40.0 * P.N * l, B * p.ndiag);
+        ledger.add("add", l, 48.0 * l * P.N, B * std::max(0, p.ndiag - 1));
     }
 }
 

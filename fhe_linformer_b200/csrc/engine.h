@@ -31,6 +31,17 @@ struct KsBatch {
     const u64* plus; size_t plus_bs;    // optional [2][l][N] addend that is NOT permuted (rotate-and-add)
 };
 
+// BSGS plan of a diagonal linear transform  out = sum_j sigma_{G_j}( sum_i pt[j][i] * sigma_{g_i}(ct) )  (double hoisting).
+// Baby step 0 is the identity; a giant step without rotation (g = 1), if any, is stored last.
+struct LtPlan {
+    int n1 = 1, n2 = 1, l = 0;
+    uint32_t baby_g[kBsgsMax] = {};  const u64* baby_evk[kBsgsMax] = {};
+    uint32_t giant_g[kBsgsMax] = {}; const u64* giant_evk[kBsgsMax] = {};
+    uint32_t mask[kBsgsMax] = {};    // per giant step: bit i set when plaintext (j, i) is present
+    const u64* pts = nullptr;        // [n2][n1][l+K][N] plaintext diagonals over Q_l u P, evaluation form
+    int ndiag = 0;                   // present diagonals (ledger)
+};
+
 class Engine {
 public:
     explicit Engine(const ParamSpec& spec, int device = -1);
@@ -65,6 +76,9 @@ public:
     void keyswitch(u64* out, const u64* c, const u64* evk, int l, const u64* add0, const u64* add1, uint32_t g);
     void keyswitch(const KsBatch& io, const u64* evk, uint32_t g);
     void rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64* evk, int B, bool accumulate);   // ct, out: [B][2][l][N]
+    // out[b] = plan(ct[b]) for B ciphertexts stored back to back: one ModUp for all baby rotations, plaintext products in the
+    // extended basis, one ModDown per giant step, giant rotations summed before a single final ModDown
+    void linear_transform(u64* out, const u64* ct, int B, const LtPlan& plan);
     // out[b] = (self ? ct[b] : 0) + sum_k rotate(ct[b], g_k): the rotations share one ModUp and one ModDown (hoisting); nk <= 8
     void rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self);
     // the same with HOST operands: uploads, key switches and downloads of successive chunks overlap on three streams
@@ -94,6 +108,11 @@ public:
     size_t cached_bytes() const { return cached_bytes_; }
 
 private:
+    // the tail of a key switch: acc [Bn][2][l+K][N] (eval) -> out [Bn][2][l][N] = (acc - conv_P->Q(acc_P)) P^-1 + addends
+    void moddown_acc(u64* out, size_t out_bs, u64* acc, int Bn, int l, const u64* add0, size_t add0_bs, const u64* add1, size_t add1_bs,
+                     const u64* plus, size_t plus_bs, uint32_t g);
+    void modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l);   // digits + ModUp + NTT of Bn polynomials [l][N] -> [Bn][beta][l+K][N]
+    ScalarSet pmod_{};           // P mod q_i with Shoup companions
     std::map<size_t, std::vector<u64*>> free_blocks_;    // exact-size cache in front of the stream-ordered pool
     std::unordered_map<u64*, size_t> block_size_;
     size_t cached_bytes_ = 0, cache_cap_bytes_ = (size_t)96 << 30;   // of the 180 GB; FLK_CACHE_GB overrides

@@ -242,6 +242,74 @@ __global__ void __launch_bounds__(kThreads) gather_sum_kernel(u64* __restrict__ 
     s0[(size_t)b * s0_bs + (size_t)i * T.N + j] = v;
 }
 
+// ---- BSGS diagonal linear transform, double hoisting (CoeffsToSlots / SlotsToCoeffs, ct x pt matrix products) ----
+// W[(j B + b)][p][t][x] = sum_i pt[j][i][t][x] * u_i[b][p][t][x] over the extended basis Q_l u P, where u_i is baby rotation i of
+// ciphertext b BEFORE its ModDown: u_0 = P * ct (Q limbs; zero on the P limbs), u_i = sigma_i(IP_i(ModUp(c1)) + (P c0, 0)).
+// The automorphism is the gather x -> map_i[x]; one ModDown per giant step j then serves all n1 products (Bossuat et al.).
+// A thread owns coefficient x of limb t of BOTH polynomials of one ciphertext for every giant step, so a baby value is
+// fetched once and a plaintext word is used twice; products accumulate carry-free (mac3), one reduction per 8 terms.
+// grid (B, N / 256, ext): the B ciphertexts of a batch run side by side and share each plaintext word through L2.
+template <int N1>
+__global__ void __launch_bounds__(kThreads) bsgs_inner_kernel(u64* __restrict__ W, const u64* __restrict__ pts, const u64* __restrict__ pc,
+                                                              BsgsArgs a, DevTables T, int l, int B, size_t acc_bs, size_t pc_bs) {
+    const int b = blockIdx.x, t = blockIdx.z, ext = l + T.K;
+    const int x = blockIdx.y * kThreads + threadIdx.x;
+    if (x >= T.N) return;
+    const int m = t < l ? t : T.L + (t - l);
+    const RedC rc = load_redc(T, m);
+    const size_t row = (size_t)t * T.N, ppoly = (size_t)ext * T.N, cpoly = (size_t)l * T.N;
+    Split30 u0[N1], u1[N1];
+#pragma unroll
+    for (int i = 0; i < N1; ++i) {
+        u64 v0 = 0, v1 = 0;
+        if (i < a.n1) {
+            if (i == 0) {
+                if (t < l) { v0 = pc[(size_t)b * pc_bs + row + x]; v1 = pc[(size_t)b * pc_bs + cpoly + row + x]; }
+            } else if (a.accb[i]) {
+                const uint32_t src = a.map[i][x];
+                const u64* ab = a.accb[i] + (size_t)b * acc_bs + row + src;
+                v0 = ab[0]; v1 = ab[ppoly];
+                if (t < l) v0 = addmod(v0, pc[(size_t)b * pc_bs + row + src], rc.q);
+            }
+        }
+        u0[i] = split30(v0); u1[i] = split30(v1);
+    }
+    for (int j = 0; j < a.n2; ++j) {
+        const uint32_t mask = a.mask[j];
+        const u64* pj = pts + ((size_t)j * a.n1 * ext + t) * T.N + x;
+        u64 r0 = 0, r1 = 0;
+#pragma unroll
+        for (int i0 = 0; i0 < N1; i0 += 8) {
+            if (i0 >= a.n1) break;
+            Acc3 s0{0, 0, 0}, s1{0, 0, 0};
+#pragma unroll
+            for (int i = i0; i < i0 + 8 && i < N1; ++i) {
+                if (i < a.n1 && ((mask >> i) & 1u)) {
+                    const Split30 ps = split30(__ldg(pj + (size_t)i * ppoly));
+                    mac3(s0, u0[i], ps); mac3(s1, u1[i], ps);
+                }
+            }
+            r0 = i0 ? addmod(r0, reduce3(s0, rc), rc.q) : reduce3(s0, rc);
+            r1 = i0 ? addmod(r1, reduce3(s1, rc), rc.q) : reduce3(s1, rc);
+        }
+        u64* o = W + ((size_t)j * B + b) * acc_bs + row + x;
+        o[0] = r0; o[ppoly] = r1;
+    }
+}
+
+// out[b][r][x] = sum_k src_k[b][r][map_k[x]]  (rows r of rpp limbs per polynomial, modulus by extended-basis index)   grid (N / 256, rows, B)
+__global__ void __launch_bounds__(kThreads) gather_multi_kernel(u64* __restrict__ out, GatherArgs g, DevTables T, int l, int rpp, size_t out_bs,
+                                                                size_t src_bs) {
+    const int x = blockIdx.x * kThreads + threadIdx.x, r = blockIdx.y, b = blockIdx.z;
+    if (x >= T.N) return;
+    const int t = r % rpp;
+    const u64 q = T.q[t < l ? t : T.L + (t - l)];
+    const size_t o = (size_t)b * src_bs + (size_t)r * T.N;
+    u64 v = 0;
+    for (int k = 0; k < g.n; ++k) v = addmod(v, g.src[k][o + g.map[k][x]], q);
+    out[(size_t)b * out_bs + (size_t)r * T.N + x] = v;
+}
+
 // grid: (N / 256, target groups, batch * polys); pcoef = P part (coefficient form, pre-scaled) of accumulator (b, p)
 template <int KK>
 __global__ void __launch_bounds__(kThreads) moddown_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ pcoef, size_t pstride, DevTables T,
@@ -515,6 +583,19 @@ void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishAr
     moddown_finish_kernel<<<dim3(cdiv(t.N, kThreads), rg.count, polys * batch), kThreads, 0, s>>>(a.out, a.acc, a.acc_ps, a.tq, a.add0, a.add1, map, t, md, l,
                                                                                                  polys, a.out_bs, a.acc_bs, a.tq_bs, a.add0_bs,
                                                                                                  a.add1_bs, a.plus, a.plus_bs, rg.first);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_bsgs_inner(const DevTables& t, u64* W, const u64* pts, const u64* pc, const BsgsArgs& a, int l, int B, size_t acc_bs, size_t pc_bs,
+                       cudaStream_t s) {
+    if (a.n1 < 1 || a.n1 > kBsgsMax || a.n2 < 1 || a.n2 > kBsgsMax) throw std::invalid_argument("linear transform: 1..16 baby and giant steps");
+    const dim3 grid(B, cdiv(t.N, kThreads), l + t.K);
+    if (a.n1 <= 8) bsgs_inner_kernel<8><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    else bsgs_inner_kernel<16><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_gather_multi(const DevTables& t, u64* out, const GatherArgs& g, int l, int rows_per_poly, int rows, int batch, size_t out_bs, size_t src_bs,
+                         cudaStream_t s) {
+    gather_multi_kernel<<<dim3(cdiv(t.N, kThreads), rows, batch), kThreads, 0, s>>>(out, g, t, l, rows_per_poly, out_bs, src_bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s) {

@@ -70,6 +70,26 @@ void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
                          size_t tq_bs, size_t p_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
 // out[b][p][i][j] = ((acc[b][p][i] - tq[b][p][i]) * P^-1 + add_p[b][i])[map ? map[j] : j] + (plus ? plus[b][p][i][j] : 0)
+// BSGS linear transform (engine.cu: Engine::linear_transform)
+constexpr int kBsgsMax = 16;
+struct BsgsArgs {
+    const u64* accb[kBsgsMax];        // unpermuted key inner products of baby rotation i >= 1, [B][2][l+K][N]; null = baby not used
+    const uint32_t* map[kBsgsMax];    // automorphism gather map of baby rotation i (unused for i = 0, the identity)
+    uint32_t mask[kBsgsMax];          // per giant step: bit i set when diagonal (j, i) is present
+    int n1, n2;
+};
+struct GatherArgs {
+    const u64* src[kBsgsMax];
+    const uint32_t* map[kBsgsMax];
+    int n;
+};
+// W[(j B + b)] = sum_i pt[j][i] * u_i[b] in the extended basis; pts [n2][n1][l+K][N], pc = P * ct [B][2][l][N]
+void launch_bsgs_inner(const DevTables& t, u64* W, const u64* pts, const u64* pc, const BsgsArgs& a, int l, int B, size_t acc_bs, size_t pc_bs,
+                       cudaStream_t s);
+// out[b][r] = sum_k src_k[b][r] gathered through map_k; rows of rows_per_poly limbs per polynomial
+void launch_gather_multi(const DevTables& t, u64* out, const GatherArgs& g, int l, int rows_per_poly, int rows, int batch, size_t out_bs, size_t src_bs,
+                         cudaStream_t s);
+
 struct FinishArgs {
     u64* out; size_t out_bs;
     const u64* acc; size_t acc_ps, acc_bs;
@@ -113,8 +133,9 @@ void upload_gauss_table(const u64* cdt30);
 void launch_sample_limbs(const DevTables& t, u64* dst, u64 seed, int kind, const LimbSel& sel, cudaStream_t s);
 // dst limb i <- uniform residues mod q_{sel.m[i]} from SplitMix64(seeds[i])
 void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const LimbSel& sel, cudaStream_t s);
-// special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd)
+// special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd);
+// kext > 0 appends the residues modulo the first kext special limbs (plaintexts in the extended basis Q_l u P)
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,
-                   const double* cim, cudaStream_t s);
+                   const double* cim, cudaStream_t s, int kext = 0);
 
 }  // namespace flk

@@ -51,6 +51,20 @@ struct SplitMix {
 
 struct BootPrecomp;   // bootstrap.cpp
 
+// A slots x slots matrix given by its (generalised) diagonals, prepared for the baby-step/giant-step evaluation
+// (M v)[p] = sum_d diag_d[p] v[(p + d) mod slots]  ==  sum_j Rot_{G_j}( sum_i P_{j,i} * Rot_{g i}(v) ),  P_{j,i} = Rot_{-G_j}(diag).
+// This is the ct x pt matrix product of CoeffsToSlots / SlotsToCoeffs and of packed linear layers (lintrans.cpp).
+struct LinTrans {
+    int slots = 0, g = 1, n1 = 1, n2 = 1, off = 0, cnt = 0;
+    std::vector<int> giant_rot;                          // rotation of giant step j; rotating steps first, the identity (0) last
+    std::vector<std::vector<std::vector<cplx>>> host;    // [j][i] pre-rotated diagonals, empty = absent
+    std::vector<uint32_t> mask;
+    int ndiag = 0;
+    int level = -1;                                      // level the device plaintexts are encoded at (-1: not yet)
+    double pt_scale = 0;
+    Mem pts;                                             // [n2][n1][l+K][N] over Q_l u P, evaluation form
+};
+
 class Scheme {
 public:
     explicit Scheme(const ParamSpec& spec, int device = -1);
@@ -100,6 +114,12 @@ public:
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);
     Elem rotsum(const Elem& a, int steps, int stride);   // FHEController::rotsum / repeat ladders F.cpp:829-867
+    // BSGS diagonal linear transforms (EvalLinearTransform of CoeffsToSlots / SlotsToCoeffs; packed ct x pt matrix products)
+    LinTrans lintrans_plan(const std::map<int, std::vector<cplx>>& diags, int slots, int max_baby = 0);
+    std::vector<int> lintrans_rotations(const LinTrans& t) const;
+    void lintrans_encode(LinTrans& t, int level);
+    Elem lintrans_apply(LinTrans& t, const Elem& ct);          // result: deg + 1, scale = ct.scale * sf[level]
+    Elem lintrans_apply_plain(LinTrans& t, const Elem& ct);    // the same transform, one EvalRotate / EvalMult / EvalAdd at a time (checker)
     Elem apply_galois(const Elem& a, uint32_t g);
     Elem clone(const Elem& a);                        // Ciphertext::Clone M:223
     Elem pack(const std::vector<Elem>& v);            // gather ciphertexts of identical level / scale into one batched operand

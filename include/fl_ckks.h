@@ -145,6 +145,23 @@ int fl_eval_poly(fl_ctx* c, const fl_ct* a, const double* coeffs, int n, fl_ct**
 int fl_eval_chebyshev(fl_ctx* c, const fl_ct* x, const double* coeffs, int n, double a, double b, fl_ct** out);
 int fl_chebyshev_coefficients(double (*f)(double, void*), void* user, double a, double b, int degree, double* out /* degree+1 */);
 
+/* BSGS diagonal ciphertext x plaintext matrix product (OpenFHE EvalLinearTransform, the kernel of CoeffsToSlots / SlotsToCoeffs
+ * inside EvalBootstrap F.cpp:445; BASELINE.json north star: "the BSGS diagonal ciphertext x plaintext matmul behind the Linformer
+ * E/F projections and the Q/K/V/FFN linears").  The matrix is given by its generalised diagonals:
+ *   (M v)[p] = sum_k diag_k[p] * v[(p + shifts[k]) mod slots],   re / im: [ndiag][slots] (im may be NULL).
+ * fl_lt_create plans baby / giant steps (max_baby = 0: ~sqrt of the diagonal span, <= 16 each) and, for level >= 0, encodes the
+ * pre-rotated diagonals over Q_l u P at that level; fl_lt_rotations lists the rotation keys fl_lt_apply needs (returns their
+ * count).  fl_lt_apply evaluates the product in one call with double hoisting (one ModUp for all baby steps, one ModDown per giant
+ * step, one for all giant rotations); a batched operand is transformed as one.  The result has one more scaling degree, like
+ * EvalMult(ct, pt).  fl_lt_apply_plain is the same plan as separate EvalRotate / EvalMult / EvalAdd calls (test checker). */
+typedef struct fl_lt fl_lt;
+int fl_lt_create(fl_ctx* c, const int* shifts, int ndiag, const double* re, const double* im, int slots, int level, int max_baby, fl_lt** out);
+int fl_lt_rotations(fl_ctx* c, const fl_lt* t, int* out, int cap);
+int fl_lt_shape(const fl_lt* t, int* n1, int* n2, int* stride, int* ndiag);
+int fl_lt_apply(fl_ctx* c, fl_lt* t, const fl_ct* a, fl_ct** out);
+int fl_lt_apply_plain(fl_ctx* c, fl_lt* t, const fl_ct* a, fl_ct** out);
+void fl_lt_free(fl_lt* t);
+
 /* EvalBootstrapSetup F.cpp:238,280, EvalBootstrapKeyGen F.cpp:239, EvalBootstrap F.cpp:445 */
 int fl_bootstrap_setup(fl_ctx* c, int budget_cts, int budget_stc, int slots);
 int fl_bootstrap_keygen(fl_ctx* c, int slots);
