@@ -280,6 +280,10 @@ def run_b200(a):
     fwd = None
     if not a.no_forward:
         fwd = run_forward(a, local, rank, world, torch, dist)
+        if fwd and cpu is not None:
+            fwd["cpu_estimate"] = forward_cpu_estimate(a, fwd.pop("_ledger"), e.K, e.alpha)
+        if fwd:
+            fwd.pop("_ledger", None)
 
     if rank == 0:
         launches_per_group = 12         # kernels per batched call: 4 NTT pass pairs (8) + modup / inner product / moddown conv / finish (4); plus 1 D2D copy
@@ -306,6 +310,32 @@ def run_b200(a):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def forward_cpu_estimate(a, led, K, alpha):
+    """Same-host CPU time of the forward's key switches (SURVEY 8(d) "stratified sample of the ledger"): the oracle's EvalRotate is
+    timed at four limb counts on the forward's ring and every rotate@l / mul_relin@l row of the op ledger is charged the time
+    interpolated (linearly in the algorithmic bytes of a key switch) for its l.  Additions, plaintext products, rescales and
+    encodings are NOT charged, so the estimate is a lower bound of the CPU time and the ratio a lower bound of the speed-up."""
+    from oracle.oracle import Oracle, lib
+    o = Oracle(logN=a.forward_logn, L=28, dnum=4)
+    N = 1 << a.forward_logn
+    pts = []
+    for l in (28, 21, 14, 7):
+        pts.append((algorithmic_bytes_rotate(N, l, K, alpha), cpu_rotations(o, l, 3, seed=l)))
+    xs = np.array([p[0] for p in pts], float); ys = np.array([p[1] for p in pts], float)
+    slope, icpt = np.polyfit(xs, ys, 1)
+    total, n_ks = 0.0, 0
+    for key, (n, _) in led.items():
+        op, _, l = key.partition("@")
+        if op in ("rotate", "mul_relin"):
+            total += n * max(0.0, slope * algorithmic_bytes_rotate(N, int(l), K, alpha) + icpt)
+            n_ks += n
+    cores = int(lib().orc_num_threads())
+    return {"seconds_per_sample_lower_bound": float(total), "key_switches": n_ks, "cores": cores, "kind": "port",
+            "sampled": {str(l): round(t * 1e3, 2) for l, (_, t) in zip((28, 21, 14, 7), pts)}, "sampled_unit": "ms per EvalRotate at l limbs",
+            "method": "oracle/ckks_oracle.c EvalRotate (OpenMP, all host cores) timed at l = 28, 21, 14, 7 on the forward's ring; "
+                      "each rotate / mul_relin row of the op ledger charged the interpolated time; other ops not charged"}
 
 
 def run_forward(a, local, rank, world, torch, dist):
@@ -365,7 +395,7 @@ def run_forward(a, local, rank, world, torch, dist):
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
-            "n16": n16,
+            "n16": n16, "_ledger": led,
             "note": "text files -> encode/encrypt -> encoder1 -> pooler -> classifier -> decrypt, wall clock incl. host encode; "
                     "lean = same logits without the operations main.cpp issues but never reads"}
 
