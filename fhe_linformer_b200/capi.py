@@ -51,7 +51,7 @@ def load_library():
         "fl_raw_keyswitch": (ci, [vp, vp, vp, vp, ci]),
         "fl_raw_rotate": (ci, [vp, vp, vp, ci, u32, vp]),
         "fl_raw_rotate_batch": (ci, [vp, vp, vp, ci, u32, vp, ci]),
-        "fl_host_rotate_batch": (ci, [vp, vp, vp, ci, u32, vp, ci]),
+        "fl_host_rotate_batch": (ci, [vp, vp, vp, ci, u32, vp, ci]), "fl_host_rotate_batch_async": (ci, [vp, vp, vp, ci, u32, vp, ci]),
         "fl_raw_mul_relin": (ci, [vp, vp, vp, vp, ci, vp]),
         "fl_raw_mul_plain": (ci, [vp, vp, vp, vp, ci]),
         "fl_host_ntt": (ci, [vp, vp, ci, ci]),
@@ -205,9 +205,11 @@ class Engine:
         out = out or self.buf(cts.shape)
         self._ck(self.lib.fl_raw_rotate_batch(self.h, out.ptr, cts.ptr, cts.shape[2], g, evk.ptr, cts.shape[0])); return out
 
-    def host_rotate_batch(self, cts, g, evk, out=None):
+    def host_rotate_batch(self, cts, g, evk, out=None, wait=True):
+        """EvalRotate of host-resident ciphertexts [B][2][l][N]; wait=False returns at once (results valid after sync())."""
         out = np.empty_like(cts) if out is None else out
-        self._ck(self.lib.fl_host_rotate_batch(self.h, _ptr(out), _ptr(cts), cts.shape[2], g, evk.ptr, cts.shape[0])); return out
+        fn = self.lib.fl_host_rotate_batch if wait else self.lib.fl_host_rotate_batch_async
+        self._ck(fn(self.h, _ptr(out), _ptr(cts), cts.shape[2], g, evk.ptr, cts.shape[0])); return out
 
     def mul_relin(self, a, b, evk, out=None):
         out = out or self.buf(a.shape)

@@ -186,8 +186,17 @@ int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l
         e.release(in); e.release(out);
     })
 }
+// ciphertexts per pipeline stage of the host-operand calls (FLK_HOST_CHUNK overrides).  Measured (scripts/e2e_sweep.py): a call that
+// waits for its results is shortest with one ciphertext per stage (smallest drain), overlapped calls with two.
+static int host_chunk(bool wait) {
+    static const int v = [] { const char* e = std::getenv("FLK_HOST_CHUNK"); return e ? std::max(1, std::atoi(e)) : 0; }();
+    return v ? v : (wait ? 1 : 2);
+}
 int fl_host_rotate_batch(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch) {
-    FL_TRY(c->eng->rotate_batch_host(out_host, ct_host, l, g, evk_dev, batch, 2))
+    FL_TRY(c->eng->rotate_batch_host(out_host, ct_host, l, g, evk_dev, batch, host_chunk(true), true))
+}
+int fl_host_rotate_batch_async(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch) {
+    FL_TRY(c->eng->rotate_batch_host(out_host, ct_host, l, g, evk_dev, batch, host_chunk(false), false))
 }
 int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev) {
     FL_TRY({

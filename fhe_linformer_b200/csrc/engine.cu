@@ -107,6 +107,10 @@ Engine::~Engine() {
     cudaStreamSynchronize(stream);
     for (auto& kv : maps_) cudaFree(kv.second);
     for (void* p : owned_) cudaFree(p);
+    for (auto& sl : host_slots_) {
+        if (sl.in) { cudaFree(sl.in); cudaFree(sl.out); }
+        if (sl.in_consumed) { cudaEventDestroy(sl.in_consumed); cudaEventDestroy(sl.out_drained); }
+    }
     if (h2d_stream) cudaStreamDestroy(h2d_stream);
     if (d2h_stream) cudaStreamDestroy(d2h_stream);
     cudaStreamDestroy(stream);
@@ -160,7 +164,10 @@ void Engine::download(u64* dst, const u64* src, size_t words) {
     FLK_CUDA(cudaStreamSynchronize(stream));
 }
 void Engine::copy(u64* dst, const u64* src, size_t words) { FLK_CUDA(cudaMemcpyAsync(dst, src, words * 8, cudaMemcpyDeviceToDevice, stream)); }
-void Engine::sync() { FLK_CUDA(cudaStreamSynchronize(stream)); }
+void Engine::sync() {
+    FLK_CUDA(cudaStreamSynchronize(stream));
+    if (d2h_stream) { FLK_CUDA(cudaStreamSynchronize(h2d_stream)); FLK_CUDA(cudaStreamSynchronize(d2h_stream)); }
+}
 
 void Engine::ntt(u64* data, const LimbSel& sel, int batch, size_t bs) { launch_ntt(T, data, sel, batch, bs, stream); }
 void Engine::intt(u64* data, const LimbSel& sel, int batch, size_t bs) { launch_intt(T, data, sel, batch, bs, nullptr, nullptr, stream); }
@@ -526,22 +533,34 @@ void Engine::linear_transform(u64* out, const u64* ct, int B, const LtPlan& p) {
 
 // Host-resident caller (the reference keeps ciphertexts in host memory): chunk c+1 is uploaded while chunk c is key
 // switched and chunk c-1 is downloaded, so a PCIe-bound call costs max(H2D, D2H, compute) instead of their sum.
-void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk) {
+// The device-side staging areas are two persistent slots used alternately by successive calls, each guarded by its own
+// events, so with wait = false call n+1 starts uploading while call n is still computing / downloading (the caller
+// synchronises once with sync()); wait = true returns with the results in out_host.
+void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk, bool wait) {
     if (B <= 0) return;
     if (!h2d_stream) {
         FLK_CUDA(cudaStreamCreateWithFlags(&h2d_stream, cudaStreamNonBlocking));
         FLK_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+        for (auto& sl : host_slots_) {
+            FLK_CUDA(cudaEventCreateWithFlags(&sl.in_consumed, cudaEventDisableTiming));
+            FLK_CUDA(cudaEventCreateWithFlags(&sl.out_drained, cudaEventDisableTiming));
+        }
     }
     chunk = std::max(1, std::min(chunk, B));
     const size_t cs = (size_t)2 * l * P.N;
-    u64* in = alloc(cs * B);
-    u64* out = alloc(cs * B);
+    if (host_slots_[0].words < cs * B) {           // grow both slots: only after everything that uses them has finished
+        sync();
+        for (auto& s2 : host_slots_) {
+            if (s2.in) { FLK_CUDA(cudaFree(s2.in)); FLK_CUDA(cudaFree(s2.out)); }
+            FLK_CUDA(cudaMalloc(&s2.in, cs * B * 8)); FLK_CUDA(cudaMalloc(&s2.out, cs * B * 8));
+            s2.words = cs * B;
+        }
+    }
+    HostSlot& sl = host_slots_[host_next_++ & 1];
     automorph_map(g);   // table upload (first use of g) happens before the pipeline starts
     ks_level(l);
-    cudaEvent_t ready;
-    FLK_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    FLK_CUDA(cudaEventRecord(ready, stream));             // the stream-ordered allocations above are valid from here on
-    FLK_CUDA(cudaStreamWaitEvent(h2d_stream, ready, 0));
+    FLK_CUDA(cudaStreamWaitEvent(h2d_stream, sl.in_consumed, 0));     // the slot's previous key switches have read their inputs
+    FLK_CUDA(cudaStreamWaitEvent(stream, sl.out_drained, 0));         // ... and its previous results have left for the host
     const int nch = (B + chunk - 1) / chunk;
     std::vector<cudaEvent_t> up(nch), done(nch);
     for (int c = 0; c < nch; ++c) {
@@ -550,21 +569,18 @@ void Engine::rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_
     }
     for (int c = 0; c < nch; ++c) {
         const int b0 = c * chunk, nb = std::min(chunk, B - b0);
-        FLK_CUDA(cudaMemcpyAsync(in + b0 * cs, ct_host + b0 * cs, cs * nb * 8, cudaMemcpyHostToDevice, h2d_stream));
+        FLK_CUDA(cudaMemcpyAsync(sl.in + b0 * cs, ct_host + b0 * cs, cs * nb * 8, cudaMemcpyHostToDevice, h2d_stream));
         FLK_CUDA(cudaEventRecord(up[c], h2d_stream));
         FLK_CUDA(cudaStreamWaitEvent(stream, up[c], 0));
-        rotate_batch(out + b0 * cs, in + b0 * cs, l, g, evk, nb, false);
+        rotate_batch(sl.out + b0 * cs, sl.in + b0 * cs, l, g, evk, nb, false);
         FLK_CUDA(cudaEventRecord(done[c], stream));
         FLK_CUDA(cudaStreamWaitEvent(d2h_stream, done[c], 0));
-        FLK_CUDA(cudaMemcpyAsync(out_host + b0 * cs, out + b0 * cs, cs * nb * 8, cudaMemcpyDeviceToHost, d2h_stream));
+        FLK_CUDA(cudaMemcpyAsync(out_host + b0 * cs, sl.out + b0 * cs, cs * nb * 8, cudaMemcpyDeviceToHost, d2h_stream));
     }
-    FLK_CUDA(cudaEventRecord(ready, d2h_stream));
-    FLK_CUDA(cudaStreamWaitEvent(stream, ready, 0));      // buffers are released only after the last download
-    release(in); release(out);
-    FLK_CUDA(cudaStreamSynchronize(d2h_stream));
-    FLK_CUDA(cudaStreamSynchronize(stream));
-    for (int c = 0; c < nch; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(done[c]); }
-    cudaEventDestroy(ready);
+    FLK_CUDA(cudaEventRecord(sl.in_consumed, stream));
+    FLK_CUDA(cudaEventRecord(sl.out_drained, d2h_stream));
+    for (int c = 0; c < nch; ++c) { cudaEventDestroy(up[c]); cudaEventDestroy(done[c]); }   // released when they complete
+    if (wait) sync();
 }
 
 void Engine::mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk) { mul_relin_batch(out, a, b, l, evk, 1, 0); }

@@ -82,7 +82,7 @@ public:
     // out[b] = (self ? ct[b] : 0) + sum_k rotate(ct[b], g_k): the rotations share one ModUp and one ModDown (hoisting); nk <= 8
     void rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self);
     // the same with HOST operands: uploads, key switches and downloads of successive chunks overlap on three streams
-    void rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk);
+    void rotate_batch_host(u64* out_host, const u64* ct_host, int l, uint32_t g, const u64* evk, int B, int chunk, bool wait = true);
     void rotate(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);
     void rotate_add(u64* out, const u64* ct, int l, uint32_t g, const u64* evk);   // out = ct + rotate(ct)
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
@@ -113,6 +113,9 @@ private:
                      const u64* plus, size_t plus_bs, uint32_t g);
     void modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l);   // digits + ModUp + NTT of Bn polynomials [l][N] -> [Bn][beta][l+K][N]
     ScalarSet pmod_{};           // P mod q_i with Shoup companions
+    struct HostSlot { u64* in = nullptr; u64* out = nullptr; size_t words = 0; cudaEvent_t in_consumed = nullptr, out_drained = nullptr; };
+    HostSlot host_slots_[2];     // device staging of the host-operand pipeline, alternated by successive calls
+    unsigned host_next_ = 0;
     std::map<size_t, std::vector<u64*>> free_blocks_;    // exact-size cache in front of the stream-ordered pool
     std::unordered_map<u64*, size_t> block_size_;
     size_t cached_bytes_ = 0, cache_cap_bytes_ = (size_t)96 << 30;   // of the 180 GB; FLK_CACHE_GB overrides

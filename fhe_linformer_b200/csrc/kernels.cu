@@ -1,6 +1,7 @@
 // kernels.cu -- element-wise, automorphism, base-conversion, inner-product, ModDown and rescale kernels
 // (K2-K7 of SURVEY.md 2.1) for sm_100a.  All are HBM-streaming integer kernels: limb-major layout,
 // adjacent threads on adjacent coefficients, 128-bit accumulators reduced once.
+#include <cstdlib>
 #include "kernels.cuh"
 #include "modarith.cuh"
 
@@ -183,7 +184,7 @@ struct MultiKeys {
     const uint32_t* map[8];
     int n;
 };
-template <int BETA>
+template <int BETA, int KPR_MAX>
 __global__ void __launch_bounds__(kThreads) inner_product_multi_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                        MultiKeys mk, DevTables T, KsLevel ks, int batch, size_t acc_bs, size_t up_bs,
                                                                        size_t c_bs) {
@@ -195,9 +196,14 @@ __global__ void __launch_bounds__(kThreads) inner_product_multi_kernel(u64* __re
     const size_t kpoly = (size_t)(T.L + T.K) * T.N;
     const int own_d = t < l ? t / ks.alpha : -1;
     const RedC rc = load_redc(T, m);
+    // The carry-free accumulators take 8 products before they must be reduced, so the digit products of KPR = 8 / BETA keys
+    // (gathered at different source positions, but summed into the same output) share one reduction -- the reduction costs
+    // more instructions than a key's products.
+    constexpr int KPR = (BETA >= 8 ? 1 : 8 / BETA) < KPR_MAX ? (BETA >= 8 ? 1 : 8 / BETA) : KPR_MAX;
     u64 r0[IPB], r1[IPB];
+    Acc3 s0[IPB], s1[IPB];
 #pragma unroll
-    for (int i = 0; i < IPB; ++i) r0[i] = r1[i] = 0;
+    for (int i = 0; i < IPB; ++i) { r0[i] = r1[i] = 0; s0[i] = Acc3{0, 0, 0}; s1[i] = Acc3{0, 0, 0}; }
     for (int k = 0; k < mk.n; ++k) {
         const uint32_t src = mk.map[k][j];
         Split30 k0[BETA], k1[BETA];
@@ -206,19 +212,22 @@ __global__ void __launch_bounds__(kThreads) inner_product_multi_kernel(u64* __re
             const u64* kb = mk.evk[k] + (size_t)d * 2 * kpoly + (size_t)m * T.N + src;
             k0[d] = split30(__ldg(kb)); k1[d] = split30(__ldg(kb + kpoly));
         }
+        const bool flush = (k % KPR) == KPR - 1 || k == mk.n - 1;
 #pragma unroll
         for (int i = 0; i < IPB; ++i) {
             if (b0 + i >= batch) break;
-            Acc3 s0{0, 0, 0}, s1{0, 0, 0};
 #pragma unroll
             for (int d = 0; d < BETA; ++d) {
                 const u64 u = d == own_d ? c_eval[(size_t)(b0 + i) * c_bs + (size_t)t * T.N + src]
                                          : up[(size_t)(b0 + i) * up_bs + ((size_t)d * ext + t) * T.N + src];
                 const Split30 us = split30(u);
-                mac3(s0, us, k0[d]); mac3(s1, us, k1[d]);
+                mac3(s0[i], us, k0[d]); mac3(s1[i], us, k1[d]);
             }
-            r0[i] = addmod(r0[i], reduce3(s0, rc), rc.q);
-            r1[i] = addmod(r1[i], reduce3(s1, rc), rc.q);
+            if (flush) {
+                r0[i] = addmod(r0[i], reduce3(s0[i], rc), rc.q);
+                r1[i] = addmod(r1[i], reduce3(s1[i], rc), rc.q);
+                s0[i] = Acc3{0, 0, 0}; s1[i] = Acc3{0, 0, 0};
+            }
         }
     }
 #pragma unroll
@@ -545,8 +554,10 @@ void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc,
     mk.n = nk;
     for (int k = 0; k < nk; ++k) { mk.evk[k] = evks[k]; mk.map[k] = maps[k]; }
     const dim3 grid(cdiv(t.N, kThreads), ks.l + t.K, (batch + 1) / 2);
+    static const bool group = [] { const char* e = std::getenv("FLK_IPM_GROUP"); return !e || e[0] != '0'; }();
     switch (ks.beta) {
-#define FLK_CASE(X) case X: inner_product_multi_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, mk, t, ks, batch, acc_bs, up_bs, c_bs); break;
+#define FLK_CASE(X) case X: if (group) inner_product_multi_kernel<X, 8><<<grid, kThreads, 0, s>>>(acc, up, c_eval, mk, t, ks, batch, acc_bs, up_bs, c_bs); \
+                            else inner_product_multi_kernel<X, 1><<<grid, kThreads, 0, s>>>(acc, up, c_eval, mk, t, ks, batch, acc_bs, up_bs, c_bs); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
 #undef FLK_CASE
         default: throw std::invalid_argument("more than 8 key-switch digits is not supported");

@@ -91,6 +91,10 @@ int fl_raw_ks_moddown(fl_ctx* c, uint64_t* out, uint64_t* tq, const uint64_t* ac
 int fl_host_ntt(fl_ctx* c, uint64_t* poly_host, int l, int inverse);
 int fl_host_rotate(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev);
 int fl_host_rotate_batch(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch);
+/* The same call without the final wait: uploads, key switches and downloads of successive calls overlap on three streams (two
+ * device staging slots used alternately); out_host is valid after fl_sync().  Buffers should be pinned (cudaHostAlloc /
+ * cudaHostRegister), and neither buffer of a call may be reused before the second following call or fl_sync(). */
+int fl_host_rotate_batch_async(fl_ctx* c, uint64_t* out_host, const uint64_t* ct_host, int l, uint32_t g, const uint64_t* evk_dev, int batch);
 int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, const uint64_t* b_host, int l, const uint64_t* evk_dev);
 
 /* ================= scheme level: what FHEController's methods call on `context` ================= */

@@ -192,6 +192,14 @@ def test_batched_rotation_equals_single(pair):
         for b in range(5):
             assert (got[b] == o.rotate(cts[b], g, evk)).all(), (l, b)
         assert (e.host_rotate_batch(cts, g, d_evk) == got).all()
+        # overlapped calls (no wait inside the call, two staging slots used alternately, one sync at the end)
+        outs = [np.zeros_like(cts) for _ in range(5)]
+        ins = [np.roll(cts, i, axis=0).copy() for i in range(5)]
+        for i in range(5):
+            e.host_rotate_batch(ins[i], g, d_evk, out=outs[i], wait=False)
+        e.sync()
+        for i in range(5):
+            assert (outs[i] == np.roll(got, i, axis=0)).all(), (l, i)
 
 
 def test_batched_ntt_equals_single(pair):
