@@ -185,7 +185,7 @@ struct MultiKeys {
     int n;
 };
 template <int BETA, int KPR_MAX>
-__global__ void __launch_bounds__(kThreads) inner_product_multi_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
+__global__ void __launch_bounds__(kThreads, KPR_MAX > 1 ? 4 : 1) inner_product_multi_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                        MultiKeys mk, DevTables T, KsLevel ks, int batch, size_t acc_bs, size_t up_bs,
                                                                        size_t c_bs) {
     constexpr int IPB = 2;
