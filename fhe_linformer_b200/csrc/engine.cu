@@ -56,7 +56,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
         std::vector<u64> rc((size_t)Tn * 8, 0);
         for (int m = 0; m < Tn; ++m) {
             const u64 qq = P.q[m];
-            if ((qq >> 60) || qq < (1ull << 31)) throw std::invalid_argument("moduli must lie between 2^31 and 2^60");
+            if ((qq >> 60) || qq < (1ull << 33)) throw std::invalid_argument("moduli must lie between 2^33 and 2^60");
             const u64 c30 = (1ull << 30) % qq, c60 = (1ull << 60) % qq;
             u64* r = &rc[(size_t)m * 8];
             r[0] = qq; r[1] = 0 - qq; r[2] = P.mu_hi[m]; r[3] = c30; r[4] = nt::shoup(c30, qq); r[5] = c60; r[6] = nt::shoup(c60, qq);

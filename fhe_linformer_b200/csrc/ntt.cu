@@ -85,7 +85,10 @@ __device__ __forceinline__ void gs_block(u64* e, const ulonglong2* t, u64 nq, u6
 template <bool WIDE>
 __device__ __forceinline__ u64 final_reduce(u64 v, u64 q, u64 q4, u64 nq, u64 qinv64) {
     if (WIDE) return csub(csub(csub(v, q4), q4 >> 1), q);   // v < 8q
-    return csub(v + __umul64hi(v, qinv64) * nq, q);          // v < 65q: one Barrett step with floor(2^64/q)
+    // v < 69q < 2^63: the quotient from the top words only, k = hi32((v >> 32) floor(2^64/q)) (floor(2^64/q) < 2^32 as q > 2^33),
+    // is floor(v/q) or one less (dropping the low word of v loses < 2^-19, the floor of the reciprocal < 0.25)
+    const u32 k = (u32)(((u64)(u32)(v >> 32) * (u32)qinv64) >> 32);
+    return csub(v + (u64)k * nq, q);
 }
 
 // ---------------- column pass (register radix-16) ----------------
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256, 3) ntt_column_kernel(u64* __restrict__ da
     if (FWD) {
         if (is_wide(q)) ct_block<kRadix1Log, true>(e, stw, nq, q4); else ct_block<kRadix1Log, false>(e, stw, nq, q4);
 #pragma unroll
-        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 8q (wide) or < 20q (narrow)
+        for (int k = 0; k < R1; ++k) a[(size_t)k * cols] = e[k];   // lazy: < 8q (wide) or < 21q (narrow)
     } else {
         gs_block<kRadix1Log>(e, stw, nq, q4);
         const u64 w = post ? post[m] : T.ninv[m], ws = post ? post_sh[m] : T.ninv_sh[m];
