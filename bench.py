@@ -224,6 +224,28 @@ def run_b200(a):
     e.sync()
     ntt_ms = n0.elapsed_time(n1) / (reps * B)
     ntt_bytes = 16 * N * 2 * l
+    # the other primitive rates of BASELINE.json's metric (ii): INTT and EvalMult + relinearisation, same buffers / chain
+    n0.record(stream)
+    for _ in range(reps):
+        for sbuf in scratch:
+            e.ntt_batch(sbuf, midx2, inverse=True)
+    n1.record(stream)
+    e.sync()
+    intt_ms = n0.elapsed_time(n1) / (reps * B)
+    ma, mb = e.to_dev(host_batch[0]), e.to_dev(host_batch[1 % B])
+    mo = e.buf(ma.shape)
+    e.mul_relin(ma, mb, evks[0], out=mo)
+    e.sync()
+    n0.record(stream)
+    for _ in range(4 * reps):
+        e.mul_relin(ma, mb, evks[0], out=mo)
+    n1.record(stream)
+    e.sync()
+    mul_ms = n0.elapsed_time(n1) / (4 * reps)
+    beta_l = (l + e.alpha - 1) // e.alpha
+    mul_bytes = (6 * l + 2 * beta_l * (l + e.K)) * 8 * N
+    for x in (ma, mb, mo):
+        x.free()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -298,6 +320,11 @@ def run_b200(a):
                          "algorithmic_bytes_per_launch": ntt_bytes * G, "avg_launch_ms": ntt_ms * G,
                          "units_per_launch": f"{G} ciphertexts x {2 * l} limbs (16 N bytes per limb)"},
             "rotate_roofline": {"algorithmic_bytes_per_rotation": rot_bytes, "achieved": rot_gbs, "unit": "GB/s", "frac": rot_gbs / peak},
+            "primitives": {"ring": f"N=2^{a.logN}, l={l}", "ntt_polys_per_s": 2.0 / (ntt_ms * 1e-3), "intt_polys_per_s": 2.0 / (intt_ms * 1e-3),
+                           "ntt_limbs_per_s": 2.0 * l / (ntt_ms * 1e-3), "intt_GBps": ntt_bytes / (intt_ms * 1e-3) / 1e9,
+                           "mul_relin_per_s": 1e3 / mul_ms, "mul_relin_GBps": mul_bytes / (mul_ms * 1e-3) / 1e9,
+                           "mul_relin_roofline_frac": mul_bytes / (mul_ms * 1e-3) / 1e9 / peak,
+                           "note": "per GPU; NTT / INTT batched (8 ciphertexts per launch pair), EvalMult+relin one ciphertext pair per call"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 2 * l * N * 8, "d2h_bytes_per_step": B * 2 * l * N * 8,
                     "steps": e2e_steps, "matches_device_path": ok},
             "gpu_launches": launches_per_group * len(ins) * a.steps,
