@@ -276,17 +276,38 @@ def run_b200(a):
         h_in[i][...] = host_batch[i * G:(i + 1) * G]
     e2e_steps = max(2, min(a.steps, 5))
     e.host_rotate_batch(h_in[0], g, evks[0], out=h_out[0])
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        for i in range(ngroups):
-            e.host_rotate_batch(h_in[i], g, evks[i % nkeys], out=h_out[i], wait=False)   # calls overlap; one wait at the end of the timed region
+    e.host_rotate_batch(h_in[0], g, evks[0], out=h_out[0], wait=False)    # warm-up of the overlapped form (its batch shapes, both staging slots)
     e.sync()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / float(te.item())
+    e2e_runs = []
+    for _rep in range(3):     # the PCIe path is shared with the other tenants of the host: three timed regions, the median is reported
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for i in range(ngroups):
+                e.host_rotate_batch(h_in[i], g, evks[i % nkeys], out=h_out[i], wait=False)   # calls overlap; one wait at the end of the timed region
+        e.sync()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_runs.append(world * B * e2e_steps / float(te.item()))
+    e2e_val = sorted(e2e_runs)[1]
+    # what the link gives at that moment: the same pinned buffers copied both ways at once, no kernels
+    cp0, cp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    d_t = torch.empty(tuple(ins[0].shape), dtype=torch.int64, device="cuda")
+    d_t2 = torch.empty_like(d_t)
+    torch.cuda.synchronize()
+    tp = time.perf_counter()
+    for _ in range(4):
+        with torch.cuda.stream(s_up):
+            d_t.copy_(pin_in[0], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            pin_out[1 % ngroups].copy_(d_t2, non_blocking=True)
+    torch.cuda.synchronize()
+    pcie_gbs = 4 * d_t.numel() * 8 / (time.perf_counter() - tp) / 1e9
+    del d_t, d_t2
+    e.host_rotate_batch(h_in[0], g, evks[0], out=h_out[0])               # h_out[0] again holds the result checked below
     ok = bool((h_out[0] == outs[0].download()).all())      # e2e result equals the device-resident result
 
     cpu = None
@@ -326,7 +347,10 @@ def run_b200(a):
                            "mul_relin_roofline_frac": mul_bytes / (mul_ms * 1e-3) / 1e9 / peak,
                            "note": "per GPU; NTT / INTT batched (8 ciphertexts per launch pair), EvalMult+relin one ciphertext pair per call"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": B * 2 * l * N * 8, "d2h_bytes_per_step": B * 2 * l * N * 8,
-                    "steps": e2e_steps, "matches_device_path": ok},
+                    "steps": e2e_steps, "matches_device_path": ok, "timed_regions_rot_per_s": [round(x, 1) for x in e2e_runs],
+                    "GBps_each_way": e2e_val / world * 2 * l * N * 8 / 1e9, "pcie_duplex_probe_GBps_each_way": pcie_gbs,
+                    "note": "overlapped fl_host_rotate_batch_async calls + one fl_sync per timed region; median of three regions; "
+                            "bound by the host link (probe = plain pinned copies both ways at once, measured right after)"},
             "gpu_launches": launches_per_group * len(ins) * a.steps,
             "clocks": clocks,
         }
