@@ -24,6 +24,24 @@ METRIC = "EvalRotate throughput, N=2^16, full chain (L=28 Q limbs + 7 P limbs, d
 UNIT = "rotations/s"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: everything else this process (or NCCL, or the controller's progress messages)
+    writes to fd 1 is sent to stderr; emit() writes the line to the original stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,7 +155,7 @@ def run_reference(a):
                                    "OpenFHE-equivalent CPU restatement, not OpenFHE"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(a):
@@ -358,7 +376,7 @@ def run_b200(a):
             line["cpu_baseline"] = cpu
         if fwd:
             line["forward"] = fwd
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -453,6 +471,7 @@ def run_forward(a, local, rank, world, torch, dist):
 
 def main():
     a = parse()
+    claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
