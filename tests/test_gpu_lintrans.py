@@ -52,6 +52,15 @@ def test_dense_band(ctx):
     assert s["diagonals"] == 21 and s["n1"] * s["n2"] >= 21 and s["stride"] == 1
 
 
+def test_wide_band_sixteen_baby_steps(ctx):
+    """More than 64 diagonal positions: 16 baby steps (the 16-wide instantiation of the inner kernel) and 6 giant steps."""
+    n = ctx.N // 2
+    rng = np.random.default_rng(5)
+    diags = {d: rng.uniform(-1, 1, n) for d in range(-40, 50) if d % 7}
+    lt = run(ctx, diags, n, level=1)
+    assert lt.shape["n1"] == 16 and lt.shape["n2"] == 6
+
+
 def test_strided_sparse_diagonals_and_levels(ctx):
     n = ctx.N // 2
     rng = np.random.default_rng(2)
