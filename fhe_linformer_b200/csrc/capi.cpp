@@ -261,6 +261,11 @@ int fl_mul_many(fl_ctx* c, fl_ct* const* v, int n, fl_ct** out) {
 int fl_linear_wsum(fl_ctx* c, const fl_ct* in, const double* w, int n_out, fl_ct** out) { FL_TRY(*out = wrap(c->sch->linear_wsum(in->e, w, n_out))) }
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotate(a->e, k))) }
 int fl_has_rot_key(fl_ctx* c, int k) { return c->sch->has_rotation_key(k) ? 1 : 0; }
+int fl_rotsum_rotations(int steps, int stride, int* out, int cap) {
+    const std::vector<int> r = Scheme::ladder_rotations(steps, stride);
+    for (int i = 0; i < (int)r.size() && i < cap; ++i) out[i] = r[i];
+    return (int)r.size();
+}
 int fl_rotsum(fl_ctx* c, const fl_ct* a, int steps, int stride, fl_ct** out) { FL_TRY(*out = wrap(c->sch->rotsum(a->e, steps, stride))) }
 int fl_bootstrap_iter(fl_ctx* c, const fl_ct* a, int iterations, int precision, fl_ct** out) {
     FL_TRY(*out = wrap(c->sch->bootstrap_iter(a->e, iterations, precision)))

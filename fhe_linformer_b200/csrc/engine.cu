@@ -363,11 +363,12 @@ void Engine::ks_moddown_part(u64* out, u64* tq, const u64* acc, int l, int first
 // Bossuat et al.).  Used by the rotate-and-add ladders (two doubling steps = three rotations of one operand).
 void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self) {
     if (B <= 0) return;
+    if (nk < 1 || nk > kHoistMax) throw std::invalid_argument("hoisted rotation sum: 1..15 rotations per call");
     const KsLevel& ks = ks_level(l);
     const int N = P.N, K = P.K, ext = l + K, beta = ks.beta;
     const size_t cs = (size_t)2 * l * N, dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N, acc_bs = (size_t)2 * ext * N, tq_bs = cs;
     const u64* c1 = ct + (size_t)l * N;
-    const uint32_t* maps[8];
+    const uint32_t* maps[kHoistMax];
     for (int k = 0; k < nk; ++k) maps[k] = automorph_map(gs[k]);
     u64* dco = alloc(dco_bs * B);
     if (B == 1) copy(dco, c1, dco_bs);

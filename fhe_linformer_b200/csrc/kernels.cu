@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict
 // (gather at map_k[j]), so a single ModDown finishes all of them.  Per key the digit products accumulate carry-free and
 // are reduced once; the nk reduced values add up modulo q.
 struct MultiKeys {
-    const u64* evk[8];
-    const uint32_t* map[8];
+    const u64* evk[kHoistMax];
+    const uint32_t* map[kHoistMax];
     int n;
 };
 template <int BETA, int KPR_MAX>
@@ -549,7 +549,7 @@ void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const
 }
 void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
                                 const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s) {
-    if (nk < 1 || nk > 8) throw std::invalid_argument("hoisted rotation sum: 1..8 rotations per call");
+    if (nk < 1 || nk > kHoistMax) throw std::invalid_argument("hoisted rotation sum: 1..15 rotations per call");
     MultiKeys mk{};
     mk.n = nk;
     for (int k = 0; k < nk; ++k) { mk.evk[k] = evks[k]; mk.map[k] = maps[k]; }

@@ -59,7 +59,7 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
 // acc[b][{0,1}][t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[b][t] inside digit d else up[b][d][t]
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
-// hoisted multi-rotation: acc[b][{0,1}][t][j] = sum_k (sum_d U_d[b][t] evk_k[d][mod(t)])[map_k[j]], nk <= 8 keys with their gather maps
+// hoisted multi-rotation: acc[b][{0,1}][t][j] = sum_k (sum_d U_d[b][t] evk_k[d][mod(t)])[map_k[j]], nk <= kHoistMax keys with their gather maps
 void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
                                 const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
 // s0[b][i][j] = (self ? c0[b][i][j] : 0) + sum_k c0[b][i][map_k[j]]
@@ -70,6 +70,8 @@ void launch_gather_sum(const DevTables& t, u64* s0, const u64* c0, const uint32_
 void launch_moddown_conv(const DevTables& t, const MdConst& md, u64* tq, const u64* pcoef, size_t pstride, int l, int polys, int batch,
                          size_t tq_bs, size_t p_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
 // out[b][p][i][j] = ((acc[b][p][i] - tq[b][p][i]) * P^-1 + add_p[b][i])[map ? map[j] : j] + (plus ? plus[b][p][i][j] : 0)
+constexpr int kHoistMax = 15;   // rotations sharing one ModUp / ModDown in a hoisted rotate-and-sum (four doubling steps)
+
 // BSGS linear transform (engine.cu: Engine::linear_transform)
 constexpr int kBsgsMax = 16;
 struct BsgsArgs {

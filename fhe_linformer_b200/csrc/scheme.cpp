@@ -724,6 +724,39 @@ Elem Scheme::rotate(const Elem& a, int k) {
 }
 Elem Scheme::conjugate(const Elem& a) { return apply_galois(a, P.galois_conj()); }
 
+// How many doubling steps each hoisted key switch of a ladder takes.  A group of g steps costs one ModUp + ModDown (measured
+// ~ 12 evaluation-key products, scripts/prof_rotsum.py) plus 2^g - 1 key products, so the cheapest partition of `steps` is
+// found by dynamic programming over group sizes 1 .. 4 (15 rotations); smaller groups first.  FLK_HOIST_GMAX overrides the cap.
+std::vector<int> Scheme::ladder_plan(int steps) {
+    static const int gmax = [] { const char* e = std::getenv("FLK_HOIST_GMAX"); return e ? std::max(1, std::min(4, std::atoi(e))) : 4; }();
+    const long C = 12;
+    std::vector<long> best(steps + 1, 0);
+    std::vector<int> pick(steps + 1, 0);
+    for (int s = 1; s <= steps; ++s) {
+        best[s] = -1;
+        for (int g = 1; g <= std::min(gmax, s); ++g) {
+            const long c = best[s - g] + C + ((1L << g) - 1);
+            if (best[s] < 0 || c < best[s]) { best[s] = c; pick[s] = g; }
+        }
+    }
+    std::vector<int> groups;
+    for (int s = steps; s > 0; s -= pick[s]) groups.push_back(pick[s]);
+    std::sort(groups.begin(), groups.end());
+    return groups;
+}
+// rotation amounts a ladder uses with that plan (the doubling keys stride 2^i first)
+std::vector<int> Scheme::ladder_rotations(int steps, int stride) {
+    std::vector<int> r;
+    for (int i = 0; i < steps; ++i) r.push_back(stride * (1 << i));
+    int i = 0;
+    for (int g : ladder_plan(steps)) {
+        for (int t = 3; t < (1 << g); ++t)
+            if (t & (t - 1)) r.push_back(t * stride * (1 << i));
+        i += g;
+    }
+    return r;
+}
+
 // r <- r + rot(r, stride 2^i), i = 0 .. steps-1: the rotate-and-add ladders of FHEController::rotsum / repeat
 // (F.cpp:829-867) as one call; the running ciphertext never leaves the device.
 Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
@@ -734,11 +767,16 @@ Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
         auto it = gk_.find(P.galois_for_rotation(k));
         return it == gk_.end() ? nullptr : it->second;
     };
+    const std::vector<int> plan = ladder_plan(steps);
+    size_t pi = 0;
+    int planned_left = 0;
     for (int i = 0; i < steps;) {
         const int k = stride * (1 << i);
         if (!key_of(k)) throw std::runtime_error("rotsum: no evaluation key for rotation " + std::to_string(k));
         // g doubling steps at once: r + sum_{t = 1 .. 2^g - 1} rot(r, t k), all rotations hoisted on one ModUp / one ModDown.
-        // Pairs (three rotations) are the sweet spot; an odd tail is taken as a triple (seven rotations) instead of 2 + 1.
+        // The group sizes come from ladder_plan(); a group whose extra keys (t k, t not a power of two) are missing is
+        // taken in smaller groups.
+        if (planned_left == 0 && pi < plan.size()) planned_left = plan[pi++];
         int g = 1;
         if (!no_hoist) {
             auto have = [&](int gg) {
@@ -746,13 +784,13 @@ Elem Scheme::rotsum(const Elem& a, int steps, int stride) {
                     if (!key_of(t * k)) return false;
                 return true;
             };
-            const int left = steps - i;
-            if (left == 3 && have(3)) g = 3;
-            else if (left >= 2 && have(2)) g = 2;
+            g = std::max(1, std::min(planned_left, steps - i));
+            while (g > 1 && !have(g)) --g;
         }
+        planned_left = std::max(0, planned_left - g);
         const int nk = (1 << g) - 1;
-        uint32_t gs[8];
-        const u64* evks[8];
+        uint32_t gs[kHoistMax];
+        const u64* evks[kHoistMax];
         for (int t = 1; t <= nk; ++t) { gs[t - 1] = P.galois_for_rotation(t * k); evks[t - 1] = key_of(t * k); }
         Elem nx = make(2, r.l, r.deg, r.scale, r.slots, r.batch);
         for (int b0 = 0, mb = max_batch(r.l); b0 < r.batch; b0 += mb) {

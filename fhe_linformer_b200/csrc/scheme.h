@@ -114,6 +114,8 @@ public:
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);
     Elem rotsum(const Elem& a, int steps, int stride);   // FHEController::rotsum / repeat ladders F.cpp:829-867
+    static std::vector<int> ladder_plan(int steps);                   // doubling steps per hoisted key switch
+    static std::vector<int> ladder_rotations(int steps, int stride);  // rotation keys rotsum(steps, stride) uses with that plan
     // BSGS diagonal linear transforms (EvalLinearTransform of CoeffsToSlots / SlotsToCoeffs; packed ct x pt matrix products)
     LinTrans lintrans_plan(const std::map<int, std::vector<cplx>>& diags, int slots, int max_baby = 0);
     std::vector<int> lintrans_rotations(const LinTrans& t) const;

@@ -430,21 +430,14 @@ void FHEController::print_min_max(const Ctxt& c) {
 Ctxt FHEController::ladder(const Ctxt& in, int slots, int stride) {
     int steps = 0;
     while ((1 << steps) < slots) ++steps;
-    for (int i = 0; i < steps; ++i) {
-        int k = stride * (1 << i);
+    // the doubling keys, plus (hoist_ladders) the extra multiples the engine's hoisted groups use -- up to four doubling steps
+    // share one ModUp / ModDown (r + rot(r,k) + ... + rot(r,15k)); generated on first use
+    int rots[64];
+    const int nr = fl_rotsum_rotations(steps, stride, rots, 64);
+    for (int i = 0; i < nr && i < 64; ++i) {
+        if (i >= steps && !hoist_ladders) break;
+        int k = rots[i];
         if (!fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
-    }
-    // the engine takes two doubling steps per hoisted key switch (r + rot(r,k) + rot(r,2k) + rot(r,3k)) when the 3k key exists,
-    // and an odd tail of three steps as one (rotations k .. 7k): generate those extra keys on first use
-    if (hoist_ladders) {
-        for (int i = 0; i < steps;) {
-            const int k = stride * (1 << i), g = steps - i == 3 ? 3 : (steps - i >= 2 ? 2 : 1);
-            for (int t = 3; t < (1 << g); ++t) {
-                int kt = t * k;
-                if (!fl_has_rot_key(ctx_, kt)) need(fl_gen_rot_keys(ctx_, &kt, 1), "EvalRotateKeyGen");
-            }
-            i += g;
-        }
     }
     fl_elem* e = nullptr;
     need(fl_rotsum(ctx_, in->handle(), steps, stride, &e), "EvalRotate ladder");

@@ -141,6 +141,10 @@ int fl_linear_wsum(fl_ctx* c, const fl_ct* in, const double* w, int n_out, fl_ct
 int fl_rotate(fl_ctx* c, const fl_ct* a, int k, fl_ct** out);                   /* EvalRotate F.cpp:435,833,843 */
 int fl_has_rot_key(fl_ctx* c, int k);                                           /* is the EvalRotateKeyGen key for index k resident? */
 /* out = sum_{t < 2^steps} rot(a, t * stride): FHEController::rotsum / rotsum_padded / repeat, F.cpp:829-867 */
+/* rotation amounts fl_rotsum(steps, stride) uses when all of them have keys: the doubling steps stride * 2^i plus the extra
+ * multiples of its hoisted groups (up to four doubling steps = 15 rotations share one ModUp / ModDown); returns their count.
+ * Missing extra keys only make the ladder fall back to smaller groups. */
+int fl_rotsum_rotations(int steps, int stride, int* out, int cap);
 int fl_rotsum(fl_ctx* c, const fl_ct* a, int steps, int stride, fl_ct** out);
 int fl_conjugate(fl_ctx* c, const fl_ct* a, fl_ct** out);
 int fl_rescale(fl_ctx* c, const fl_ct* a, fl_ct** out);

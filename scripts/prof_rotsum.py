@@ -9,14 +9,15 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 c = CKKS(logN=15, L=28, dnum=4)
 c.keygen(3)
-keys = [t * k for k in (128, 512) for t in (1, 2, 3)] + [t * 2048 for t in range(1, 8)]
-c.gen_rot_keys(keys)
+import ctypes as C
+rots = (C.c_int * 64)()
+nr = c.lib.fl_rotsum_rotations(7, 128, rots, 64)          # doubling keys + the extra multiples of the hoisted groups
+c.gen_rot_keys([int(rots[i]) for i in range(nr)])
 n = c.N // 2
 rng = np.random.default_rng(0)
 vs = [rng.uniform(-1, 1, n) for _ in range(B)]
 b = c.pack([c.encrypt(v, level=level) for v in vs])
 rotsum = lambda x: c._out(c.lib.fl_rotsum, x.h, 7, 128)
-import ctypes as C
 c.lib.fl_rotsum.restype = C.c_int
 c.lib.fl_rotsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 r = rotsum(b); c.sync()
