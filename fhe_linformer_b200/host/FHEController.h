@@ -152,7 +152,7 @@ public:
     int device = 0;                               // CUDA device of this controller: one context per GPU
     unsigned long long key_seed = 20261018ULL;    // all key / encryption randomness derives from it
     bool batch_rows = true;                       // independent rows share kernel launches (FHEController.cpp "row batching")
-    bool hoist_ladders = true;                    // extra 3 * stride * 4^i keys: ladders take two doubling steps per key switch
+    bool hoist_ladders = true;                    // extra rotation keys (fl_rotsum_rotations): ladders take up to four doubling steps per hoisted key switch
     int max_rows_per_batch = 64;                  // same speed as 256 (1.698 vs 1.693 s at S = 256) with 50 GB instead of 85 GB cached
     fl_ctx* native() const { return ctx_; }
     Ctxt adopt(fl_elem* e) const;                 // take ownership of a raw C-ABI handle
