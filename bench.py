@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=20, help="rotations timed on the host for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the encrypted Linformer forward (extra `forward` key)")
+    ap.add_argument("--forward-in-flight", type=int, default=2, help="forwards in flight per GPU for the extra throughput-mode figure (1 = skip)")
     ap.add_argument("--forward-rows", type=int, default=129, help="S = rows of the forward sample (129..256)")
     ap.add_argument("--no-forward-n16", action="store_true", help="skip the extra forward at the reference's commented-out ring N=2^16")
     ap.add_argument("--forward-logn", type=int, default=15, help="ring of the forward: 15 = the reference's parameters, 16 = its commented-out variant (sparse packing)")
@@ -413,6 +414,8 @@ def run_forward(a, local, rank, world, torch, dist):
     evaluates its own synthetic sample (sample-parallel, no collective); samples/s = ranks / max-over-ranks seconds."""
     import tempfile
     from fhe_linformer_b200 import host, synth
+    if a.forward_in_flight > 1:
+        os.environ.setdefault("FLK_CACHE_GB", str(max(16, 120 // a.forward_in_flight)))    # block cache cap per controller (default 96 GB)
     root = tempfile.mkdtemp(prefix="flb200_bench_%d_" % rank)
     model = synth.make_model(n_classes=8)
     sample = synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 1 + rank)
@@ -440,6 +443,30 @@ def run_forward(a, local, rank, world, torch, dist):
             fc.forward(dirs, dead_work=False)
             lean_runs.append(time.perf_counter() - t1)
         lean = sorted(lean_runs)[1]
+        conc = None
+        if a.forward_in_flight > 1:
+            # throughput mode for batches of samples (BASELINE config 5): several forwards in flight on one GPU, one controller
+            # (engine + stream + keys) per host thread; the kernels of one fill the gaps the small-batch stages of another leave
+            import threading
+            ctl = [(fc, dirs)]
+            for t in range(1, a.forward_in_flight):
+                root_t = tempfile.mkdtemp(prefix="flb200_bench_%d_%d_" % (rank, t))
+                dirs_t = synth.write_files(root_t, model, synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 101 * t + rank))
+                fc_t = host.FHEController(device=local, root=root_t).generate()
+                fc_t.forward(dirs_t, dead_work=True)
+                ctl.append((fc_t, dirs_t))
+            reps_c = 3
+            def work(c, d):
+                for _ in range(reps_c):
+                    c.forward(d, dead_work=True)
+            th = [threading.Thread(target=work, args=cd) for cd in ctl]
+            tc = time.perf_counter()
+            for x in th: x.start()
+            for x in th: x.join()
+            conc_dt = time.perf_counter() - tc
+            conc = {"in_flight": a.forward_in_flight, "samples": a.forward_in_flight * reps_c, "seconds": conc_dt}
+            for c, _d in ctl[1:]:
+                c.close()
         fc.close()
         n16 = None
         if a.forward_logn == 15 and not a.no_forward_n16:
@@ -454,17 +481,21 @@ def run_forward(a, local, rank, world, torch, dist):
     finally:
         os.dup2(saved, 1)
         os.close(devnull); os.close(saved)
-    t = torch.tensor([dt, lean], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dt, lean, conc["seconds"] if conc else 0.0], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt, lean = float(t[0].item()), float(t[1].item())
+    if conc:
+        conc = {"in_flight_per_gpu": conc["in_flight"], "samples_per_s": world * conc["samples"] / float(t[2].item()),
+                "seconds_per_sample_per_stream": float(t[2].item()) / (conc["samples"] / conc["in_flight"]),
+                "note": "throughput mode: that many forwards in flight per GPU (one controller per host thread); latency per sample rises accordingly"}
     rot = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
     alg = sum(b for _, b in led.values())
     return {"seconds_per_sample": dt, "samples_per_s": world / dt, "rows_S": S, "ring": "N=2^%d, 28 limbs, dnum 4, 2^14 slots" % a.forward_logn,
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
-            "n16": n16, "_ledger": led,
+            "n16": n16, "throughput_mode": conc, "_ledger": led,
             "note": "text files -> encode/encrypt -> encoder1 -> pooler -> classifier -> decrypt, wall clock incl. host encode; "
                     "lean = same logits without the operations main.cpp issues but never reads"}
 
