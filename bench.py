@@ -414,8 +414,6 @@ def run_forward(a, local, rank, world, torch, dist):
     evaluates its own synthetic sample (sample-parallel, no collective); samples/s = ranks / max-over-ranks seconds."""
     import tempfile
     from fhe_linformer_b200 import host, synth
-    if a.forward_in_flight > 1:
-        os.environ.setdefault("FLK_CACHE_GB", str(max(16, 120 // a.forward_in_flight)))    # block cache cap per controller (default 96 GB)
     root = tempfile.mkdtemp(prefix="flb200_bench_%d_" % rank)
     model = synth.make_model(n_classes=8)
     sample = synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 1 + rank)
@@ -448,6 +446,8 @@ def run_forward(a, local, rank, world, torch, dist):
             # throughput mode for batches of samples (BASELINE config 5): several forwards in flight on one GPU, one controller
             # (engine + stream + keys) per host thread; the kernels of one fill the gaps the small-batch stages of another leave
             import threading
+            cap_before = os.environ.get("FLK_CACHE_GB")
+            os.environ["FLK_CACHE_GB"] = str(max(16, 100 // a.forward_in_flight))    # block-cache cap of the extra controllers (default 96 GB each)
             ctl = [(fc, dirs)]
             for t in range(1, a.forward_in_flight):
                 root_t = tempfile.mkdtemp(prefix="flb200_bench_%d_%d_" % (rank, t))
@@ -467,6 +467,10 @@ def run_forward(a, local, rank, world, torch, dist):
             conc = {"in_flight": a.forward_in_flight, "samples": a.forward_in_flight * reps_c, "seconds": conc_dt}
             for c, _d in ctl[1:]:
                 c.close()
+            if cap_before is None:
+                os.environ.pop("FLK_CACHE_GB", None)
+            else:
+                os.environ["FLK_CACHE_GB"] = cap_before
         fc.close()
         n16 = None
         if a.forward_logn == 15 and not a.no_forward_n16:

@@ -114,6 +114,11 @@ Engine::~Engine() {
     if (h2d_stream) cudaStreamDestroy(h2d_stream);
     if (d2h_stream) cudaStreamDestroy(d2h_stream);
     cudaStreamDestroy(stream);
+    // hand the pool's unused reservations back to the driver: the next context on this device (another ring, another controller)
+    // starts from free memory instead of a fragmented pool
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
 }
 
 // Device memory comes from CUDA's stream-ordered pool, fronted by an exact-size cache: a forward pass asks for the same few

@@ -50,6 +50,11 @@ FHEController::~FHEController() {
     // ciphertexts handed out may outlive the controller (main.cpp keeps globals); the context is released at exit
 }
 
+void FHEController::release_context() {
+    mask_cache_.clear();
+    if (ctx_) { fl_ctx_destroy(ctx_); ctx_ = nullptr; }
+}
+
 string FHEController::key_path(const string& name) const {
     const char* root = std::getenv("FHE_LINFORMER_ROOT");   // default: the reference's "../" relative layout
     return string(root ? root : "..") + "/" + parameters_folder + "/" + name;

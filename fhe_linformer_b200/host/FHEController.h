@@ -39,6 +39,9 @@ class FHEController {
 public:
     FHEController() {}
     ~FHEController();
+    // Destroys the context (keys, caches, device memory).  The destructor leaves it alive because ciphertexts handed out may
+    // outlive the controller (main.cpp keeps globals); call this only when none are left.
+    void release_context();
 
     // ---- data members the pipeline reads ------------------------------------------------------------------------------
     int circuit_depth;                       // multiplicative depth chosen at generation (27) / recomputed at load (26)

@@ -55,7 +55,11 @@ flh_controller* flh_new(int device, unsigned long long key_seed) {
     c->fc.key_seed = key_seed;
     return c;
 }
-void flh_free(flh_controller* c) { delete c; }
+void flh_free(flh_controller* c) {
+    if (!c) return;
+    c->fc.release_context();     // the handles this face hands out are device copies owned by the caller's context wrapper: none are left here
+    delete c;
+}
 fl_ctx* flh_native(flh_controller* c) { return c->fc.native(); }
 
 int flh_generate(flh_controller* c, int log_ring, const int* rotations, int n_rot, int bootstrap_slots, int serialize) {
