@@ -45,3 +45,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "ckks_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_ladder_key_plan_without_a_device():
+    """fl_rotsum_rotations is pure host logic: the doubling keys come first, then the extra multiples of the hoisted groups."""
+    import ctypes as C
+    from fhe_linformer_b200 import load_library
+    lib = load_library()
+    lib.fl_rotsum_rotations.restype = C.c_int
+    lib.fl_rotsum_rotations.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int]
+
+    def plan(steps, stride):
+        out = (C.c_int * 64)()
+        n = lib.fl_rotsum_rotations(steps, stride, out, 64)
+        return [out[i] for i in range(n)]
+
+    r = plan(7, 128)                                   # matmulRE's ladder: 3 + 4 doubling steps
+    assert r[:7] == [128 << i for i in range(7)]
+    assert set(r) == {128 * t for t in range(1, 8)} | {1024 * t for t in range(1, 16)}
+    r = plan(6, 1)                                     # matmulCR: 3 + 3
+    assert set(r) == set(range(1, 8)) | {8 * t for t in range(1, 8)}
+    assert plan(1, -128) == [-128] and plan(0, 5) == []
+    r = plan(5, -1)                                    # repeat(., 32): 2 + 3, negative stride
+    assert set(r) == {-1, -2, -3} | {-4 * t for t in range(1, 8)}
