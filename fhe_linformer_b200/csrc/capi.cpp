@@ -25,6 +25,9 @@ struct fl_ctx {
 struct ProfScope {
     fl_ctx* c; ProfRec r; std::chrono::steady_clock::time_point t0;
     ProfScope(fl_ctx* ctx, const char* name) : c(ctx && ctx->prof_on ? ctx : nullptr) {
+        // the current device is per host thread: a caller that drives several contexts (or one context from a worker thread)
+        // lands on the engine's device here, whichever device its thread last used
+        if (ctx && ctx->eng) cudaSetDevice(ctx->eng->device_id);
         if (!c) return;
         r.name = name;
         cudaEventCreate(&r.a); cudaEventCreate(&r.b);

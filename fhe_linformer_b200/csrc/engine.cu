@@ -30,6 +30,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     FLK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int dev = 0;
     FLK_CUDA(cudaGetDevice(&dev));
+    device_id = dev;
     cudaMemPool_t pool;
     FLK_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     uint64_t keep = ~0ull;
@@ -103,6 +104,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
 }
 
 Engine::~Engine() {
+    cudaSetDevice(device_id);
     trim_cache(0);
     cudaStreamSynchronize(stream);
     for (auto& kv : maps_) cudaFree(kv.second);
@@ -155,6 +157,7 @@ void Engine::release(u64* p) {
     if (cached_bytes_ > cache_cap_bytes_) trim_cache(cache_cap_bytes_ / 8 * 7);
 }
 void Engine::trim_cache(size_t keep_bytes) {
+    cudaSetDevice(device_id);   // may run from fl_elem_free on a thread bound to another device
     ++cache_trims;
     for (auto it = free_blocks_.rbegin(); it != free_blocks_.rend() && cached_bytes_ > keep_bytes; ++it)   // largest classes first
         while (!it->second.empty() && cached_bytes_ > keep_bytes) {

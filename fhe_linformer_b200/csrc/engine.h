@@ -51,6 +51,7 @@ public:
     const Params P;
     DevTables T{};
     cudaStream_t stream = nullptr;
+    int device_id = 0;          // the device this engine lives on; every C-ABI entry binds the calling thread to it (capi.cpp)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the host-operand pipeline (created on first use)
     OpLedger ledger;
     bool ledger_on = false;
