@@ -120,3 +120,29 @@ def test_maximum_rows_forward_S256(tmp_path):
     with pytest.raises(RuntimeError, match="129 <= S <= 256"):
         fc.forward(dirs, token_limit=100)           # S = 101: below the two-half packing
     fc.close()
+
+
+def test_two_controllers_in_worker_threads(setup, tmp_path_factory):
+    """Throughput mode (bench.py forward.throughput_mode): a second controller with its own engine / stream / keys, both driven from
+    worker threads at the same time (every C-ABI entry binds the calling thread to its engine's device).  The forwards must not
+    disturb each other: each gives the logits it gives alone (same class, fresh encryption noise only)."""
+    import threading
+    from fhe_linformer_b200 import host
+    fc, model, sample, dirs, _ = setup
+    alone = fc.__dict__.get("_faithful_logits")
+    if alone is None:
+        alone, _, _ = fc.forward(dirs, dead_work=True)
+    other = host.FHEController(root=str(tmp_path_factory.mktemp("linformer2"))).generate()
+    try:
+        out = {}
+        def work(name, c):
+            out[name] = c.forward(dirs, dead_work=True)[0]
+        th = [threading.Thread(target=work, args=("a", fc)), threading.Thread(target=work, args=("b", other))]
+        for t in th: t.start()
+        for t in th: t.join()
+        assert set(out) == {"a", "b"}
+        for name in out:
+            assert np.abs(out[name] - alone).max() < 1e-4, name
+            assert int(np.argmax(out[name])) == int(np.argmax(alone))
+    finally:
+        other.close()
