@@ -29,6 +29,10 @@ def matvec(diags, v):
 def run(c, diags, n, level=0, batch=1, max_baby=0, tol=2e-6):
     rng = np.random.default_rng(len(diags) * 7 + n)
     lt = c.linear_transform(diags, slots=n, level=level, max_baby=max_baby)
+    from oracle import bsgs
+    pl = bsgs.plan(diags, n, max_baby)                  # the engine plans the same split as the restatement
+    assert lt.shape == {"n1": pl["n1"], "n2": pl["n2"], "stride": pl["g"], "diagonals": pl["ndiag"]}
+    assert sorted(lt.rotations()) == pl["rotations"]
     c.gen_rot_keys(lt.rotations())
     vs = [rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n) for _ in range(batch)]
     cts = [c.encrypt(v, level=level, slots=n) for v in vs]
