@@ -11,7 +11,7 @@ vp, ci, u32, u64, dbl = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_double
 CHEB_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 _SIGS = {
-    "fl_keygen": (ci, [vp, u64]), "fl_gen_mult_key": (ci, [vp]), "fl_gen_rot_keys": (ci, [vp, vp, ci]), "fl_gen_conj_key": (ci, [vp]),
+    "fl_keygen": (ci, [vp, u64]), "fl_keygen_seeded": (ci, [vp, u64]), "fl_gen_mult_key": (ci, [vp]), "fl_gen_rot_keys": (ci, [vp, vp, ci]), "fl_gen_conj_key": (ci, [vp]),
     "fl_keys_clear": (ci, [vp, ci]), "fl_num_rot_keys": (ci, [vp]),
     "fl_export_sk": (ci, [vp, vp]), "fl_export_pk": (ci, [vp, vp]), "fl_export_evk": (ci, [vp, u32, vp]),
     "fl_import_keys": (ci, [vp, vp, vp]), "fl_import_evk": (ci, [vp, u32, vp]),
@@ -22,7 +22,7 @@ _SIGS = {
     "fl_add": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_sub": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_mul": (ci, [vp, vp, vp, C.POINTER(vp)]),
     "fl_add_many": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_mul_many": (ci, [vp, vp, ci, C.POINTER(vp)]),
     "fl_add_const": (ci, [vp, vp, dbl, C.POINTER(vp)]), "fl_mul_const": (ci, [vp, vp, dbl, C.POINTER(vp)]),
-    "fl_rotate": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_conjugate": (ci, [vp, vp, C.POINTER(vp)]), "fl_rescale": (ci, [vp, vp, C.POINTER(vp)]),
+    "fl_rotate": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_rotsum": (ci, [vp, vp, ci, ci, C.POINTER(vp)]), "fl_conjugate": (ci, [vp, vp, C.POINTER(vp)]), "fl_rescale": (ci, [vp, vp, C.POINTER(vp)]),
     "fl_eval_poly": (ci, [vp, vp, vp, ci, C.POINTER(vp)]),
     "fl_eval_chebyshev": (ci, [vp, vp, vp, ci, dbl, dbl, C.POINTER(vp)]),
     "fl_chebyshev_coefficients": (ci, [CHEB_FN, vp, dbl, dbl, ci, vp]),
@@ -113,7 +113,9 @@ class CKKS(Engine):
         return Elem(self, h)
 
     # keys
-    def keygen(self, seed=1): self._ck(self.lib.fl_keygen(self.h, seed))
+    def keygen(self, seed=0):
+        """seed 0: operating-system randomness (ChaCha20); any other value: reproducible TEST keys (fl_keygen_seeded)."""
+        self._ck(self.lib.fl_keygen_seeded(self.h, seed) if seed else self.lib.fl_keygen(self.h, 0))
     def gen_mult_key(self): self._ck(self.lib.fl_gen_mult_key(self.h))
     def gen_rot_keys(self, idx):
         a = np.ascontiguousarray(idx, np.int32); self._ck(self.lib.fl_gen_rot_keys(self.h, _ptr(a), len(a)))
@@ -174,6 +176,9 @@ class CKKS(Engine):
     def pack(self, v): return self._many(self.lib.fl_batch_pack, v)                 # ciphertexts of equal level / scale as one batched operand
     def unpack(self, b): return [self._out(self.lib.fl_batch_slice, b.h, i) for i in range(self.lib.fl_elem_batch(b.h))]
     def rotate(self, a, k): return self._out(self.lib.fl_rotate, a.h, int(k))
+    def rotsum(self, a, steps, stride):
+        """r <- r + rot(r, stride 2^i), i < steps (FHEController::rotsum / repeat); hoisted groups only where their extra keys exist."""
+        return self._out(self.lib.fl_rotsum, a.h, int(steps), int(stride))
     def conjugate(self, a): return self._out(self.lib.fl_conjugate, a.h)
     def rescale(self, a): return self._out(self.lib.fl_rescale, a.h)
     def clone(self, a): return self._out(self.lib.fl_elem_clone, a.h)

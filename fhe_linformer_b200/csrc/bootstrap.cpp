@@ -234,7 +234,7 @@ Elem Scheme::bootstrap(const Elem& in) {
     {
         u64* x = eng.alloc((size_t)2 * N * B);
         eng.copy(x, ct.data(), (size_t)2 * N * B);
-        LimbSel s0; s0.n = 1; s0.m[0] = 0; s0.pos[0] = 0;
+        LimbSel s0; s0.push(0, 0);
         eng.intt(x, s0, 2 * B, (size_t)N);
         launch_mod_switch(eng.T, raised.data(), x, 0, sel_range(0, L), 2 * B, eng.stream);
         eng.ntt(raised.data(), sel_range(0, L), 2 * B, (size_t)L * N);

@@ -79,8 +79,8 @@ static inline fl_ctx* prof_ctx(const void*) { return nullptr; }   // entry point
 
 static LimbSel make_sel(const int* midx, int nl) {
     if (nl < 0 || nl > kMaxLimbSel) throw std::invalid_argument("limb count out of range");
-    LimbSel s; s.n = nl;
-    for (int i = 0; i < nl; ++i) { s.m[i] = (uint8_t)midx[i]; s.pos[i] = (uint8_t)i; }
+    LimbSel s;
+    for (int i = 0; i < nl; ++i) s.push(midx[i], i);
     return s;
 }
 
@@ -218,11 +218,15 @@ int fl_host_mul_relin(fl_ctx* c, uint64_t* out_host, const uint64_t* a_host, con
 static fl_elem* wrap(Elem&& e) { return new fl_elem{std::move(e)}; }
 
 int fl_keygen(fl_ctx* c, uint64_t seed) { FL_TRY(c->sch->keygen(seed)) }
+int fl_keygen_seeded(fl_ctx* c, uint64_t seed) {
+    FL_TRY(if (seed == 0) throw std::invalid_argument("fl_keygen_seeded: the seed must be non-zero (0 selects operating-system randomness)"); c->sch->keygen(seed))
+}
 int fl_gen_mult_key(fl_ctx* c) { FL_TRY(c->sch->gen_mult_key()) }
 int fl_gen_rot_keys(fl_ctx* c, const int* idx, int n) { FL_TRY(for (int i = 0; i < n; ++i) c->sch->gen_rotation_key(idx[i])) }
 int fl_gen_conj_key(fl_ctx* c) { FL_TRY(c->sch->gen_galois_key(c->sch->P.galois_conj())) }
 int fl_keys_clear(fl_ctx* c, int kind) { FL_TRY(if (kind == 0) c->sch->clear_rotation_keys(); else c->sch->clear_mult_key()) }
 int fl_num_rot_keys(fl_ctx* c) { return (int)c->sch->num_galois_keys(); }
+double fl_rot_key_bytes(fl_ctx* c) { return (double)c->sch->num_galois_keys() * (double)c->sch->eng.evk_words() * 8.0; }
 int fl_export_sk(fl_ctx* c, uint64_t* out) { FL_TRY(c->sch->export_sk(out)) }
 int fl_export_pk(fl_ctx* c, uint64_t* out) { FL_TRY(c->sch->export_pk(out)) }
 int fl_export_evk(fl_ctx* c, uint32_t g, uint64_t* out) { FL_TRY(c->sch->export_evk(g, out)) }

@@ -19,7 +19,7 @@ namespace flk {
                                      __FILE__ + ":" + std::to_string(__LINE__));                   \
     } while (0)
 
-constexpr int kMaxLimbSel = 160;
+constexpr int kMaxLimbSel = 256;   // limbs one launch may address: beta (l + K) - l of a ModUp; checked in LimbSel::push / Engine::ks_level
 constexpr int kRadix1Log = 4;   // stages done by the register-only column pass (strides N/2 .. N/16)
 
 // Passed by value to kernels.
@@ -37,21 +37,29 @@ struct DevTables {
 
 // modulus index of every limb of a buffer (limb-major [n][N])
 struct LimbSel {
-    int n;
-    uint8_t m[kMaxLimbSel];     // modulus index
-    uint8_t pos[kMaxLimbSel];   // limb slot inside the buffer (NTT kernels only; identity elsewhere)
+    int n = 0;
+    uint8_t m[kMaxLimbSel];      // modulus index (a chain holds at most 255 moduli: Params checks L + K)
+    uint16_t pos[kMaxLimbSel];   // limb slot inside the buffer (NTT kernels only; identity elsewhere)
+    // bounds-checked append: a parameter set whose key switch needs more limbs than one launch can address is an error, not a
+    // silent overrun of this by-value struct
+    void push(int mod, int slot) {
+        if (n >= kMaxLimbSel || mod < 0 || mod > 255 || slot < 0 || slot > 65535)
+            throw std::invalid_argument("limb selection overflow: " + std::to_string(n + 1) + " limbs (modulus " + std::to_string(mod) + ", slot " +
+                                        std::to_string(slot) + ") exceed the " + std::to_string(kMaxLimbSel) + "-limb launch descriptor");
+        m[n] = (uint8_t)mod; pos[n] = (uint16_t)slot; ++n;
+    }
 };
 
 inline LimbSel sel_range(int first_mod, int count) {
-    LimbSel s; s.n = count;
-    for (int i = 0; i < count; ++i) { s.m[i] = (uint8_t)(first_mod + i); s.pos[i] = (uint8_t)i; }
+    LimbSel s;
+    for (int i = 0; i < count; ++i) s.push(first_mod + i, i);
     return s;
 }
 // Q limbs 0..l-1 followed by the K P limbs
 inline LimbSel sel_ext(int l, int L, int K) {
-    LimbSel s; s.n = l + K;
-    for (int i = 0; i < l; ++i) { s.m[i] = (uint8_t)i; s.pos[i] = (uint8_t)i; }
-    for (int k = 0; k < K; ++k) { s.m[l + k] = (uint8_t)(L + k); s.pos[l + k] = (uint8_t)(l + k); }
+    LimbSel s;
+    for (int i = 0; i < l; ++i) s.push(i, i);
+    for (int k = 0; k < K; ++k) s.push(L + k, l + k);
     return s;
 }
 

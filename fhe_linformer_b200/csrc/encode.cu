@@ -8,6 +8,7 @@
 //   * scale, round to nearest-even, exact conversion to a 128-bit integer and reduction into every RNS limb;
 //   * ternary / discrete-Gaussian (CDT) / uniform sampling from counter-based SplitMix64 streams: output j of a stream is
 //     mix(seed + (j + 1) * gamma), so every coefficient is generated independently and equals the sequential host stream.
+#include "chacha.cuh"
 #include "kernels.cuh"
 #include "modarith.cuh"
 
@@ -25,22 +26,33 @@ __device__ __forceinline__ u64 splitmix_at(u64 seed, u64 k) {   // k-th output (
     return z ^ (z >> 31);
 }
 
-__constant__ u64 c_gauss_cdt[30];
+__constant__ u64 c_gauss_cdt[30] = FLK_GAUSS_CDT_INIT;   // part of the device image: nothing to upload, nothing to order
+
+__device__ __forceinline__ int ternary_of(u64 r) { const u64 v = r % 3; return v == 2 ? -1 : (int)v; }
+__device__ __forceinline__ int gauss_of(u64 u, u64 sign_bit) {
+    int k = 0;
+    while (k < 29 && u >= c_gauss_cdt[k]) ++k;
+    return sign_bit ? -k : k;
+}
 
 // kind 0: uniform ternary {0, 1, -1};  kind 1: discrete Gaussian by cumulative-distribution table (two outputs per coefficient)
 __global__ void __launch_bounds__(kThreads) sample_limbs_kernel(u64* __restrict__ dst, u64 seed, int kind, DevTables T, LimbSel sel) {
     const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
     if (j >= T.N) return;
-    int v;
-    if (kind == 0) {
-        const u64 r = splitmix_at(seed, (u64)j + 1) % 3;
-        v = r == 2 ? -1 : (int)r;
-    } else {
-        const u64 u = splitmix_at(seed, 2 * (u64)j + 1), sg = splitmix_at(seed, 2 * (u64)j + 2) & 1;
-        int k = 0;
-        while (k < 29 && u >= c_gauss_cdt[k]) ++k;
-        v = sg ? -k : k;
-    }
+    const int v = kind == 0 ? ternary_of(splitmix_at(seed, (u64)j + 1))
+                            : gauss_of(splitmix_at(seed, 2 * (u64)j + 1), splitmix_at(seed, 2 * (u64)j + 2) & 1);
+    const u64 q = T.q[sel.m[limb]];
+    dst[(size_t)sel.pos[limb] * T.N + j] = v >= 0 ? (u64)v : q - (u64)(-v);
+}
+// the same two samplers from ChaCha20 key stream: coefficient j takes block j of stream `nonce` (every limb of the polynomial
+// recomputes the block, so all limbs hold the same small integer)
+__global__ void __launch_bounds__(kThreads) sample_limbs_csprng_kernel(u64* __restrict__ dst, ChaChaKey key, u64 nonce, int kind, DevTables T,
+                                                                       LimbSel sel) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
+    if (j >= T.N) return;
+    uint32_t blk[16];
+    chacha20_block(key, (u64)j, nonce, blk);
+    const int v = kind == 0 ? ternary_of(chacha_u64(blk, 0)) : gauss_of(chacha_u64(blk, 0), chacha_u64(blk, 1) & 1);
     const u64 q = T.q[sel.m[limb]];
     dst[(size_t)sel.pos[limb] * T.N + j] = v >= 0 ? (u64)v : q - (u64)(-v);
 }
@@ -52,6 +64,16 @@ __global__ void __launch_bounds__(kThreads) uniform_limbs_kernel(u64* __restrict
     const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
     if (j >= T.N) return;
     dst[(size_t)sel.pos[limb] * T.N + j] = splitmix_at(seeds.s[limb], (u64)j + 1) % T.q[sel.m[limb]];
+}
+
+// uniform residues from 128 key-stream bits each (bias below 2^-64); limb i is stream nonce + i
+__global__ void __launch_bounds__(kThreads) uniform_limbs_csprng_kernel(u64* __restrict__ dst, ChaChaKey key, u64 nonce, DevTables T, LimbSel sel) {
+    const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
+    if (j >= T.N) return;
+    uint32_t blk[16];
+    chacha20_block(key, (u64)j, nonce + (u64)limb, blk);
+    const int m = sel.m[limb];
+    dst[(size_t)sel.pos[limb] * T.N + j] = barrett128(U128{chacha_u64(blk, 0), chacha_u64(blk, 1)}, T.q[m], T.mu_lo[m], T.mu_hi[m]);
 }
 
 // ---- special inverse FFT: stage `len` pairs (i + j, i + j + len/2) with twiddle zeta^(-5^j) ----
@@ -138,8 +160,6 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 }  // namespace
 
-void upload_gauss_table(const u64* cdt30) { FLK_CUDA(cudaMemcpyToSymbol(c_gauss_cdt, cdt30, 30 * sizeof(u64))); }
-
 void launch_sample_limbs(const DevTables& t, u64* dst, u64 seed, int kind, const LimbSel& sel, cudaStream_t s) {
     sample_limbs_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, seed, kind, t, sel);
     FLK_CUDA(cudaGetLastError());
@@ -148,6 +168,14 @@ void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const 
     SeedSet ss;
     for (int i = 0; i < sel.n; ++i) ss.s[i] = seeds[i];
     uniform_limbs_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, ss, t, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s) {
+    sample_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, key, nonce, kind, t, sel);
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s) {
+    uniform_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, key, nonce, t, sel);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,

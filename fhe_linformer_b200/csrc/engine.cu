@@ -207,6 +207,9 @@ const KsLevel& Engine::ks_level(int l) {
     if (it != ks_.end()) return it->second;
     if (l < 1 || l > P.L) throw std::invalid_argument("key switch: limb count out of range");
     const int beta = P.beta(l), ext = l + P.K, a = P.alpha;
+    if (beta * ext - l > kMaxLimbSel)
+        throw std::invalid_argument("key switch at " + std::to_string(l) + " limbs needs " + std::to_string(beta * ext - l) + " extended limbs per ModUp; one launch addresses " +
+                                    std::to_string(kMaxLimbSel) + " (fewer digits or a shorter chain)");
     std::vector<u64> post(P.T, 0), post_sh(P.T, 0), hm((size_t)beta * a * ext, 0), hm30(hm.size(), 0);
     for (int d = 0; d < beta; ++d) {
         const int lo = d * a, hi = std::min(lo + a, l), ns = hi - lo;
@@ -239,7 +242,7 @@ void Engine::rescale(u64* out, const u64* in, int l, int polys) {
     const int N = P.N;
     u64* xlast = alloc((size_t)polys * N);
     FLK_CUDA(cudaMemcpy2DAsync(xlast, (size_t)N * 8, in + (size_t)(l - 1) * N, (size_t)l * N * 8, (size_t)N * 8, polys, cudaMemcpyDeviceToDevice, stream));
-    LimbSel s1; s1.n = 1; s1.m[0] = (uint8_t)(l - 1); s1.pos[0] = 0;
+    LimbSel s1; s1.push(l - 1, 0);
     launch_intt(T, xlast, s1, polys, (size_t)N, nullptr, nullptr, stream);
     u64* tq = alloc((size_t)polys * (l - 1) * N);
     launch_rescale_conv(T, tq, xlast, l, polys, stream);
@@ -275,12 +278,12 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     // 2. ModUp: basis-extend every digit to the limbs outside it, back to evaluation form
     u64* up = alloc(up_bs * B);
     launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
-    LimbSel su; su.n = 0;
+    LimbSel su;
     for (int d = 0; d < beta; ++d) {
         const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
         for (int t = 0; t < ext; ++t) {
             if (t >= lo && t < hi) continue;
-            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+            su.push(P.mod_index_ext(l, t), d * ext + t);
         }
     }
     ntt_l2(up, su, B, up_bs);
@@ -288,14 +291,14 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     u64* acc = alloc(acc_bs * B);
     launch_inner_product(T, ks, acc, up, io.c, evk, B, acc_bs, up_bs, io.c_bs, stream);
     // 4. ModDown both accumulators
-    LimbSel sp; sp.n = 2 * K;
+    LimbSel sp;
     for (int p = 0; p < 2; ++p)
-        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+        for (int k = 0; k < K; ++k) sp.push(P.L + k, p * ext + l + k);
     launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * B);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
-    LimbSel sq; sq.n = 2 * l;
-    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    LimbSel sq;
+    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
     ntt_l2(tq, sq, B, tq_bs);
     FinishArgs fa{io.out, io.out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, io.add0, io.add0_bs, io.add1, io.add1_bs, io.plus, io.plus_bs};
     launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, B, stream);
@@ -334,12 +337,12 @@ void Engine::ks_modup_part(u64* up, const u64* dco, int l, int first, int count)
     const KsLevel& ks = ks_level(l);
     const int ext = l + P.K;
     launch_modup_conv(T, ks, up, dco, 1, 0, 0, stream, LimbRange{first, count});
-    LimbSel su; su.n = 0;
+    LimbSel su;
     for (int d = 0; d < ks.beta; ++d) {
         const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
         for (int t = first; t < first + count; ++t) {
             if (t >= lo && t < hi) continue;
-            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+            su.push(P.mod_index_ext(l, t), d * ext + t);
         }
     }
     launch_ntt(T, up, su, 1, 0, stream);
@@ -349,17 +352,17 @@ void Engine::ks_inner_part(u64* acc, const u64* up, const u64* c, const u64* evk
 }
 void Engine::ks_pcoef_part(u64* acc, int l, int first, int count) {   // first, count: a range of the K special limbs (0-based inside P)
     const int ext = l + P.K;
-    LimbSel sp; sp.n = 0;
+    LimbSel sp;
     for (int p = 0; p < 2; ++p)
-        for (int k = first; k < first + count; ++k) { sp.m[sp.n] = (uint8_t)(P.L + k); sp.pos[sp.n] = (uint8_t)(p * ext + l + k); sp.n++; }
+        for (int k = first; k < first + count; ++k) sp.push(P.L + k, p * ext + l + k);
     launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
 }
 void Engine::ks_moddown_part(u64* out, u64* tq, const u64* acc, int l, int first, int count, const u64* add0, const u64* add1, uint32_t g) {
     const int N = P.N, ext = l + P.K;
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, 1, 0, 0, stream, LimbRange{first, count});
-    LimbSel sq; sq.n = 0;
+    LimbSel sq;
     for (int p = 0; p < 2; ++p)
-        for (int i = first; i < first + count; ++i) { sq.m[sq.n] = (uint8_t)i; sq.pos[sq.n] = (uint8_t)(p * l + i); sq.n++; }
+        for (int i = first; i < first + count; ++i) sq.push(i, p * l + i);
     launch_ntt(T, tq, sq, 1, 0, stream);
     FinishArgs fa{out, 0, acc, (size_t)ext * N, 0, tq, 0, add0, 0, add1, 0, nullptr, 0};
     launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, 1, stream, LimbRange{first, count});
@@ -384,12 +387,12 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
     launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream);
     u64* up = alloc(up_bs * B);
     launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
-    LimbSel su; su.n = 0;
+    LimbSel su;
     for (int d = 0; d < beta; ++d) {
         const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
         for (int t = 0; t < ext; ++t) {
             if (t >= lo && t < hi) continue;
-            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+            su.push(P.mod_index_ext(l, t), d * ext + t);
         }
     }
     launch_ntt(T, up, su, B, up_bs, stream);
@@ -397,14 +400,14 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
     launch_inner_product_multi(T, ks, acc, up, c1, evks, maps, nk, B, acc_bs, up_bs, cs, stream);
     u64* s0 = alloc(dco_bs * B);
     launch_gather_sum(T, s0, ct, maps, nk, l, B, dco_bs, cs, self, stream);
-    LimbSel sp; sp.n = 2 * K;
+    LimbSel sp;
     for (int p = 0; p < 2; ++p)
-        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+        for (int k = 0; k < K; ++k) sp.push(P.L + k, p * ext + l + k);
     launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * B);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
-    LimbSel sq; sq.n = 2 * l;
-    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    LimbSel sq;
+    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
     launch_ntt(T, tq, sq, B, tq_bs, stream);
     FinishArgs fa{out, cs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, s0, dco_bs, self ? c1 : nullptr, cs, nullptr, 0};
     launch_moddown_finish(T, md_, fa, nullptr, l, 2, B, stream);
@@ -428,12 +431,12 @@ void Engine::modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l) {
     else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, c, c_bs * 8, dco_bs * 8, Bn, cudaMemcpyDeviceToDevice, stream));
     launch_intt(T, dco, sel_range(0, l), Bn, dco_bs, ks.post, ks.post_sh, stream);
     launch_modup_conv(T, ks, up, dco, Bn, up_bs, dco_bs, stream);
-    LimbSel su; su.n = 0;
+    LimbSel su;
     for (int d = 0; d < beta; ++d) {
         const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
         for (int t = 0; t < ext; ++t) {
             if (t >= lo && t < hi) continue;
-            su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(d * ext + t); su.n++;
+            su.push(P.mod_index_ext(l, t), d * ext + t);
         }
     }
     launch_ntt(T, up, su, Bn, up_bs, stream);
@@ -444,14 +447,14 @@ void Engine::moddown_acc(u64* out, size_t out_bs, u64* acc, int Bn, int l, const
                          const u64* plus, size_t plus_bs, uint32_t g) {
     const int N = P.N, K = P.K, ext = l + K;
     const size_t acc_bs = (size_t)2 * ext * N, tq_bs = (size_t)2 * l * N;
-    LimbSel sp; sp.n = 2 * K;
+    LimbSel sp;
     for (int p = 0; p < 2; ++p)
-        for (int k = 0; k < K; ++k) { sp.m[p * K + k] = (uint8_t)(P.L + k); sp.pos[p * K + k] = (uint8_t)(p * ext + l + k); }
+        for (int k = 0; k < K; ++k) sp.push(P.L + k, p * ext + l + k);
     launch_intt(T, acc, sp, Bn, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * Bn);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, Bn, tq_bs, acc_bs, stream);
-    LimbSel sq; sq.n = 2 * l;
-    for (int i = 0; i < 2 * l; ++i) { sq.m[i] = (uint8_t)(i % l); sq.pos[i] = (uint8_t)i; }
+    LimbSel sq;
+    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
     launch_ntt(T, tq, sq, Bn, tq_bs, stream);
     FinishArgs fa{out, out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, add0, add0_bs, add1, add1_bs, plus, plus_bs};
     launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, Bn, stream);
@@ -615,10 +618,10 @@ void Engine::modup(u64* out_ext, const u64* c_eval, int l, int digit) {
     u64* up = alloc((size_t)ks.beta * ext * N);
     launch_modup_conv(T, ks, up, dco, 1, 0, 0, stream);
     const int lo = digit * ks.alpha, hi = std::min(lo + ks.alpha, l);
-    LimbSel su; su.n = 0;
+    LimbSel su;
     for (int t = 0; t < ext; ++t) {
         if (t >= lo && t < hi) continue;
-        su.m[su.n] = (uint8_t)P.mod_index_ext(l, t); su.pos[su.n] = (uint8_t)(digit * ext + t); su.n++;
+        su.push(P.mod_index_ext(l, t), digit * ext + t);
     }
     ntt(up, su);
     copy(out_ext, up + (size_t)digit * ext * N, (size_t)ext * N);
@@ -630,8 +633,8 @@ void Engine::moddown(u64* out, const u64* in_ext, int l) {
     const int N = P.N, K = P.K, ext = l + K;
     u64* acc = alloc((size_t)ext * N);
     copy(acc, in_ext, (size_t)ext * N);
-    LimbSel sp; sp.n = K;
-    for (int k = 0; k < K; ++k) { sp.m[k] = (uint8_t)(P.L + k); sp.pos[k] = (uint8_t)(l + k); }
+    LimbSel sp;
+    for (int k = 0; k < K; ++k) sp.push(P.L + k, l + k);
     launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
     u64* tq = alloc((size_t)l * N);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 1, 1, 0, 0, stream);

@@ -8,12 +8,37 @@
 
 namespace flk {
 namespace {
+constexpr uint32_t kFormatVersion = 2;       // 2: version / byte-order mark / chain fingerprint / batch count added to the header
+constexpr uint32_t kByteOrderMark = 0x01020304u;
 struct FileHdr {
     char magic[4];
     uint32_t kind;     // 1 = element, 2 = key bundle
     int32_t logN, L, K, ncomp, l, deg, slots, nkeys;
     double scale;
+    uint32_t version, bom;
+    uint64_t chain;    // fingerprint of the modulus chain (moduli and scaling rule): same logN / L with other primes must not load
+    int32_t batch, pad;
 };
+// FNV-1a over the moduli: a file written under another prime chain decrypts to garbage, so it is refused instead
+uint64_t chain_fingerprint(const Params& P) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](uint64_t v) { for (int i = 0; i < 8; ++i) { h ^= (v >> (8 * i)) & 0xff; h *= 0x100000001b3ull; } };
+    for (u64 q : P.q) mix(q);
+    mix((uint64_t)P.spec.first_bits); mix((uint64_t)P.spec.scale_bits); mix((uint64_t)P.dnum);
+    return h;
+}
+void fill_header(FileHdr& hd, uint32_t kind, const Params& P) {
+    std::memcpy(hd.magic, "FLCK", 4);
+    hd.kind = kind; hd.logN = P.logN; hd.L = P.L; hd.K = P.K;
+    hd.version = kFormatVersion; hd.bom = kByteOrderMark; hd.chain = chain_fingerprint(P);
+}
+void check_header(const FileHdr& hd, uint32_t kind, const Params& P, const char* what) {
+    if (std::memcmp(hd.magic, "FLCK", 4) || hd.kind != kind) throw std::runtime_error(std::string("not a ") + what + " file");
+    if (hd.bom != kByteOrderMark) throw std::runtime_error(std::string(what) + " file written with another byte order or by format version 1");
+    if (hd.version != kFormatVersion) throw std::runtime_error(std::string(what) + " file has format version " + std::to_string(hd.version) + ", expected " + std::to_string(kFormatVersion));
+    if (hd.logN != P.logN || hd.L != P.L || hd.K != P.K || hd.chain != chain_fingerprint(P))
+        throw std::runtime_error(std::string(what) + " file belongs to another context (ring, chain length or moduli differ)");
+}
 struct File {
     FILE* f;
     File(const char* path, const char* mode) : f(std::fopen(path, mode)) {
@@ -35,11 +60,12 @@ Elem Scheme::import_elem(const u64* host, int ncomp, int l, int deg, double scal
 
 void Scheme::save_elem(const Elem& a, const char* path) {
     if (!a.valid()) throw std::invalid_argument("save: empty ciphertext");
+    if (a.batch != 1) throw std::invalid_argument("save: a batched operand holds " + std::to_string(a.batch) + " ciphertexts; save its slices one by one");
     std::vector<u64> h((size_t)a.ncomp * a.l * P.N);
     eng.download(h.data(), a.data(), h.size());
     FileHdr hd{};
-    std::memcpy(hd.magic, "FLCK", 4);
-    hd.kind = 1; hd.logN = P.logN; hd.L = P.L; hd.K = P.K; hd.ncomp = a.ncomp; hd.l = a.l; hd.deg = a.deg; hd.slots = a.slots; hd.scale = a.scale;
+    fill_header(hd, 1, P);
+    hd.ncomp = a.ncomp; hd.l = a.l; hd.deg = a.deg; hd.slots = a.slots; hd.scale = a.scale; hd.batch = 1;
     File f(path, "wb");
     f.write(&hd, sizeof hd);
     f.write(h.data(), h.size() * 8);
@@ -49,7 +75,11 @@ Elem Scheme::load_elem(const char* path) {
     File f(path, "rb");
     FileHdr hd{};
     f.read(&hd, sizeof hd);
-    if (std::memcmp(hd.magic, "FLCK", 4) || hd.kind != 1 || hd.logN != P.logN || hd.L != P.L) throw std::runtime_error("not a ciphertext file of this context");
+    check_header(hd, 1, P, "ciphertext");
+    // validate every field before it sizes an allocation
+    if (hd.ncomp < 1 || hd.ncomp > 2 || hd.l < 1 || hd.l > P.L || hd.deg < 1 || hd.deg > 4 || hd.batch != 1 || hd.slots < 1 || hd.slots > P.N / 2 ||
+        (hd.slots & (hd.slots - 1)) || !(hd.scale > 0))
+        throw std::runtime_error("corrupt ciphertext header");
     std::vector<u64> h((size_t)hd.ncomp * hd.l * P.N);
     f.read(h.data(), h.size() * 8);
     return import_elem(h.data(), hd.ncomp, hd.l, hd.deg, hd.scale, hd.slots);
@@ -60,8 +90,7 @@ Elem Scheme::load_elem(const char* path) {
 // mirroring the reference's separate secret-key / public-key / mult-keys / rot_* files (FHEController.cpp:59-89,251).
 void Scheme::save_keys(const char* path, int what) {
     FileHdr hd{};
-    std::memcpy(hd.magic, "FLCK", 4);
-    hd.kind = 2; hd.logN = P.logN; hd.L = P.L; hd.K = P.K;
+    fill_header(hd, 2, P);
     std::vector<uint32_t> evks;
     if ((what & 4) && mk_) evks.push_back(0);
     if (what & 8) for (auto& kv : gk_) evks.push_back(kv.first);
@@ -80,7 +109,8 @@ void Scheme::load_keys(const char* path) {
     File f(path, "rb");
     FileHdr hd{};
     f.read(&hd, sizeof hd);
-    if (std::memcmp(hd.magic, "FLCK", 4) || hd.kind != 2 || hd.logN != P.logN || hd.L != P.L || hd.K != P.K) throw std::runtime_error("not a key file of this context");
+    check_header(hd, 2, P, "key");
+    if (hd.nkeys < 0 || hd.nkeys > (1 << 20)) throw std::runtime_error("corrupt key file");
     std::vector<u64> buf;
     for (int i = 0; i < hd.nkeys; ++i) {
         uint32_t tag, g; uint64_t words;

@@ -130,11 +130,14 @@ void launch_reduce_i128(const DevTables& t, u64* out, const int64_t* coef_lohi, 
 void launch_reduce_i8(const DevTables& t, u64* out, const int8_t* coef, const LimbSel& sel, cudaStream_t s);
 
 // ---- encode.cu: device-side encoding and samplers ----
-void upload_gauss_table(const u64* cdt30);
 // dst[sel.pos][N] <- residues of a ternary (kind 0) or discrete-Gaussian (kind 1) polynomial drawn from SplitMix64(seed)
 void launch_sample_limbs(const DevTables& t, u64* dst, u64 seed, int kind, const LimbSel& sel, cudaStream_t s);
 // dst limb i <- uniform residues mod q_{sel.m[i]} from SplitMix64(seeds[i])
 void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const LimbSel& sel, cudaStream_t s);
+// the production samplers: ChaCha20 key stream (chacha.cuh), block j of stream `nonce` per coefficient; uniform limb i uses stream nonce + i
+struct ChaChaKey;
+void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s);
+void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s);
 // special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd);
 // kext > 0 appends the residues modulo the first kext special limbs (plaintexts in the extended basis Q_l u P)
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,

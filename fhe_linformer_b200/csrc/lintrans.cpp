@@ -97,8 +97,8 @@ void Scheme::lintrans_encode(LinTrans& t, int level) {
     const double scale = P.sf[level];
     t.pts = std::make_shared<DevMem>(&eng, (size_t)t.n2 * t.n1 * ext * P.N);
     DevFft& f = dev_fft(n);
-    LimbSel se; se.n = ext;
-    for (int k = 0; k < ext; ++k) { se.m[k] = (uint8_t)P.mod_index_ext(l, k); se.pos[k] = (uint8_t)k; }
+    LimbSel se;
+    for (int k = 0; k < ext; ++k) se.push(P.mod_index_ext(l, k), k);
     for (int j = 0; j < t.n2; ++j)
         for (int i = 0; i < t.n1; ++i) {
             if (!((t.mask[j] >> i) & 1u)) continue;

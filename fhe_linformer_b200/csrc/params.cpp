@@ -2,6 +2,8 @@
 // Stands in for GenCryptoContext (reference FHEController.cpp:37); rules per SURVEY.md Appendix A.
 #include "params.h"
 
+#include <string>
+
 #include <cmath>
 #include <stdexcept>
 
@@ -120,6 +122,11 @@ Params::Params(const ParamSpec& s) : spec(s) {
     }
     K = (int)std::ceil(std::ceil(widest) / s.aux_bits);
     T = L + K;
+    // launch descriptors index moduli with 8 bits and address at most 256 limbs per ModUp (device_ctx.h LimbSel): reject what
+    // they cannot hold here, at context creation, instead of corrupting memory in the first key switch
+    if (T > 255) throw std::invalid_argument("modulus chain too long: L + K = " + std::to_string(T) + " > 255");
+    if (dnum * T - L > 256)
+        throw std::invalid_argument("dnum (L + K) - L = " + std::to_string(dnum * T - L) + " extended limbs per ModUp exceed the 256 a launch addresses: use fewer digits");
     u64 p = first_prime_above(s.aux_bits, M);
     for (int k = 0; k < K; ++k) {
         do { p = step_prime(p, M, false); } while (contains(q, 0, L, p));

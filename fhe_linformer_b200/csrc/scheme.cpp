@@ -2,49 +2,49 @@
 // FLEXIBLEAUTO bookkeeping, all arithmetic on the device engine.
 #include "scheme.h"
 
+#include <sys/random.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace flk {
 
 namespace {
 
-// |X| cumulative distribution of the discrete Gaussian, sigma = 3.19, scaled to 2^64 (DESIGN.md "Randomness")
-const u64 kGaussCdt[30] = {
-    0x2003F343659528D0ull, 0x5CF9E7DE0F06D96Bull, 0x9194FD0BB0694AF3ull, 0xBABAA2EF1EEC1101ull, 0xD7E6AB30AA084360ull,
-    0xEAA5B92100F77DABull, 0xF591040AC34992E9ull, 0xFB54CB2CA496FFFAull, 0xFE1702297749D972ull, 0xFF4953F8BD4AE9D1ull,
-    0xFFC1C20EF5DE7233ull, 0xFFECAC7F021E2BA0ull, 0xFFFA892133378B29ull, 0xFFFE9810099A70DBull, 0xFFFFABC31CFFB430ull,
-    0xFFFFEE138CF385DBull, 0xFFFFFC88B8F21ED7ull, 0xFFFFFF641EF54A94ull, 0xFFFFFFE7207A46BAull, 0xFFFFFFFC6560DA3Aull,
-    0xFFFFFFFF86A24B98ull, 0xFFFFFFFFF1822EC9ull, 0xFFFFFFFFFE6DFC66ull, 0xFFFFFFFFFFD877EFull, 0xFFFFFFFFFFFC7916ull,
-    0xFFFFFFFFFFFFB6EAull, 0xFFFFFFFFFFFFFAA2ull, 0xFFFFFFFFFFFFFFA4ull, 0xFFFFFFFFFFFFFFFAull, 0xFFFFFFFFFFFFFFFFull};
-
-std::vector<int8_t> sample_ternary(int N, u64 seed) {
-    SplitMix r(seed);
-    std::vector<int8_t> s(N);
-    for (int j = 0; j < N; ++j) { u64 v = r.next() % 3; s[j] = v == 2 ? -1 : (int8_t)v; }
-    return s;
-}
-std::vector<int8_t> sample_sparse(int N, int h, u64 seed) {
-    SplitMix r(seed);
+// sparse ternary secret with h non-zero coefficients (rejection loop, host side).  next() is the 64-bit stream to draw from:
+// SplitMix64 for the seeded test entry, ChaCha20 key stream otherwise.
+template <class Next>
+std::vector<int8_t> sample_sparse(int N, int h, Next&& next) {
     std::vector<int8_t> s(N, 0);
     for (int placed = 0; placed < h;) {
-        u64 pos = r.next() % N, sg = r.next() & 1;
+        u64 pos = next() % N, sg = next() & 1;
         if (!s[pos]) { s[pos] = sg ? -1 : 1; ++placed; }
     }
     return s;
 }
-std::vector<int8_t> sample_gauss(int N, u64 seed) {
-    SplitMix r(seed);
-    std::vector<int8_t> s(N);
-    for (int j = 0; j < N; ++j) {
-        u64 u = r.next(), sg = r.next() & 1;
-        int k = 0;
-        while (k < 29 && u >= kGaussCdt[k]) ++k;
-        s[j] = (int8_t)(sg ? -k : k);
+
+// 32 bytes from the operating system's CSPRNG
+ChaChaKey os_random_key() {
+    ChaChaKey k;
+    size_t got = 0;
+    while (got < sizeof k.k) {
+        const ssize_t r = getrandom(reinterpret_cast<char*>(k.k) + got, sizeof k.k - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
     }
-    return s;
+    if (got < sizeof k.k) {
+        FILE* f = std::fopen("/dev/urandom", "rb");
+        if (!f || std::fread(reinterpret_cast<char*>(k.k) + got, 1, sizeof k.k - got, f) != sizeof k.k - got) {
+            if (f) std::fclose(f);
+            throw std::runtime_error("no operating-system randomness available (getrandom and /dev/urandom both failed)");
+        }
+        std::fclose(f);
+    }
+    return k;
 }
 
 // special FFT of CKKS encoding (A.9), tables cached per slot count
@@ -52,8 +52,12 @@ struct FftTables {
     std::vector<uint32_t> rot;
     std::vector<double> cre, cim;
 };
+// process-wide cache shared by every Scheme (one controller per host thread is a supported mode): guarded, and std::map never
+// moves its nodes, so the reference handed out stays valid while other threads insert
 const FftTables& fft_tables(int n) {
     static std::map<int, FftTables> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(n);
     if (it != cache.end()) return it->second;
     FftTables t;
@@ -117,7 +121,10 @@ void fft_special(double* re, double* im, int n) {
 
 }  // namespace
 
-Scheme::Scheme(const ParamSpec& spec, int device) : eng(spec, device), P(eng.P) {}
+Scheme::Scheme(const ParamSpec& spec, int device) : eng(spec, device), P(eng.P) {
+    // independent keys for the secret key, the public `a` polynomials, the key errors and the encryption randomness
+    for (ChaChaKey& k : rng_keys_) k = os_random_key();
+}
 
 Scheme::~Scheme() {
     try {
@@ -193,34 +200,63 @@ void Scheme::sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSe
     eng.release((u64*)d8);
 }
 
-// Uniform, ternary and Gaussian polynomials are generated on the device from the same SplitMix64 streams the host
-// restatement walks sequentially (encode.cu): no host loop, no upload, no synchronisation.
-void Scheme::uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel) {
+// Uniform, ternary and Gaussian polynomials are generated on the device (encode.cu): no host loop, no upload, no
+// synchronisation.  A Draw names the stream: production draws (seeded == false) are ChaCha20 key stream under the key of their
+// purpose with a fresh 64-bit stream number each; seeded draws are the SplitMix64 streams the CPU restatement walks, reachable
+// only through fl_keygen_seeded / fl_encrypt_seeded (parity tests).
+void Scheme::uniform_to_dev(u64* dst, const Draw& d, const LimbSel& sel) {
+    if (!d.seeded) {
+        launch_uniform_limbs_csprng(eng.T, dst, rng_keys_[(int)d.use], rng_stream_, sel, eng.stream);
+        rng_stream_ += (u64)sel.n;   // one stream per limb
+        return;
+    }
     u64 seeds[kMaxLimbSel];
-    for (int i = 0; i < sel.n; ++i) seeds[i] = SplitMix::sub(seed, 1000 + sel.m[i]);
+    for (int i = 0; i < sel.n; ++i) seeds[i] = SplitMix::sub(d.seed, 1000 + sel.m[i]);
     launch_uniform_limbs(eng.T, dst, seeds, sel, eng.stream);
 }
 
-void Scheme::sample_dev_to_eval(u64* dst, u64 seed, int kind, const LimbSel& sel) {
-    if (!gauss_table_ready_) { upload_gauss_table(kGaussCdt); gauss_table_ready_ = true; }
-    launch_sample_limbs(eng.T, dst, seed, kind, sel, eng.stream);
+void Scheme::sample_dev_to_eval(u64* dst, const Draw& d, int kind, const LimbSel& sel) {
+    if (d.seeded) launch_sample_limbs(eng.T, dst, d.seed, kind, sel, eng.stream);
+    else launch_sample_limbs_csprng(eng.T, dst, rng_keys_[(int)d.use], rng_stream_++, kind, sel, eng.stream);
     eng.ntt(dst, sel);
 }
 
+// seed != 0: the deterministic test entry (every stream derives from `seed`; never use outside tests).  seed == 0: operating-
+// system randomness, nothing to persist, nothing from which a public polynomial could be traced back to the secret key.
 void Scheme::keygen(u64 seed) {
+    seeded_keys_ = seed != 0;
     key_seed_ = seed;
+    if (!seeded_keys_) for (ChaChaKey& k : rng_keys_) k = os_random_key();
     const int T = P.T, N = P.N;
     if (!sk_) sk_ = eng.alloc((size_t)T * N);
     if (!pk_) pk_ = eng.alloc((size_t)2 * P.L * N);
-    if (P.spec.sparse_h > 0) sample_to_eval(sk_, sample_sparse(N, P.spec.sparse_h, SplitMix::sub(seed, 0)), sel_range(0, T));   // rejection loop: host
-    else sample_dev_to_eval(sk_, SplitMix::sub(seed, 0), 0, sel_range(0, T));
+    if (P.spec.sparse_h > 0) {   // rejection loop: host
+        std::vector<int8_t> s;
+        if (seeded_keys_) {
+            SplitMix r(SplitMix::sub(seed, 0));
+            s = sample_sparse(N, P.spec.sparse_h, [&] { return r.next(); });
+        } else {
+            uint32_t blk[16];
+            u64 ctr = 0;
+            int at = 8;
+            const u64 stream = rng_stream_++;
+            s = sample_sparse(N, P.spec.sparse_h, [&] {
+                if (at == 8) { chacha20_block(rng_keys_[(int)Use::Secret], ctr++, stream, blk); at = 0; }
+                return chacha_u64(blk, at++);
+            });
+        }
+        sample_to_eval(sk_, s, sel_range(0, T));
+        std::fill(s.begin(), s.end(), 0);
+    } else {
+        sample_dev_to_eval(sk_, draw(Use::Secret, SplitMix::sub(seed, 0)), 0, sel_range(0, T));
+    }
     // pk = (e - a*s, a)
     const LimbSel q = sel_range(0, P.L);
     const size_t pl = (size_t)P.L * N;
     const u64 pseed = seed + 1;
-    uniform_to_dev(pk_ + pl, SplitMix::sub(pseed, 10), q);
+    uniform_to_dev(pk_ + pl, draw(Use::Public, SplitMix::sub(pseed, 10)), q);
     u64* e = eng.alloc(pl);
-    sample_dev_to_eval(e, SplitMix::sub(pseed, 11), 1, q);
+    sample_dev_to_eval(e, draw(Use::Error, SplitMix::sub(pseed, 11)), 1, q);
     launch_ew(eng.T, EwOp::Mul, pk_, pk_ + pl, sk_, q, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Sub, pk_, e, pk_, q, 1, 1, 0, 0, 0, eng.stream);
     eng.release(e);
@@ -237,8 +273,8 @@ void Scheme::keyswitch_gen(const u64* sk_old, const u64* sk_new, u64 seed, u64* 
     for (int d = 0; d < P.dnum; ++d) {
         u64* b = evk + (size_t)d * 2 * kl;
         u64* a = b + kl;
-        uniform_to_dev(a, SplitMix::sub(seed, 100 + 2 * d), all);
-        sample_dev_to_eval(e, SplitMix::sub(seed, 101 + 2 * d), 1, all);
+        uniform_to_dev(a, draw(Use::Public, SplitMix::sub(seed, 100 + 2 * d)), all);
+        sample_dev_to_eval(e, draw(Use::Error, SplitMix::sub(seed, 101 + 2 * d)), 1, all);
         launch_ew(eng.T, EwOp::Mul, b, a, sk_new, all, 1, 1, 0, 0, 0, eng.stream);
         launch_ew(eng.T, EwOp::Sub, b, e, b, all, 1, 1, 0, 0, 0, eng.stream);
         const int lo = d * P.alpha, hi = std::min(lo + P.alpha, P.L), ns = hi - lo;
@@ -433,7 +469,12 @@ void Scheme::decode(const Elem& pt, cplx* out, int slots) {
 }
 
 // ---------------------------------------------------------------- encrypt / decrypt
-Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) {
+Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) { return encrypt_with(pt, true, seed); }
+// every encryption draws (v, e0, e1) from fresh ChaCha20 streams under the encryption key of this process: no two
+// encryptions, in this or any other process, share randomness
+Elem Scheme::encrypt(const Elem& pt) { return encrypt_with(pt, false, 0); }
+
+Elem Scheme::encrypt_with(const Elem& pt, bool seeded, u64 seed) {
     if (!pk_) throw std::runtime_error("Encrypt: no public key");
     if (pt.ncomp != 1) throw std::invalid_argument("Encrypt: plaintext expected");
     const int l = pt.l, N = P.N;
@@ -442,19 +483,19 @@ Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) {
     Elem ct = make(2, l, pt.deg, pt.scale, pt.slots);
     u64* v = eng.alloc(pl);
     u64* e = eng.alloc(pl);
-    sample_dev_to_eval(v, SplitMix::sub(seed, 1), 0, sel);
-    sample_dev_to_eval(e, SplitMix::sub(seed, 2), 1, sel);
+    const auto dr = [&](u64 tag) { return Draw{seeded, SplitMix::sub(seed, tag), Use::Encrypt}; };
+    sample_dev_to_eval(v, dr(1), 0, sel);
+    sample_dev_to_eval(e, dr(2), 1, sel);
     u64* c0 = ct.data(); u64* c1 = c0 + pl;
     launch_ew(eng.T, EwOp::Mul, c0, pk_, v, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c0, c0, e, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c0, c0, pt.data(), sel, 1, 1, 0, 0, 0, eng.stream);
-    sample_dev_to_eval(e, SplitMix::sub(seed, 3), 1, sel);
+    sample_dev_to_eval(e, dr(3), 1, sel);
     launch_ew(eng.T, EwOp::Mul, c1, pk_ + pkl, v, sel, 1, 1, 0, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, c1, c1, e, sel, 1, 1, 0, 0, 0, eng.stream);
     eng.release(v); eng.release(e);
     return ct;
 }
-Elem Scheme::encrypt(const Elem& pt) { return encrypt_seeded(pt, SplitMix::sub(key_seed_, 0xE0000 + (seed_counter++))); }
 
 void Scheme::decrypt(const Elem& ct_in, cplx* out, int slots) {
     if (ct_in.batch != 1) throw std::invalid_argument("Decrypt: take a slice of the batched ciphertext first");

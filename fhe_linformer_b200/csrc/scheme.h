@@ -8,6 +8,7 @@
 #include <memory>
 #include <vector>
 
+#include "chacha.cuh"
 #include "engine.h"
 
 namespace flk {
@@ -157,7 +158,6 @@ public:
     void load_keys(const char* path);
 
     int level_of(const Elem& a) const { return P.L - a.l; }
-    u64 seed_counter = 0x5EEDull;
 
 private:
     friend struct BootPrecomp;
@@ -165,8 +165,13 @@ private:
     std::vector<Elem> split_run(const Elem& a, const std::function<Elem(const Elem&)>& f);
     void keyswitch_gen(const u64* sk_old_dev, const u64* sk_new_dev, u64 seed, u64* evk_dev);
     void sample_to_eval(u64* dst, const std::vector<int8_t>& s, const LimbSel& sel);
-    void uniform_to_dev(u64* dst, u64 seed, const LimbSel& sel);
-    void sample_dev_to_eval(u64* dst, u64 seed, int kind, const LimbSel& sel);   // kind 0 ternary, 1 Gaussian (device sampler + NTT)
+    // randomness: what a stream is for (independent ChaCha20 keys) and, for the seeded test entries, its SplitMix64 seed
+    enum class Use { Secret = 0, Public = 1, Error = 2, Encrypt = 3 };
+    struct Draw { bool seeded; u64 seed; Use use; };
+    Draw draw(Use use, u64 seed) const { return Draw{seeded_keys_, seed, use}; }
+    void uniform_to_dev(u64* dst, const Draw& d, const LimbSel& sel);
+    void sample_dev_to_eval(u64* dst, const Draw& d, int kind, const LimbSel& sel);   // kind 0 ternary, 1 Gaussian (device sampler + NTT)
+    Elem encrypt_with(const Elem& pt, bool seeded, u64 seed);
     struct DevFft { uint32_t* rot; double* cre; double* cim; };               // special-FFT tables of one slot count, on the device
     DevFft& dev_fft(int slots);
     double* stage_slot(int& slot);                                   // next free slot of the pinned staging ring
@@ -186,8 +191,10 @@ private:
     double* stage_ = nullptr;                 // pinned staging ring for slot values
     cudaEvent_t stage_ev_[kStageSlots] = {};
     int stage_next_ = 0;
-    bool gauss_table_ready_ = false;
-    u64 key_seed_ = 1;
+    ChaChaKey rng_keys_[4];                   // per Use, from getrandom(); re-drawn by every unseeded keygen
+    u64 rng_stream_ = 0;                      // next unused ChaCha20 stream number (never reused under one key)
+    bool seeded_keys_ = false;                // keys of this context came from fl_keygen_seeded (tests only)
+    u64 key_seed_ = 0;
     u64* sk_ = nullptr;      // (L+K) limbs eval
     u64* pk_ = nullptr;      // [2][L][N]
     u64* mk_ = nullptr;      // relinearisation key

@@ -65,7 +65,7 @@ class _Borrowed(CKKS):
 class FHEController:
     """The reference's FHEController (src/FHEController.h:22-162) on the B200 engine."""
 
-    def __init__(self, device=0, key_seed=20261018, root=None):
+    def __init__(self, device=0, key_seed=0, root=None):
         self.hl = load_host_library()
         if root is not None:
             os.environ["FHE_LINFORMER_ROOT"] = root

@@ -11,6 +11,8 @@
 // -8, -16 and -512); key / ciphertext files use the engine's own container (DESIGN.md "Files").
 #include "FHEController.h"
 
+#include <set>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -29,7 +31,7 @@ bool file_exists(const std::string& p) { return std::ifstream(p).good(); }
 struct ContextFile {   // crypto-context.txt: the CCParams needed to rebuild the context
     char magic[8];
     int32_t logN, L, dnum, first_bits, scale_bits, aux_bits, sparse_h, budget0, budget1, depth;
-    uint64_t key_seed;
+    uint64_t reserved;   // was a key seed in round 1: never written any more (a seed next to the public key gives the secret key away)
 };
 
 double cheb_trampoline(double x, void* user) { return (*static_cast<const std::function<double(double)>*>(user))(x); }
@@ -115,7 +117,7 @@ void FHEController::serialize_context() {
     std::memcpy(cf.magic, "FLCKCTX", 8);
     cf.logN = params_.logN; cf.L = params_.L; cf.dnum = params_.dnum; cf.first_bits = params_.first_bits; cf.scale_bits = params_.scale_bits;
     cf.aux_bits = params_.aux_bits; cf.sparse_h = params_.sparse_h; cf.budget0 = (int)level_budget[0]; cf.budget1 = (int)level_budget[1];
-    cf.depth = circuit_depth; cf.key_seed = key_seed;
+    cf.depth = circuit_depth; cf.reserved = 0;
     std::ofstream out(key_path("crypto-context.txt"), ios::out | ios::binary);
     if (out.write(reinterpret_cast<const char*>(&cf), sizeof cf)) cout << "Crypto Context have been serialized" << endl;
     else cerr << "Error writing serialization of the crypto context to crypto-context.txt" << endl;
@@ -132,7 +134,6 @@ void FHEController::load_context(bool verbose) {
     std::ifstream in(key_path("crypto-context.txt"), ios::in | ios::binary);
     if (!in.read(reinterpret_cast<char*>(&cf), sizeof cf) || std::memcmp(cf.magic, "FLCKCTX", 8))
         die("I cannot read serialized data from: " + key_path("crypto-context.txt"));
-    key_seed = cf.key_seed;
     if (ctx_) { mask_cache_.clear(); fl_ctx_destroy(ctx_); ctx_ = nullptr; }
     params_.logN = cf.logN; params_.L = cf.L; params_.dnum = cf.dnum; params_.first_bits = cf.first_bits; params_.scale_bits = cf.scale_bits;
     params_.aux_bits = cf.aux_bits; params_.sparse_h = cf.sparse_h;
@@ -162,9 +163,52 @@ void FHEController::generate_rotation_keys(vector<int> rotations, bool serialize
         return;
     }
     need(fl_gen_rot_keys(ctx_, rotations.data(), (int)rotations.size()), "EvalRotateKeyGen");
+    // The batched recipes of this backend use more indices than the reference's sequential loops: the hoisted ladder groups
+    // (multiples of a ladder's stride, fl_rotsum_rotations) and the binary trees that replace rotate(., -1) / rotate(., -512)
+    // chains.  They are derived from the list given here and generated NOW, so that no key is ever made from the secret key
+    // in the middle of an evaluation (and none inside a timed region); rotate() on a missing index fails as OpenFHE does.
+    const vector<int> extra = derived_rotations(rotations);
+    if (!extra.empty()) need(fl_gen_rot_keys(ctx_, extra.data(), (int)extra.size()), "EvalRotateKeyGen");
     if (!serialize) return;
     if (fl_keys_save_sel(ctx_, key_path("rot_" + filename).c_str(), 8)) die("Error serializing Rotation keys" + key_path("rot_" + filename));
     cout << "Rotation keys \"" << filename << "\" have been serialized" << endl;
+}
+
+vector<int> FHEController::derived_rotations(const vector<int>& listed) const {
+    std::set<int> have(listed.begin(), listed.end()), out;
+    auto chain = [&](int stride, int steps) {   // stride * 2^i listed for every doubling step?
+        for (int i = 0; i < steps; ++i) if (!have.count(stride * (1 << i))) return false;
+        return true;
+    };
+    if (hoist_ladders) {
+        // every ladder F.cpp:829-867 is called with on this circuit (rotsum 128/64/32 x stride 128 or 1, repeat 128/64 x -1, -128)
+        static const int ladders[][2] = {{128, 128}, {128, 1}, {64, 1}, {32, 128}, {128, -1}, {64, -1}, {128, -128}, {64, 128}, {32, 1}};
+        for (auto& ld : ladders) {
+            int steps = 0;
+            while ((1 << steps) < ld[0]) ++steps;
+            if (!chain(ld[1], steps)) continue;
+            int rots[64];
+            const int nr = fl_rotsum_rotations(steps, ld[1], rots, 64);
+            for (int i = 0; i < nr && i < 64; ++i) if (!have.count(rots[i])) out.insert(rots[i]);
+        }
+    }
+    if (batch_rows) {   // shifted_sum trees: stride * 2^b for up to 256 rows (stride -1) / 8 containers (stride -512)
+        if (have.count(-1)) for (int b = 1; b < 8; ++b) if (!have.count(-(1 << b))) out.insert(-(1 << b));
+        if (have.count(-512)) for (int b = 1; b < 3; ++b) out.insert(-512 * (1 << b));
+    }
+    return vector<int>(out.begin(), out.end());
+}
+
+double FHEController::rotation_key_bytes() const {
+    return fl_rot_key_bytes(ctx_);
+}
+
+void FHEController::require_rotation_key(int index) {
+    if (fl_has_rot_key(ctx_, index)) return;
+    if (!auto_rotation_keys)
+        throw std::runtime_error("EvalRotate: no evaluation key for rotation index " + std::to_string(index) +
+                                 " (EvalRotateKeyGen was not called for it; set auto_rotation_keys to generate keys on demand)");
+    need(fl_gen_rot_keys(ctx_, &index, 1), "EvalRotateKeyGen");
 }
 
 void FHEController::generate_bootstrapping_and_rotation_keys(vector<int> rotations, int bootstrap_slots, bool serialize, const string& filename) {
@@ -288,10 +332,7 @@ Ctxt FHEController::mult(const Ctxt& c1, const Ctxt& c2) {
     return wrap(e);
 }
 Ctxt FHEController::rotate(const Ctxt& c, int index) {
-    if (!fl_has_rot_key(ctx_, index)) {
-        // the reference would throw from EvalRotate here; with the secret key resident we can make the key instead
-        need(fl_gen_rot_keys(ctx_, &index, 1), "EvalRotateKeyGen");
-    }
+    require_rotation_key(index);   // missing key: an error, as from OpenFHE's EvalRotate (unless auto_rotation_keys)
     fl_elem* e = nullptr;
     need(fl_rotate(ctx_, c->handle(), index, &e), "EvalRotate");
     return wrap(e);
@@ -441,8 +482,7 @@ Ctxt FHEController::ladder(const Ctxt& in, int slots, int stride) {
     const int nr = fl_rotsum_rotations(steps, stride, rots, 64);
     for (int i = 0; i < nr && i < 64; ++i) {
         if (i >= steps && !hoist_ladders) break;
-        int k = rots[i];
-        if (!fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
+        require_rotation_key(rots[i]);
     }
     fl_elem* e = nullptr;
     need(fl_rotsum(ctx_, in->handle(), steps, stride, &e), "EvalRotate ladder");
@@ -726,7 +766,7 @@ Ctxt FHEController::wrap_containers(vector<Ctxt> c, int inputs_number) {
     vector<Ctxt> items(c.rend() - inputs_number, c.rend());
     for (int b = 0; (1 << b) < inputs_number; ++b) {
         int k = -512 * (1 << b);
-        if (batch_rows && !fl_has_rot_key(ctx_, k)) need(fl_gen_rot_keys(ctx_, &k, 1), "EvalRotateKeyGen");
+        if (batch_rows) require_rotation_key(k);
     }
     return shifted_sum(items, -512);
 }

@@ -153,7 +153,8 @@ public:
     // Additions of the B200 backend (not part of the reference interface)
     // =====================================================================================================================
     int device = 0;                               // CUDA device of this controller: one context per GPU
-    unsigned long long key_seed = 20261018ULL;    // all key / encryption randomness derives from it
+    unsigned long long key_seed = 0;              // 0: operating-system randomness (production); non-zero: reproducible TEST keys
+    bool auto_rotation_keys = false;              // false: rotate() on an index without a key fails, as OpenFHE's EvalRotate does
     bool batch_rows = true;                       // independent rows share kernel launches (FHEController.cpp "row batching")
     bool hoist_ladders = true;                    // extra rotation keys (fl_rotsum_rotations): ladders take up to four doubling steps per hoisted key switch
     int max_rows_per_batch = 64;                  // same speed as 256 (1.698 vs 1.693 s at S = 256) with 50 GB instead of 85 GB cached
@@ -170,7 +171,11 @@ public:
     // out[o] = sum_t weights[o][t] * rows[t] (+ bias[o]): the Linformer E / F projection on the row ciphertexts
     Rows project_rows(const Rows& rows, const vector<vector<double>>& weights, const vector<Ptxt>& bias);
 
+    vector<int> derived_rotations(const vector<int>& listed) const;  // extra indices the batched / hoisted recipes use for a key list
+    double rotation_key_bytes() const;                               // device memory held by automorphism keys
+
 private:
+    void require_rotation_key(int index);
     void create(int log_ring, int depth, int digits, int first_bits, int scale_bits);
     void serialize_context();
     string key_path(const string& name) const;

@@ -102,13 +102,20 @@ typedef struct fl_elem fl_elem;   /* ciphertext (2 polynomials) or plaintext (1)
 typedef fl_elem fl_ct;            /* Ctxt = Ciphertext<DCRTPoly>   FHEController.h:20 */
 typedef fl_elem fl_pt;            /* Ptxt = Plaintext              FHEController.h:19 */
 
-/* keys: KeyGen F.cpp:47, EvalMultKeyGen F.cpp:49, EvalRotateKeyGen F.cpp:248 (seeded; DESIGN.md "Randomness") */
-int fl_keygen(fl_ctx* c, uint64_t seed);
+/* keys: KeyGen F.cpp:47, EvalMultKeyGen F.cpp:49, EvalRotateKeyGen F.cpp:248.
+ * fl_keygen(c, 0) draws the secret key, the public polynomials, the key errors and all later encryption randomness from
+ * ChaCha20 streams under independent keys taken from the operating system (getrandom), as OpenFHE's CSPRNG does; nothing
+ * is derived from a seed and nothing seed-like is ever written to a file.  A non-zero seed is fl_keygen_seeded. */
+int fl_keygen(fl_ctx* c, uint64_t seed_or_zero);
+/* TEST ONLY: every key stream derives from `seed` (SplitMix64), so the CPU restatement reproduces the keys limb for limb.
+ * Keys made this way are not secret: a public polynomial reveals the seed. */
+int fl_keygen_seeded(fl_ctx* c, uint64_t seed);
 int fl_gen_mult_key(fl_ctx* c);
 int fl_gen_rot_keys(fl_ctx* c, const int* indices, int n);
 int fl_gen_conj_key(fl_ctx* c);
 int fl_keys_clear(fl_ctx* c, int kind);   /* 0: ClearEvalAutomorphismKeys F.cpp:336, 1: ClearEvalMultKeys F.cpp:342 */
 int fl_num_rot_keys(fl_ctx* c);
+double fl_rot_key_bytes(fl_ctx* c);      /* device memory held by the automorphism keys (dnum x 2 x (L + K) x N words each) */
 /* raw key material <-> host (Serial::SerializeToFile / DeserializeFromFile of keys, F.cpp:59-89,192-220,251,291) */
 int fl_export_sk(fl_ctx* c, uint64_t* out /* (L+K) N */);
 int fl_export_pk(fl_ctx* c, uint64_t* out /* 2 L N */);
@@ -123,6 +130,7 @@ int fl_keys_load(fl_ctx* c, const char* path);   /* merges whatever records the 
 /* MakeCKKSPackedPlaintext(vec, 1, level, nullptr, slots) F.cpp:353; im may be NULL */
 int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out);
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out);                         /* Encrypt F.cpp:380 */
+/* TEST ONLY: fixed encryption randomness (v, e0, e1 from SplitMix64(seed)) for the limb-exact parity tests */
 int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out);
 int fl_decrypt(fl_ctx* c, const fl_ct* a, double* re, double* im, int slots);   /* Decrypt + GetRealPackedValue F.cpp:389,402 */
 int fl_decode(fl_ctx* c, const fl_pt* p, double* re, double* im, int slots);

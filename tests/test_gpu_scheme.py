@@ -1,0 +1,125 @@
+"""Scheme-level parity: keys, encoding and seeded encryption of the CUDA engine are
+limb-for-limb those of the CPU restatement (oracle/ckks_oracle.c), at a small ring and at the reference ring
+(FHEController.cpp:6-35: N = 2^15, 28 Q limbs, dnum 4); a rotate-and-add ladder without hoisting equals the sequential
+ladder of FHEController.cpp:829-837 limb for limb.  Bar: bit-exact (integer work)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RINGS = [dict(logN=12, L=14, dnum=3), dict(logN=15, L=28, dnum=4)]
+
+
+@pytest.fixture(scope="module", params=RINGS, ids=lambda p: "logN%d_L%d_d%d" % (p["logN"], p["L"], p["dnum"]))
+def ctx(request):
+    from fhe_linformer_b200 import CKKS
+    from oracle.oracle import Oracle
+    o = Oracle(**request.param)
+    c = CKKS(sparse_h=64, **request.param)
+    seed = 42
+    c.keygen(seed)            # the seeded TEST entry (fl_keygen_seeded): every stream derives from `seed`
+    c.gen_mult_key()
+    c.gen_rot_keys([1, -1, 2, 4])
+    c.gen_conj_key()
+    sk = o.gen_sk(seed, h=64)
+    pk = o.gen_pk(seed + 1, sk)
+    yield o, c, seed, sk, pk
+    c.close()
+
+
+def test_key_pair_bit_exact(ctx):
+    o, c, seed, sk, pk = ctx
+    assert (c.export_sk() == sk).all(), "secret key limbs differ from the oracle"
+    assert (c.export_pk() == pk).all(), "public key limbs differ from the oracle"
+
+
+def test_relinearisation_key_bit_exact(ctx):
+    o, c, seed, sk, pk = ctx
+    assert (c.export_evk(0) == o.gen_relin_key(seed + 2, sk)).all()
+
+
+@pytest.mark.parametrize("k", [1, -1, 4])
+def test_rotation_keys_bit_exact(ctx, k):
+    o, c, seed, sk, pk = ctx
+    g = o.galois(k)
+    assert (c.export_evk(g) == o.gen_galois_key(seed + 1000 + g, sk, g)).all()
+
+
+def test_conjugation_key_bit_exact(ctx):
+    o, c, seed, sk, pk = ctx
+    g = o.galois_conj()
+    assert (c.export_evk(g) == o.gen_galois_key(seed + 1000 + g, sk, g)).all()
+
+
+def test_encode_bit_exact_two_levels(ctx):
+    o, c, seed, sk, pk = ctx
+    n = o.N // 2
+    rng = np.random.default_rng(0)
+    v, w = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    assert (c.encode(v, level=0).export()[0] == o.encode(v, o.sf[0], o.L)).all(), "level 0"
+    assert (c.encode(v + 1j * w, level=3, slots=n).export()[0] == o.encode(v + 1j * w, o.sf[3], o.L - 3)).all(), "level 3, complex"
+    # sparse packing (fewer slots than N/2) and edge vectors
+    assert (c.encode(v[: n // 4], level=1, slots=n // 4).export()[0] == o.encode(v[: n // 4], o.sf[1], o.L - 1, slots=n // 4)).all(), "sparse packing"
+    z = np.zeros(n); e1 = np.zeros(n); e1[0] = 1.0
+    for name, x in (("zeros", z), ("unit", e1), ("ones", np.ones(n))):
+        assert (c.encode(x, level=0).export()[0] == o.encode(x, o.sf[0], o.L)).all(), name
+
+
+def test_seeded_encrypt_bit_exact(ctx):
+    o, c, seed, sk, pk = ctx
+    n = o.N // 2
+    v = np.random.default_rng(1).uniform(-1, 1, n)
+    pt = c.encode(v, level=0)
+    ct = c.encrypt(pt, seed=7)
+    assert (ct.export() == o.encrypt(7, o.encode(v, o.sf[0], o.L), pk)).all()
+    # a lower level: the ciphertext uses the first L - 2 limbs of the public key (the oracle takes the full key)
+    pt2 = c.encode(v, level=2)
+    ref = o.encrypt(9, o.encode(v, o.sf[2], o.L - 2), pk)
+    assert (c.encrypt(pt2, seed=9).export() == ref).all()
+    assert np.abs(c.decrypt(ct) - v).max() < 1e-7
+
+
+def test_unseeded_encryptions_never_repeat(ctx):
+    """fl_encrypt draws from ChaCha20 streams keyed from the operating system: two encryptions of one plaintext differ in
+    every limb, and both decrypt."""
+    o, c, seed, sk, pk = ctx
+    v = np.random.default_rng(2).uniform(-1, 1, o.N // 2)
+    pt = c.encode(v, level=0)
+    a, b = c.encrypt(pt).export(), c.encrypt(pt).export()
+    assert (a != b).mean() > 0.99
+    assert np.abs(c.decrypt(c.encrypt(pt)) - v).max() < 1e-7
+
+
+def test_sequential_ladder_limb_exact(ctx):
+    """rotsum with only the doubling keys present (no hoisted groups) is r <- r + EvalRotate(r, stride 2^i) step by step:
+    the same limbs as the oracle's sequential ladder (FHEController.cpp:829-837)."""
+    o, c, seed, sk, pk = ctx
+    l = o.L - 1
+    rng = np.random.default_rng(3)
+    q = [int(x) for x in o.moduli]
+    ct = np.stack([np.stack([rng.integers(0, q[m], o.N, dtype=np.uint64) for m in range(l)]) for _ in range(2)])
+    steps, stride = 3, 1                                   # keys 1, 2, 4 exist; 3, 5, 6, 7 do not, so no group is hoisted
+    got = c.rotsum(c.import_elem(ct, 1, float(o.sf[1]), o.N // 2), steps, stride).export()
+    ref = ct.copy()
+    for i in range(steps):
+        g = o.galois(stride << i)
+        rot = o.rotate(ref, g, o.gen_galois_key(seed + 1000 + g, sk, g))
+        ref = np.stack([o.add(ref[0], rot[0], list(range(l))), o.add(ref[1], rot[1], list(range(l)))])
+    assert (got == ref).all()
+
+
+def test_unseeded_keys_are_fresh_and_work():
+    """fl_keygen(ctx, 0): two contexts never share a key, nothing derives from a seed, encryption round-trips."""
+    from fhe_linformer_b200 import CKKS
+    P = dict(logN=11, L=4, dnum=2)
+    a, b = CKKS(sparse_h=32, **P), CKKS(sparse_h=32, **P)
+    a.keygen(); b.keygen()
+    assert (a.export_sk() != b.export_sk()).any() and (a.export_pk() != b.export_pk()).mean() > 0.99
+    sk = a.export_sk()
+    a.keygen()   # a second call draws new keys
+    assert (a.export_sk() != sk).any()
+    a.gen_mult_key(); a.gen_rot_keys([1])
+    v = np.random.default_rng(4).uniform(-1, 1, a.N // 2)
+    ct = a.encrypt(v)
+    assert np.abs(a.decrypt(a.rotate(a.mult(ct, ct), 1)) - np.roll(v * v, -1)).max() < 1e-6
+    a.close(); b.close()
