@@ -201,3 +201,25 @@ def test_bootstrap_variants_and_scalar_mult(env):
     assert err(c, b2, v) < 1e-5
     m = fc.invoke("mult", [enc(c, v)], reals=[0.37])[0]
     assert err(c, m, 0.37 * v) < TOL
+
+
+def test_bootstrap_with_openfhe_evalmod_conventions(monkeypatch):
+    """FLK_BOOT_OPENFHE=1 selects the sparse-secret EvalMod conventions SURVEY.md App. A.11 records for OpenFHE (K = 28,
+    R = 3 double-angle steps, degree-44 interpolant, its correction-factor rule uncapped) instead of the set measured best
+    here; kept working so the level accounting after main.cpp:319-320 can be lined up once OpenFHE artifacts exist."""
+    from fhe_linformer_b200 import CKKS
+    monkeypatch.setenv("FLK_BOOT_OPENFHE", "1")
+    c = CKKS(logN=13, L=24, dnum=4, sparse_h=64)
+    c.keygen(); c.gen_mult_key()
+    n = c.N // 2
+    c.bootstrap_setup((3, 3), n)
+    c.bootstrap_keygen(n)
+    v = np.random.default_rng(8).uniform(-1, 1, n)
+    ct = c.encrypt(v, level=c.L - 2)
+    b = c.bootstrap(ct)
+    # CoeffsToSlots 3 + (degree 44: 6 + 1) + 3 double-angle + SlotsToCoeffs 3 = 16 levels with this evaluator
+    # (GetBootstrapDepth = 14 in OpenFHE: its series evaluation folds the scalar coefficients, ours spends a level on them)
+    assert b.level <= 17, b.level
+    assert float(np.abs(c.decrypt(b) - v).max()) < 2e-4
+    monkeypatch.delenv("FLK_BOOT_OPENFHE")
+    c.close()

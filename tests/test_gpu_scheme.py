@@ -123,3 +123,34 @@ def test_unseeded_keys_are_fresh_and_work():
     ct = a.encrypt(v)
     assert np.abs(a.decrypt(a.rotate(a.mult(ct, ct), 1)) - np.roll(v * v, -1)).max() < 1e-6
     a.close(); b.close()
+
+
+def test_first_use_of_a_slot_count_from_two_threads():
+    """Two controllers, each on its own host thread, hit encode / decode for slot counts no one in this process has used yet:
+    the special-FFT table cache is shared by all contexts and must tolerate concurrent first use (no pre-warming here)."""
+    import threading
+    from fhe_linformer_b200 import CKKS
+    P = dict(logN=11, L=3, dnum=2)
+    ctxs = [CKKS(sparse_h=32, **P) for _ in range(2)]
+    for c in ctxs: c.keygen()
+    errs, fails = {}, []
+    barrier = threading.Barrier(2)
+
+    def work(i, c):
+        try:
+            rng = np.random.default_rng(100 + i)
+            barrier.wait()
+            worst = 0.0
+            for slots in (8, 16, 64, 128, 8, 16):            # unusual sizes: cold in the cache on first touch
+                v = rng.uniform(-1, 1, slots)
+                worst = max(worst, float(np.abs(c.decrypt(c.encrypt(v, slots=slots)) - v).max()))
+            errs[i] = worst
+        except Exception as e:   # noqa: BLE001
+            fails.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(i, c)) for i, c in enumerate(ctxs)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not fails, fails
+    assert len(errs) == 2 and max(errs.values()) < 1e-6
+    for c in ctxs: c.close()
