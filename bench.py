@@ -56,10 +56,28 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the encrypted Linformer forward (extra `forward` key)")
     ap.add_argument("--forward-in-flight", type=int, default=2, help="forwards in flight per GPU for the extra throughput-mode figure (1 = skip)")
-    ap.add_argument("--forward-rows", type=int, default=129, help="S = rows of the forward sample (129..256)")
+    ap.add_argument("--forward-rows", type=int, default=200, help="S = rows of the forward sample (129..256); 200 = SURVEY.md Config 1")
+    ap.add_argument("--samples", type=int, default=0, help="samples of the sample-parallel batch over ALL GPUs (BASELINE config 5 names 256); 0 = 8 per GPU")
+    ap.add_argument("--no-forward-configs", action="store_true", help="skip the BASELINE config 3 / 4 shapes (extra `forward.configs` block)")
     ap.add_argument("--no-forward-n16", action="store_true", help="skip the extra forward at the reference's commented-out ring N=2^16")
     ap.add_argument("--forward-logn", type=int, default=15, help="ring of the forward: 15 = the reference's parameters, 16 = its commented-out variant (sparse packing)")
     return ap.parse_args()
+
+
+def host_threads():
+    """All host cores this process may run on.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which round 1's
+    reference arm silently obeyed at N >= 2: the oracle's thread count is now set explicitly (orc_set_threads)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(logN, l, K, dnum, B, G, world, N):
+    """`config` of the JSON line: the same object for both arms, so the driver's same_config check compares like with like."""
+    return {"workload": f"EvalRotate N=2^{logN} l={l} K={K} dnum={dnum} (BASELINE.json configs[1])", "batch_per_gpu": B,
+            "parallelism": f"ciphertext-parallel x{world}", "ciphertexts_per_launch": G,
+            "l2": f"inputs larger than L2 ({B * 2 * 2 * l * N * 8 / 1e6:.0f} MB touched per step)"}
 
 
 def algorithmic_bytes_rotate(N, l, K, alpha):
@@ -138,7 +156,9 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())   # before libgomp initialises; orc_set_threads below covers the other order
     from oracle.oracle import Oracle, lib
+    lib().orc_set_threads(host_threads())
     o = Oracle(logN=a.logN, L=28, dnum=4)
     cores = int(lib().orc_num_threads())
     per_step = max(1, min(a.batch, 4))                   # bounded sample of the step's batch
@@ -150,9 +170,9 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": per_rot * per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": {"workload": f"EvalRotate N=2^{a.logN} l={a.limbs} dnum=4 (BASELINE.json configs[1])", "sample_per_step": per_step},
+        "data": "synthetic", "config": workload_config(a.logN, a.limbs, o.K, o.dnum, a.batch, max(1, min(a.group, a.batch)), a.gpus, o.N),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} rotations per step x {a.steps} steps, oracle/ckks_oracle.c with OpenMP ({cores} threads); "
+                         "sample": f"{per_step} of the step's {a.batch} rotations per step x {a.steps} steps, oracle/ckks_oracle.c with OpenMP ({cores} threads); "
                                    "OpenFHE-equivalent CPU restatement, not OpenFHE"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -332,6 +352,7 @@ def run_b200(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle.oracle import Oracle, lib
+        lib().orc_set_threads(host_threads())
         o = Oracle(logN=a.logN, L=28, dnum=4)
         per = cpu_rotations(o, l, a.cpu_sample)
         cores = int(lib().orc_num_threads())
@@ -353,8 +374,7 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": f"EvalRotate N=2^{a.logN} l={l} K={e.K} dnum={e.dnum} (BASELINE.json configs[1])", "batch_per_gpu": B,
-                       "parallelism": f"ciphertext-parallel x{world}", "ciphertexts_per_launch": G, "l2": f"inputs larger than L2 ({B * 2 * 2 * l * N * 8 / 1e6:.0f} MB touched per step)"},
+            "config": workload_config(a.logN, l, e.K, e.dnum, B, G, world, N),
             "roofline": {"bound": "hbm", "kernel": "ntt pass pair (ntt_column_kernel + ntt_chunk_kernel)", "achieved": ntt_gbs, "peak": peak,
                          "unit": "GB/s", "frac": ntt_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ntt_bytes * G, "avg_launch_ms": ntt_ms * G,
@@ -383,47 +403,104 @@ def run_b200(a):
 
 
 def forward_cpu_estimate(a, led, K, alpha):
-    """Same-host CPU time of the forward's key switches (SURVEY 8(d) "stratified sample of the ledger"): the oracle's EvalRotate is
-    timed at four limb counts on the forward's ring and every rotate@l / mul_relin@l row of the op ledger is charged the time
-    interpolated (linearly in the algorithmic bytes of a key switch) for its l.  Additions, plaintext products, rescales and
-    encodings are NOT charged, so the estimate is a lower bound of the CPU time and the ratio a lower bound of the speed-up."""
+    """Same-host CPU time of one forward, anchored on REAL runs of the CPU restatement: every operation type of the op ledger
+    (EvalRotate, EvalMult + relinearisation, ct x pt, ct + ct, rescale) is timed by oracle/ckks_oracle.c (OpenMP, all host cores)
+    at four limb counts of the forward's ring, and every ledger row (op @ l, count) is charged the time interpolated linearly in
+    l for its own l.  `coverage` is the fraction of the ledger's algorithmic bytes whose operation type was timed this way
+    (untimed: the plaintext-weighted sums of the encrypted E / F projection, and the host-side encodings, which the ledger does
+    not carry at all) -- so the figure is still a lower bound, but no longer an extrapolation from key switches alone."""
     from oracle.oracle import Oracle, lib
+    lib().orc_set_threads(host_threads())
     o = Oracle(logN=a.forward_logn, L=28, dnum=4)
-    N = 1 << a.forward_logn
-    pts = []
-    for l in (28, 21, 14, 7):
-        pts.append((algorithmic_bytes_rotate(N, l, K, alpha), cpu_rotations(o, l, 3, seed=l)))
-    xs = np.array([p[0] for p in pts], float); ys = np.array([p[1] for p in pts], float)
-    slope, icpt = np.polyfit(xs, ys, 1)
-    total, n_ks = 0.0, 0
-    for key, (n, _) in led.items():
+    rng = np.random.default_rng(5)
+    levels = (28, 21, 14, 7)
+
+    def rand(l):
+        return np.stack([rng.integers(0, int(o.moduli[m]), o.N, dtype=np.uint64) for m in range(l)])
+
+    evk = rng.integers(0, 1 << 50, (o.dnum, 2, o.L + o.K, o.N), dtype=np.uint64)
+    g = o.galois(1)
+
+    def timed(fn, reps):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    sampled = {}
+    for l in levels:
+        ct, ct2, pt = np.stack([rand(l), rand(l)]), np.stack([rand(l), rand(l)]), rand(l)
+        idx = list(range(l))
+        sampled[l] = {
+            "rotate": timed(lambda: o.rotate(ct, g, evk), 3),
+            "mul_relin": timed(lambda: o.mul_relin(ct, ct2, evk), 2),
+            "mul_plain": timed(lambda: o.mul_plain(ct, pt), 5),
+            "add": timed(lambda: (o.add(ct[0], ct2[0], idx), o.add(ct[1], ct2[1], idx)), 5),
+            "rescale": timed(lambda: (o.rescale(ct[0]), o.rescale(ct[1])), 2) if l >= 2 else 0.0,
+        }
+    fits = {}
+    for op in ("rotate", "mul_relin", "mul_plain", "add", "rescale"):
+        fits[op] = np.polyfit(np.array(levels, float), np.array([sampled[l][op] for l in levels], float), 1)
+    total, per_op, timed_bytes, all_bytes, n_ops = 0.0, {}, 0.0, 0.0, 0
+    for key, (n, nbytes) in led.items():
         op, _, l = key.partition("@")
-        if op in ("rotate", "mul_relin"):
-            total += n * max(0.0, slope * algorithmic_bytes_rotate(N, int(l), K, alpha) + icpt)
-            n_ks += n
+        all_bytes += nbytes
+        if op not in fits:
+            continue
+        t = n * max(0.0, float(np.polyval(fits[op], float(l))))
+        total += t
+        per_op[op] = per_op.get(op, 0.0) + t
+        timed_bytes += nbytes
+        n_ops += n
     cores = int(lib().orc_num_threads())
-    return {"seconds_per_sample_lower_bound": float(total), "key_switches": n_ks, "cores": cores, "kind": "port",
-            "sampled": {str(l): round(t * 1e3, 2) for l, (_, t) in zip((28, 21, 14, 7), pts)}, "sampled_unit": "ms per EvalRotate at l limbs",
-            "method": "oracle/ckks_oracle.c EvalRotate (OpenMP, all host cores) timed at l = 28, 21, 14, 7 on the forward's ring; "
-                      "each rotate / mul_relin row of the op ledger charged the interpolated time; other ops not charged"}
+    return {"seconds_per_sample_lower_bound": float(total), "operations_charged": n_ops, "coverage": timed_bytes / max(all_bytes, 1.0),
+            "seconds_by_operation": {k: round(v, 3) for k, v in per_op.items()}, "cores": cores, "kind": "port",
+            "sampled_ms": {str(l): {k: round(v * 1e3, 3) for k, v in sampled[l].items()} for l in levels},
+            "method": "oracle/ckks_oracle.c (OpenMP, all host cores) run for every ledger operation type at l = 28, 21, 14, 7 on the forward's ring; "
+                      "each ledger row charged the time interpolated for its l; coverage = share of the ledger's algorithmic bytes timed; "
+                      "OpenFHE-equivalent CPU restatement, not OpenFHE"}
+
+
+def _quiet_stdout():
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)                       # the controller prints the reference's progress messages on stdout
+    return devnull, saved
+
+
+FORWARD_CONFIGS = [   # BASELINE.json configs 3 / 4 as SURVEY.md section 8(d) shapes them: name, classes, S, E/F projection under encryption
+    ("config 3: IMDB-shaped (2 classes, S=256), client-projected E/F", 2, 256, False),
+    ("config 3: IMDB-shaped (2 classes, S=256), E/F projection under encryption", 2, 256, True),
+    ("config 4: BBC-shaped (5 classes, S=200), all bootstraps", 5, 200, False),
+    ("config 4: 20NG-shaped (20 classes, S=256), all bootstraps", 20, 256, False),
+]
 
 
 def run_forward(a, local, rank, world, torch, dist):
     """BASELINE.json's first metric: encrypted Linformer forward, seconds/sample and samples/s, at the reference CKKS
-    parameters (N=2^15, 28 limbs, 2^14 slots) through libflhost.so (FHEController + the main.cpp pipeline).  Each rank
-    evaluates its own synthetic sample (sample-parallel, no collective); samples/s = ranks / max-over-ranks seconds."""
+    parameters (N=2^15, 28 limbs, 2^14 slots) through libflhost.so (FHEController + the main.cpp pipeline).
+      * headline: SURVEY Config 1 shape (8 classes, S = --forward-rows = 200), each rank its own sample;
+      * s129: the circuit's minimum S (round 1's figure);  configs: the Config 3 / 4 shapes;  n16: the commented-out ring;
+      * batch: BASELINE config 5 -- a batch of samples sharded over the ranks (shard.my_units), one resident set of controllers per
+        GPU in throughput mode (--forward-in-flight forwards at a time), logits gathered on rank 0 (shard.gather_logits);
+        samples/s = samples of ALL ranks / max-over-ranks wall time."""
+    import queue
     import tempfile
-    from fhe_linformer_b200 import host, synth
+    from fhe_linformer_b200 import host, shard, synth
     root = tempfile.mkdtemp(prefix="flb200_bench_%d_" % rank)
     model = synth.make_model(n_classes=8)
     sample = synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 1 + rank)
     dirs = synth.write_files(root, model, sample)
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)                       # the controller prints the reference's progress messages on stdout
+    in_flight = max(1, a.forward_in_flight)
+    cache_gb = max(16, 120 // in_flight)      # block-cache cap per controller: a context parameter (fl_ctx_set_cache_bytes)
+    devnull, saved = _quiet_stdout()
     try:
-        fc = host.FHEController(device=local, root=root).generate(log_ring=0 if a.forward_logn == 15 else a.forward_logn)
-        fc.forward(dirs, dead_work=True)      # warm-up: mask / weight encodings, allocator pool, lazy rotation keys
+        t_k = time.perf_counter()
+        fc = host.FHEController(device=local, root=root, cache_gb=cache_gb).generate(log_ring=0 if a.forward_logn == 15 else a.forward_logn)
+        keygen_s = time.perf_counter() - t_k
+        key_gb = fc.rotation_key_bytes() / 1e9
+        fc.forward(dirs, dead_work=True)      # warm-up: mask / weight encodings, allocator pool (all keys were generated above)
         fc.ckks.ledger(True); fc.ckks.ledger_reset()
         runs = []
         for rep in range(3):                  # three timed samples: shared boxes show +-20 % run-to-run noise; the median is reported
@@ -441,39 +518,69 @@ def run_forward(a, local, rank, world, torch, dist):
             fc.forward(dirs, dead_work=False)
             lean_runs.append(time.perf_counter() - t1)
         lean = sorted(lean_runs)[1]
-        conc = None
-        if a.forward_in_flight > 1:
-            # throughput mode for batches of samples (BASELINE config 5): several forwards in flight on one GPU, one controller
-            # (engine + stream + keys) per host thread; the kernels of one fill the gaps the small-batch stages of another leave
-            import threading
-            cap_before = os.environ.get("FLK_CACHE_GB")
-            os.environ["FLK_CACHE_GB"] = str(max(16, 100 // a.forward_in_flight))    # block-cache cap of the extra controllers (default 96 GB each)
-            ctl = [(fc, dirs)]
-            for t in range(1, a.forward_in_flight):
-                root_t = tempfile.mkdtemp(prefix="flb200_bench_%d_%d_" % (rank, t))
-                dirs_t = synth.write_files(root_t, model, synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 101 * t + rank))
-                fc_t = host.FHEController(device=local, root=root_t).generate()
-                fc_t.forward(dirs_t, dead_work=True)
-                ctl.append((fc_t, dirs_t))
-            reps_c = 3
-            def work(c, d):
-                for _ in range(reps_c):
-                    c.forward(d, dead_work=True)
-            th = [threading.Thread(target=work, args=cd) for cd in ctl]
-            tc = time.perf_counter()
-            for x in th: x.start()
-            for x in th: x.join()
-            conc_dt = time.perf_counter() - tc
-            conc = {"in_flight": a.forward_in_flight, "samples": a.forward_in_flight * reps_c, "seconds": conc_dt}
-            for c, _d in ctl[1:]:
-                c.close()
-            if cap_before is None:
-                os.environ.pop("FLK_CACHE_GB", None)
-            else:
-                os.environ["FLK_CACHE_GB"] = cap_before
+
+        def one_shape(classes, S_rows, encp, seed):
+            m = synth.make_model(n_classes=classes)
+            d = synth.write_files(tempfile.mkdtemp(prefix="flb200_cfg_%d_" % rank), m, synth.make_sample(m, S_rows - 1, seed=seed))
+            fc.forward(d, dead_work=True, encrypted_projection=encp)
+            ts = []
+            for _ in range(2):
+                tq = time.perf_counter()
+                lg, _, _ = fc.forward(d, dead_work=True, encrypted_projection=encp)
+                ts.append(time.perf_counter() - tq)
+            return min(ts), int(np.argmax(lg[:classes]))
+
+        s129 = None
+        if a.forward_rows != 129:
+            t129, c129 = one_shape(8, 129, False, 20261018 + 1 + rank)
+            s129 = {"seconds_per_sample": t129, "rows_S": 129, "predicted_class": c129, "note": "the circuit's minimum S (round 1's headline shape)"}
+        cfgs = []
+        if not a.no_forward_configs and rank == 0:
+            for name, ncls, S_rows, encp in FORWARD_CONFIGS:
+                tc, cc = one_shape(ncls, S_rows, encp, 3000 + S_rows + ncls)
+                cfgs.append({"name": name, "classes": ncls, "rows_S": S_rows, "encrypted_projection": encp, "seconds_per_sample": tc, "predicted_class": cc})
+
+        # ---- BASELINE config 5: a batch of samples, sample-parallel over the ranks, throughput mode on every GPU ----
+        total = a.samples if a.samples > 0 else 8 * world
+        mine = list(shard.my_units(total, rank, world))
+        wdir = dirs["weights"]
+        jobs = []
+        for i in mine:
+            sd = os.path.join(root, "batch", str(i))
+            smp = synth.make_sample(model, a.forward_rows - 1, seed=20261018 + 1000 + i)
+            synth.write_sample_files(os.path.join(sd, "input"), os.path.join(sd, "tokens"), smp)
+            jobs.append((i, {"weights": wdir, "input": os.path.join(sd, "input"), "tokens": os.path.join(sd, "tokens")}))
+        ctl = [fc]
+        for t in range(1, min(in_flight, max(1, len(jobs)))):
+            root_t = tempfile.mkdtemp(prefix="flb200_bench_%d_%d_" % (rank, t))
+            fc_t = host.FHEController(device=local, root=root_t, cache_gb=cache_gb).generate()
+            fc_t.forward(dirs, dead_work=True)            # warm-up of this controller (encodings, pool)
+            ctl.append(fc_t)
+        q = queue.Queue()
+        for j in jobs:
+            q.put(j)
+        got = {}
+
+        def work(c):
+            while True:
+                try:
+                    i, d = q.get_nowait()
+                except queue.Empty:
+                    return
+                got[i] = c.forward(d, dead_work=True)[0]
+
+        if world > 1:
+            dist.barrier()
+        th = [threading.Thread(target=work, args=(c,)) for c in ctl]
+        tb = time.perf_counter()
+        for x in th: x.start()
+        for x in th: x.join()
+        batch_dt = time.perf_counter() - tb
+        for c in ctl[1:]:
+            c.close()
         fc.close()
         n16 = None
-        if a.forward_logn == 15 and not a.no_forward_n16:
+        if a.forward_logn == 15 and not a.no_forward_n16 and rank == 0:
             # the same sample at the ring the reference leaves commented out (F.cpp:12): 2^14 slots become sparse packing
             fc16 = host.FHEController(device=local, root=root).generate(log_ring=16)
             fc16.forward(dirs, dead_work=True)
@@ -485,21 +592,34 @@ def run_forward(a, local, rank, world, torch, dist):
     finally:
         os.dup2(saved, 1)
         os.close(devnull); os.close(saved)
-    t = torch.tensor([dt, lean, conc["seconds"] if conc else 0.0], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dt, lean, batch_dt], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt, lean = float(t[0].item()), float(t[1].item())
-    if conc:
-        conc = {"in_flight_per_gpu": conc["in_flight"], "samples_per_s": world * conc["samples"] / float(t[2].item()),
-                "seconds_per_sample_per_stream": float(t[2].item()) / (conc["samples"] / conc["in_flight"]),
-                "note": "throughput mode: that many forwards in flight per GPU (one controller per host thread); latency per sample rises accordingly"}
+    dt, lean, batch_worst = float(t[0].item()), float(t[1].item()), float(t[2].item())
+    # the only data that leaves a rank: its samples' logits (padded to the largest share)
+    per_rank = max(len(shard.my_units(total, r, world)) for r in range(world))
+    mat = np.full((per_rank, 20), np.nan)
+    for k, i in enumerate(mine):
+        mat[k] = got[i]
+    gathered = shard.gather_logits(mat, device="cuda")
+    classes = [int(np.argmax(row[:8])) for m_ in gathered for row in m_ if not np.isnan(row[0])]
+    batch = {"samples": total, "samples_per_gpu": [len(shard.my_units(total, r, world)) for r in range(world)], "rows_S": a.forward_rows,
+             "in_flight_per_gpu": len(ctl), "seconds": batch_worst, "samples_per_s": total / batch_worst, "logits_gathered": len(classes),
+             "predicted_class_histogram": {str(c): classes.count(c) for c in sorted(set(classes))},
+             "block_cache_GB_per_controller": cache_gb,
+             "note": "BASELINE config 5 (named size: 256 samples, --samples 256): samples sharded over the ranks (shard.my_units), resident "
+                     "controllers in throughput mode, logits gathered on rank 0; samples/s = all samples / max-over-ranks wall time"}
     rot = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
     alg = sum(b for _, b in led.values())
     return {"seconds_per_sample": dt, "samples_per_s": world / dt, "rows_S": S, "ring": "N=2^%d, 28 limbs, dnum 4, 2^14 slots" % a.forward_logn,
+            "shape": "SURVEY.md Config 1: 8 classes, S = %d rows (CLS + %d tokens), d = 128, k = 32, FFN 512" % (S, S - 1),
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
-            "n16": n16, "throughput_mode": conc, "_ledger": led,
+            "s129": s129, "configs": cfgs, "n16": n16, "batch": batch,
+            "keys": {"rotation_keys_GB": key_gb, "context_and_key_generation_s": keygen_s,
+                     "note": "every rotation key (listed + hoisted-ladder + tree indices) is generated before the first forward; none inside a timed region"},
+            "_ledger": led,
             "note": "text files -> encode/encrypt -> encoder1 -> pooler -> classifier -> decrypt, wall clock incl. host encode; "
                     "lean = same logits without the operations main.cpp issues but never reads"}
 

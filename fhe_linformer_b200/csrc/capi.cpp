@@ -113,6 +113,7 @@ uint32_t fl_galois_for_rotation(fl_ctx* c, int k) { return c->eng->P.galois_for_
 uint32_t fl_galois_conj(fl_ctx* c) { return c->eng->P.galois_conj(); }
 void* fl_ctx_stream(fl_ctx* c) { return (void*)c->eng->stream; }
 int fl_sync(fl_ctx* c) { FL_TRY(c->eng->sync()) }
+int fl_ctx_set_cache_bytes(fl_ctx* c, uint64_t bytes) { FL_TRY(c->eng->set_cache_cap((size_t)bytes)) }
 
 int fl_dev_alloc(fl_ctx* c, size_t words, uint64_t** out) { FL_TRY(*out = c->eng->alloc(words)) }
 int fl_dev_free(fl_ctx* c, uint64_t* p) { FL_TRY(c->eng->release(p)) }

@@ -36,7 +36,7 @@ Engine::Engine(const ParamSpec& spec, int device) : P(spec) {
     uint64_t keep = ~0ull;
     FLK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 
-    if (const char* ev = std::getenv("FLK_CACHE_GB")) cache_cap_bytes_ = (size_t)std::atol(ev) << 30;
+    if (const char* ev = std::getenv("FLK_CACHE_GB")) cache_cap_bytes_ = (size_t)std::atol(ev) << 30;   // start-up default only; fl_ctx_set_cache_bytes is the interface
     if (const char* ev = std::getenv("FLK_L2_BUDGET_MB")) l2_budget_bytes = std::atol(ev) << 20;   // tuning knob (bench sweeps it)
     const int Tn = P.T, N = P.N;
     {   // twiddles interleaved with their Shoup companions so one 16-byte load fetches both

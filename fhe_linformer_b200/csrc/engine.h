@@ -105,6 +105,9 @@ public:
     size_t evk_words() const { return (size_t)P.dnum * 2 * P.T * P.N; }
 
     void trim_cache(size_t keep_bytes);
+    // block-cache cap (a context parameter: fl_ctx_set_cache_bytes); several controllers on one GPU share its 180 GB
+    void set_cache_cap(size_t bytes) { cache_cap_bytes_ = bytes; if (cached_bytes_ > cache_cap_bytes_) trim_cache(cache_cap_bytes_ / 8 * 7); }
+    size_t cache_cap() const { return cache_cap_bytes_; }
     long pool_allocs = 0, cache_trims = 0;               // allocator statistics (fl_ctx_info slots 5-7)
     size_t cached_bytes() const { return cached_bytes_; }
 
@@ -119,7 +122,7 @@ private:
     unsigned host_next_ = 0;
     std::map<size_t, std::vector<u64*>> free_blocks_;    // exact-size cache in front of the stream-ordered pool
     std::unordered_map<u64*, size_t> block_size_;
-    size_t cached_bytes_ = 0, cache_cap_bytes_ = (size_t)96 << 30;   // of the 180 GB; FLK_CACHE_GB overrides
+    size_t cached_bytes_ = 0, cache_cap_bytes_ = (size_t)96 << 30;   // of the 180 GB; set_cache_cap() / fl_ctx_set_cache_bytes
     std::vector<void*> owned_;
     template <class V> V* to_device(const std::vector<V>& h);
     std::unordered_map<int, KsLevel> ks_;

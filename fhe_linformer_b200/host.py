@@ -32,6 +32,8 @@ def load_host_library():
     L.flh_new.restype = vp; L.flh_new.argtypes = [ci, C.c_ulonglong]
     L.flh_free.argtypes = [vp]
     L.flh_native.restype = vp; L.flh_native.argtypes = [vp]
+    L.flh_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    L.flh_rotation_key_bytes.restype = C.c_double; L.flh_rotation_key_bytes.argtypes = [vp]
     L.flh_generate.argtypes = [vp, ci, vp, ci, ci, ci]
     L.flh_load.argtypes = [vp, C.c_char_p, ci]
     L.flh_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
@@ -65,13 +67,22 @@ class _Borrowed(CKKS):
 class FHEController:
     """The reference's FHEController (src/FHEController.h:22-162) on the B200 engine."""
 
-    def __init__(self, device=0, key_seed=0, root=None):
+    def __init__(self, device=0, key_seed=0, root=None, **options):
+        """options: cache_gb, auto_rotation_keys, batch_rows, hoist_ladders, max_rows_per_batch (host/FHEController.h)."""
         self.hl = load_host_library()
         if root is not None:
             os.environ["FHE_LINFORMER_ROOT"] = root
         self.root = root
         self.h = C.c_void_p(self.hl.flh_new(device, key_seed))
         self.ckks = None
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def set_option(self, name, value):
+        self._ck(self.hl.flh_set_option(self.h, name.encode(), float(value)))
+
+    def rotation_key_bytes(self):
+        return float(self.hl.flh_rotation_key_bytes(self.h))
 
     def _ck(self, rc):
         if rc:

@@ -76,6 +76,8 @@ void FHEController::create(int log_ring, int depth, int digits, int first_bits, 
     if (const char* ov = std::getenv("FHE_LINFORMER_LOGN")) params_.logN = std::atoi(ov);   // test / bench override only
     if (const char* ov = std::getenv("FLK_MAX_ROWS")) max_rows_per_batch = std::max(1, std::atoi(ov));
     need(fl_ctx_create(&params_, device, &ctx_), "GenCryptoContext");
+    if (cache_gb > 0) need(fl_ctx_set_cache_bytes(ctx_, (uint64_t)(cache_gb * 1073741824.0)), "cache cap");
+    if (const char* ov = std::getenv("FLK_AUTO_ROTATION_KEYS")) auto_rotation_keys = ov[0] == '1';
 }
 
 // reference: F.cpp:3-90
@@ -138,6 +140,7 @@ void FHEController::load_context(bool verbose) {
     params_.logN = cf.logN; params_.L = cf.L; params_.dnum = cf.dnum; params_.first_bits = cf.first_bits; params_.scale_bits = cf.scale_bits;
     params_.aux_bits = cf.aux_bits; params_.sparse_h = cf.sparse_h;
     need(fl_ctx_create(&params_, device, &ctx_), "DeserializeFromFile(crypto-context)");
+    if (cache_gb > 0) need(fl_ctx_set_cache_bytes(ctx_, (uint64_t)(cache_gb * 1073741824.0)), "cache cap");
     if (fl_keys_load(ctx_, key_path("public-key.txt").c_str())) die("I cannot read serialized data from public-key.txt");
     if (fl_keys_load(ctx_, key_path("secret-key.txt").c_str())) die("I cannot read serialized data from secret-key.txt");
     if (!file_exists(key_path("mult-keys.txt"))) die("Cannot read serialization from mult-keys.txt");

@@ -154,6 +154,7 @@ public:
     // =====================================================================================================================
     int device = 0;                               // CUDA device of this controller: one context per GPU
     unsigned long long key_seed = 0;              // 0: operating-system randomness (production); non-zero: reproducible TEST keys
+    double cache_gb = 0;                          // device block-cache cap of this controller's context in GB (0: engine default, 96)
     bool auto_rotation_keys = false;              // false: rotate() on an index without a key fails, as OpenFHE's EvalRotate does
     bool batch_rows = true;                       // independent rows share kernel launches (FHEController.cpp "row batching")
     bool hoist_ladders = true;                    // extra rotation keys (fl_rotsum_rotations): ladders take up to four doubling steps per hoisted key switch

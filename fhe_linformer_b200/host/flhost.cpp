@@ -61,6 +61,19 @@ void flh_free(flh_controller* c) {
     delete c;
 }
 fl_ctx* flh_native(flh_controller* c) { return c->fc.native(); }
+int flh_set_option(flh_controller* c, const char* name, double value) {
+    return guarded([&] {
+        const std::string n = name;
+        FHEController& fc = c->fc;
+        if (n == "cache_gb") { fc.cache_gb = value; if (fc.native() && value > 0 && fl_ctx_set_cache_bytes(fc.native(), (uint64_t)(value * 1073741824.0))) throw std::runtime_error(fl_last_error()); }
+        else if (n == "auto_rotation_keys") fc.auto_rotation_keys = value != 0;
+        else if (n == "batch_rows") fc.batch_rows = value != 0;
+        else if (n == "hoist_ladders") fc.hoist_ladders = value != 0;
+        else if (n == "max_rows_per_batch") fc.max_rows_per_batch = std::max(1, (int)value);
+        else throw std::invalid_argument("flh_set_option: unknown option " + n);
+    });
+}
+double flh_rotation_key_bytes(flh_controller* c) { return c->fc.native() ? c->fc.rotation_key_bytes() : 0.0; }
 
 int flh_generate(flh_controller* c, int log_ring, const int* rotations, int n_rot, int bootstrap_slots, int serialize) {
     return guarded([&] {

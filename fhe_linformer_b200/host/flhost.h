@@ -17,6 +17,9 @@ const char* flh_last_error(void);
 flh_controller* flh_new(int device, unsigned long long key_seed);
 void flh_free(flh_controller* c);
 fl_ctx* flh_native(flh_controller* c);
+/* backend options of host/FHEController.h: cache_gb, auto_rotation_keys, batch_rows, hoist_ladders, max_rows_per_batch */
+int flh_set_option(flh_controller* c, const char* name, double value);
+double flh_rotation_key_bytes(flh_controller* c);   /* device memory held by the automorphism keys */
 /* FHEController::generate_context(serialize) + generate_bootstrapping_and_rotation_keys (main.cpp:82-85);
  * log_ring = 0 keeps the reference's 2^15 */
 int flh_generate(flh_controller* c, int log_ring, const int* rotations, int n_rot, int bootstrap_slots, int serialize);

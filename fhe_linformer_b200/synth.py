@@ -89,11 +89,18 @@ def write_files(root, model, sample):
     w("pooler_dense_bias.txt", model["bp"])
     w("fcLinear_0_weight.txt", model["Wc"])
     w("fcLinear_0_bias.txt", np.concatenate([model["bc"], np.zeros(D - MAX_CLASSES)]))   # read as a 128-vector (F.cpp:651-672)
-    for i in range(K_PROJ):
-        _write(os.path.join(ind, "XE_%d.txt" % i), sample["XE"][i])
-        _write(os.path.join(ind, "XF_%d.txt" % i), sample["XF"][i])
-    for f in os.listdir(tok):
-        os.remove(os.path.join(tok, f))
-    for i, row in enumerate(sample["tokens"]):
-        _write(os.path.join(tok, "input_%d.txt" % i), row)
+    write_sample_files(ind, tok, sample)
     return {"weights": wd, "input": ind, "tokens": tok}
+
+
+def write_sample_files(input_dir, tokens_dir, sample):
+    """The per-sample files only (../input/X{E,F}_i.txt M:161,166 and <input_folder>/input_i.txt M:172): a batch of samples shares
+    one weights directory."""
+    os.makedirs(input_dir, exist_ok=True); os.makedirs(tokens_dir, exist_ok=True)
+    for i in range(K_PROJ):
+        _write(os.path.join(input_dir, "XE_%d.txt" % i), sample["XE"][i])
+        _write(os.path.join(input_dir, "XF_%d.txt" % i), sample["XF"][i])
+    for f in os.listdir(tokens_dir):
+        os.remove(os.path.join(tokens_dir, f))
+    for i, row in enumerate(sample["tokens"]):
+        _write(os.path.join(tokens_dir, "input_%d.txt" % i), row)

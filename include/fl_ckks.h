@@ -50,6 +50,9 @@ uint32_t fl_galois_for_rotation(fl_ctx* c, int k);   /* FindAutomorphismIndex2nC
 uint32_t fl_galois_conj(fl_ctx* c);
 void* fl_ctx_stream(fl_ctx* c);                       /* cudaStream_t the engine launches on */
 int fl_sync(fl_ctx* c);
+/* Cap of the context's device block cache (freed operands are kept for reuse up to this many bytes; default 96 GB of the 180 GB).
+ * A context parameter: lower it when several contexts share one GPU (one controller per host thread). */
+int fl_ctx_set_cache_bytes(fl_ctx* c, uint64_t bytes);
 
 /* ---- device buffers (HBM-resident operands) ---- */
 int fl_dev_alloc(fl_ctx* c, size_t words, uint64_t** out);

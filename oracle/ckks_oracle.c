@@ -188,6 +188,14 @@ void orc_info(const orc_ctx* c, int* info) { info[0] = c->logN; info[1] = c->L; 
 void orc_moduli(const orc_ctx* c, u64* out) { memcpy(out, c->q, 8 * (c->L + c->K)); }
 void orc_roots(const orc_ctx* c, u64* out) { memcpy(out, c->psi, 8 * (c->L + c->K)); }
 void orc_scale_factors(const orc_ctx* c, double* sf) { memcpy(sf, c->sf, 8 * c->L); }
+/* bench.py's reference arm runs under torch.distributed.run, which exports OMP_NUM_THREADS=1: the thread count is set explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -87,6 +87,7 @@ void orc_encrypt(const orc_ctx* c, uint64_t seed, uint64_t* ct, const uint64_t* 
 void orc_decrypt(const orc_ctx* c, uint64_t* pt, const uint64_t* ct, const uint64_t* sk_eval, int l, int ncomp);
 
 int orc_num_threads(void);
+void orc_set_threads(int n);
 #ifdef __cplusplus
 }
 #endif

@@ -61,7 +61,7 @@ def lib():
             "orc_encode": (None, [vp, u64p, f64p, ci, dbl, ci]), "orc_encode_coeffs": (None, [vp, i64p, f64p, ci, dbl]),
             "orc_decode": (None, [vp, f64p, u64p, ci, dbl, ci]),
             "orc_encrypt": (None, [vp, u64, u64p, u64p, u64p, ci]), "orc_decrypt": (None, [vp, u64p, u64p, u64p, ci, ci]),
-            "orc_num_threads": (ci, []),
+            "orc_num_threads": (ci, []), "orc_set_threads": (None, [ci]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name); f.restype = res; f.argtypes = args
