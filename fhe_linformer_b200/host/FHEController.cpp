@@ -195,9 +195,9 @@ vector<int> FHEController::derived_rotations(const vector<int>& listed) const {
             for (int i = 0; i < nr && i < 64; ++i) if (!have.count(rots[i])) out.insert(rots[i]);
         }
     }
-    if (batch_rows) {   // shifted_sum trees: stride * 2^b for up to 256 rows (stride -1) / 8 containers (stride -512)
+    if (batch_rows) {   // shifted_sum trees: stride * 2^b for up to 256 rows (stride -1) / 32 tokens per container (stride -512)
         if (have.count(-1)) for (int b = 1; b < 8; ++b) if (!have.count(-(1 << b))) out.insert(-(1 << b));
-        if (have.count(-512)) for (int b = 1; b < 3; ++b) out.insert(-512 * (1 << b));
+        if (have.count(-512)) for (int b = 1; b < 5; ++b) if (!have.count(-512 * (1 << b))) out.insert(-512 * (1 << b));
     }
     return vector<int>(out.begin(), out.end());
 }
