@@ -518,6 +518,23 @@ def run_forward(a, local, rank, world, torch, dist):
             fc.forward(dirs, dead_work=False)
             lean_runs.append(time.perf_counter() - t1)
         lean = sorted(lean_runs)[1]
+        # packed mode: the same network with the FFN on 128 rows per ciphertext through BSGS diagonal products (north star)
+        fc.set_option("packed_keys", 1)
+        fc.forward(dirs, packed=True); fc.forward(dirs, packed=True)      # warm-up: plans, plaintext diagonals at their levels
+        fc.ckks.ledger(True); fc.ckks.ledger_reset()
+        packed_runs = []
+        for rep in range(3):
+            if rep == 1:
+                led_p = fc.ckks.ledger_dump(); fc.ckks.ledger(False)
+            tp0 = time.perf_counter()
+            logits_p, stages_p, _ = fc.forward(dirs, packed=True)
+            packed_runs.append(time.perf_counter() - tp0)
+        packed = {"seconds_per_sample": sorted(packed_runs)[1], "timed_samples_s": [round(x, 4) for x in packed_runs],
+                  "rotations": sum(n for k, (n, _) in led_p.items() if k.startswith("rotate@")),
+                  "max_logit_difference_to_faithful": float(np.abs(logits_p - logits).max()), "predicted_class": int(np.argmax(logits_p)),
+                  "stage_seconds": stages_p, "rotation_keys_GB": fc.rotation_key_bytes() / 1e9,
+                  "note": "LinformerForward::set_packed: rows stay wrapped-expanded (128 per ciphertext) between the two affines, every 128 x 128 FFN "
+                          "block is one FHEController::packed_linear (16 x 8 baby/giant steps, double hoisting); same logits up to CKKS noise"}
 
         def one_shape(classes, S_rows, encp, seed):
             m = synth.make_model(n_classes=classes)
@@ -554,28 +571,36 @@ def run_forward(a, local, rank, world, torch, dist):
         for t in range(1, min(in_flight, max(1, len(jobs)))):
             root_t = tempfile.mkdtemp(prefix="flb200_bench_%d_%d_" % (rank, t))
             fc_t = host.FHEController(device=local, root=root_t, cache_gb=cache_gb).generate()
+            fc_t.set_option("packed_keys", 1)
             fc_t.forward(dirs, dead_work=True)            # warm-up of this controller (encodings, pool)
+            fc_t.forward(dirs, packed=True); fc_t.forward(dirs, packed=True)
             ctl.append(fc_t)
-        q = queue.Queue()
-        for j in jobs:
-            q.put(j)
-        got = {}
 
-        def work(c):
-            while True:
-                try:
-                    i, d = q.get_nowait()
-                except queue.Empty:
-                    return
-                got[i] = c.forward(d, dead_work=True)[0]
+        def run_batch(use_packed):
+            q = queue.Queue()
+            for j in jobs:
+                q.put(j)
+            res = {}
 
-        if world > 1:
-            dist.barrier()
-        th = [threading.Thread(target=work, args=(c,)) for c in ctl]
-        tb = time.perf_counter()
-        for x in th: x.start()
-        for x in th: x.join()
-        batch_dt = time.perf_counter() - tb
+            def work(c):
+                while True:
+                    try:
+                        i, d = q.get_nowait()
+                    except queue.Empty:
+                        return
+                    res[i] = c.forward(d, packed=True)[0] if use_packed else c.forward(d, dead_work=True)[0]
+
+            if world > 1:
+                dist.barrier()
+            th = [threading.Thread(target=work, args=(c,)) for c in ctl]
+            tb = time.perf_counter()
+            for x in th: x.start()
+            for x in th: x.join()
+            return time.perf_counter() - tb, res
+
+        batch_dt, got = run_batch(False)
+        batch_packed_dt, got_packed = run_batch(True)
+        batch_agree = float(max(np.abs(got[i] - got_packed[i]).max() for i in got)) if got else 0.0
         for c in ctl[1:]:
             c.close()
         fc.close()
@@ -592,10 +617,12 @@ def run_forward(a, local, rank, world, torch, dist):
     finally:
         os.dup2(saved, 1)
         os.close(devnull); os.close(saved)
-    t = torch.tensor([dt, lean, batch_dt], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dt, lean, batch_dt, batch_packed_dt, packed["seconds_per_sample"], batch_agree], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt, lean, batch_worst = float(t[0].item()), float(t[1].item()), float(t[2].item())
+    dt, lean, batch_worst, batch_packed_worst = float(t[0].item()), float(t[1].item()), float(t[2].item()), float(t[3].item())
+    packed["seconds_per_sample"] = float(t[4].item())
+    packed["samples_per_s"] = world / packed["seconds_per_sample"]
     # the only data that leaves a rank: its samples' logits (padded to the largest share)
     per_rank = max(len(shard.my_units(total, r, world)) for r in range(world))
     mat = np.full((per_rank, 20), np.nan)
@@ -607,6 +634,7 @@ def run_forward(a, local, rank, world, torch, dist):
              "in_flight_per_gpu": len(ctl), "seconds": batch_worst, "samples_per_s": total / batch_worst, "logits_gathered": len(classes),
              "predicted_class_histogram": {str(c): classes.count(c) for c in sorted(set(classes))},
              "block_cache_GB_per_controller": cache_gb,
+             "packed": {"seconds": batch_packed_worst, "samples_per_s": total / batch_packed_worst, "max_logit_difference_to_faithful": float(t[5].item())},
              "note": "BASELINE config 5 (named size: 256 samples, --samples 256): samples sharded over the ranks (shard.my_units), resident "
                      "controllers in throughput mode, logits gathered on rank 0; samples/s = all samples / max-over-ranks wall time"}
     rot = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
@@ -616,7 +644,7 @@ def run_forward(a, local, rank, world, torch, dist):
             "rotations": rot, "algorithmic_GB": alg / 1e9, "achieved_GBps": alg / 1e9 / dt, "stage_seconds": stages,
             "lean_seconds_per_sample": lean, "predicted_class": int(np.argmax(logits)),
             "timed_samples_s": [round(r[0], 4) for r in runs], "lean_timed_samples_s": [round(x, 4) for x in sorted(lean_runs)],
-            "s129": s129, "configs": cfgs, "n16": n16, "batch": batch,
+            "packed": packed, "s129": s129, "configs": cfgs, "n16": n16, "batch": batch,
             "keys": {"rotation_keys_GB": key_gb, "context_and_key_generation_s": keygen_s,
                      "note": "every rotation key (listed + hoisted-ladder + tree indices) is generated before the first forward; none inside a timed region"},
             "_ledger": led,

@@ -109,7 +109,7 @@ class FHEController:
     def num_slots(self):
         d, n = C.c_int(), C.c_int(); self.hl.flh_info(self.h, C.byref(d), C.byref(n)); return n.value
 
-    def forward(self, dirs, token_limit=0, dead_work=True, classes=20, checkpoints=None, encrypted_projection=False, all_tokens=False):
+    def forward(self, dirs, token_limit=0, dead_work=True, classes=20, checkpoints=None, encrypted_projection=False, all_tokens=False, packed=False):
         """encoder1 -> pooler -> classifier -> decrypt (main.cpp:105-123) on the text files under `dirs`
         ({"weights", "input", "tokens"}).  Returns (logits, {stage: seconds}, S)."""
         logits = np.zeros(classes)
@@ -120,7 +120,7 @@ class FHEController:
                 checkpoints[name.decode()] = (np.ctypeslib.as_array(ptr, shape=(n,)).copy(), level)
         cb = CHECKPOINT_FN(sink) if checkpoints is not None else C.cast(None, CHECKPOINT_FN)
         self._ck(self.hl.flh_forward(self.h, dirs["weights"].encode(), dirs["input"].encode(), dirs["tokens"].encode(), token_limit,
-                                     (1 if dead_work else 0) | (2 if encrypted_projection else 0) | (4 if all_tokens else 0), classes, capi._ptr(logits), cb, None, names, len(names), capi._ptr(secs),
+                                     (1 if dead_work else 0) | (2 if encrypted_projection else 0) | (4 if all_tokens else 0) | (8 if packed else 0), classes, capi._ptr(logits), cb, None, names, len(names), capi._ptr(secs),
                                      C.byref(nt), C.byref(toks)))
         stage = dict(zip(names.value.decode().split("\n"), secs[:nt.value].tolist()))
         return logits, stage, toks.value

@@ -54,6 +54,8 @@ FHEController::~FHEController() {
 
 void FHEController::release_context() {
     mask_cache_.clear();
+    for (auto& kv : packed_) fl_lt_free(kv.second);
+    packed_.clear();
     if (ctx_) { fl_ctx_destroy(ctx_); ctx_ = nullptr; }
 }
 
@@ -200,6 +202,51 @@ vector<int> FHEController::derived_rotations(const vector<int>& listed) const {
         if (have.count(-512)) for (int b = 1; b < 5; ++b) if (!have.count(-512 * (1 << b))) out.insert(-512 * (1 << b));
     }
     return vector<int>(out.begin(), out.end());
+}
+
+/* ------------------------------------------------------------------ packed linear layers ------------------------------------------------------------------ */
+// In the wrapped-expanded layout a 128 x 128 weight acts on the block index: y[128 i + t] = sum_j W[j][i] x[128 j + t].  With
+// j = (i + k) mod 128 the source slot is (128 i + t) + 128 k modulo 16384 -- the slot vector wraps exactly where the block index
+// does -- so the layer is the sum over k < 128 of diag_k (x) rot(x, 128 k) with diag_k[128 i + t] = W[(i + k) mod 128][i]:
+// a diagonal matrix product, evaluated by Engine::linear_transform with 16 baby x 8 giant steps (double hoisting).
+namespace {
+fl_lt* plan_packed(fl_ctx* ctx, int slots, const std::function<double(int, int)>& weight, double scale) {
+    const int D = 128;
+    vector<int> shifts(D);
+    vector<double> re((size_t)D * slots, 0.0);
+    for (int k = 0; k < D; ++k) {
+        shifts[k] = D * k;
+        double* d = re.data() + (size_t)k * slots;
+        for (int i = 0; i < D; ++i) {
+            const double v = scale * weight((i + k) % D, i);
+            for (int t = 0; t < D; ++t) d[D * i + t] = v;
+        }
+    }
+    fl_lt* lt = nullptr;
+    if (fl_lt_create(ctx, shifts.data(), D, re.data(), nullptr, slots, -1, 0, &lt)) lbcrypto::fl_fail("packed linear layer: plan");
+    return lt;
+}
+}  // namespace
+
+Ctxt FHEController::packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale) {
+    if (num_slots != 128 * 128) throw std::invalid_argument("packed_linear: the wrapped-expanded layout needs 128 x 128 slots");
+    auto it = packed_.find(name);
+    if (it == packed_.end()) it = packed_.emplace(name, plan_packed(ctx_, num_slots, weight, scale)).first;
+    int rots[64];
+    const int nr = fl_lt_rotations(ctx_, it->second, rots, 64);
+    for (int i = 0; i < nr && i < 64; ++i) require_rotation_key(rots[i]);
+    fl_elem* e = nullptr;
+    need(fl_lt_apply(ctx_, it->second, x->handle(), &e), "packed linear layer");
+    return wrap(e);
+}
+
+void FHEController::generate_packed_keys() {
+    // the rotations depend on the diagonal pattern only (shifts 128 k, k < 128), not on the weights
+    fl_lt* probe = plan_packed(ctx_, num_slots, [](int, int) { return 1.0; }, 1.0);
+    int rots[64];
+    const int nr = fl_lt_rotations(ctx_, probe, rots, 64);
+    fl_lt_free(probe);
+    need(fl_gen_rot_keys(ctx_, rots, std::min(nr, 64)), "EvalRotateKeyGen (packed layers)");
 }
 
 double FHEController::rotation_key_bytes() const {

@@ -172,6 +172,13 @@ public:
     // out[o] = sum_t weights[o][t] * rows[t] (+ bias[o]): the Linformer E / F projection on the row ciphertexts
     Rows project_rows(const Rows& rows, const vector<vector<double>>& weights, const vector<Ptxt>& bias);
 
+    // ---- packed linear layers (BASELINE north star: BSGS diagonal ct x pt matrix product behind the Q/K/V/FFN linears) ----
+    // x holds up to 128 vectors in the wrapped-expanded layout (slot 128 j + t = element j of vector t, F.cpp:1070-1084);
+    // the result holds y_t = x_t W for every t in the same layout: ONE baby-step/giant-step transform over the 128 diagonals
+    // 128 k (fl_lt_apply, ~22 hoisted rotations) instead of one (x) + 7-step ladder per vector (F.cpp:869-883, 982-996).
+    // weight(j, i) = W[j][i] with y_i = sum_j x_j W[j][i]; `name` keys the cached plan (plaintext diagonals follow x's level).
+    Ctxt packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale = 1.0);
+    void generate_packed_keys();                                     // rotation keys of the packed transforms (before any packed forward)
     vector<int> derived_rotations(const vector<int>& listed) const;  // extra indices the batched / hoisted recipes use for a key list
     double rotation_key_bytes() const;                               // device memory held by automorphism keys
 
@@ -188,6 +195,7 @@ private:
     fl_params params_{};
     vector<uint32_t> level_budget = {4, 4};
     map<std::tuple<int, int, int, double, int>, Ptxt> mask_cache_;
+    map<string, fl_lt*> packed_;                                     // BSGS plans of the packed linear layers, by weight name
 };
 
 #endif  // FLB200_FHECONTROLLER_H

@@ -67,6 +67,7 @@ int flh_set_option(flh_controller* c, const char* name, double value) {
         FHEController& fc = c->fc;
         if (n == "cache_gb") { fc.cache_gb = value; if (fc.native() && value > 0 && fl_ctx_set_cache_bytes(fc.native(), (uint64_t)(value * 1073741824.0))) throw std::runtime_error(fl_last_error()); }
         else if (n == "auto_rotation_keys") fc.auto_rotation_keys = value != 0;
+        else if (n == "packed_keys") { if (value != 0) fc.generate_packed_keys(); }
         else if (n == "batch_rows") fc.batch_rows = value != 0;
         else if (n == "hoist_ladders") fc.hoist_ladders = value != 0;
         else if (n == "max_rows_per_batch") fc.max_rows_per_batch = std::max(1, (int)value);
@@ -104,6 +105,7 @@ int flh_forward(flh_controller* c, const char* weights_dir, const char* input_di
         fwd.set_dead_work((dead_work & 1) != 0);
         fwd.set_encrypted_projection((dead_work & 2) != 0);
         fwd.set_all_token_attention((dead_work & 4) != 0);
+        fwd.set_packed((dead_work & 8) != 0);
         if (sink) fwd.set_checkpoint_sink([&](const std::string& name, const std::vector<double>& v, int level) { sink(name.c_str(), v.data(), (int)v.size(), level, user); });
         const std::vector<double> z = fwd.run(classes);
         std::memcpy(logits, z.data(), sizeof(double) * z.size());

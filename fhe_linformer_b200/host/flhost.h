@@ -17,7 +17,8 @@ const char* flh_last_error(void);
 flh_controller* flh_new(int device, unsigned long long key_seed);
 void flh_free(flh_controller* c);
 fl_ctx* flh_native(flh_controller* c);
-/* backend options of host/FHEController.h: cache_gb, auto_rotation_keys, batch_rows, hoist_ladders, max_rows_per_batch */
+/* backend options of host/FHEController.h: cache_gb, auto_rotation_keys, batch_rows, hoist_ladders, max_rows_per_batch;
+ * packed_keys = 1 generates the rotation keys of the packed (BSGS) linear layers */
 int flh_set_option(flh_controller* c, const char* name, double value);
 double flh_rotation_key_bytes(flh_controller* c);   /* device memory held by the automorphism keys */
 /* FHEController::generate_context(serialize) + generate_bootstrapping_and_rotation_keys (main.cpp:82-85);
@@ -28,7 +29,8 @@ int flh_info(flh_controller* c, int* circuit_depth, int* num_slots);
 
 /* encoder1 -> pooler -> classifier -> decrypt (main.cpp:105-123).  timings: up to *n_timings (name, seconds) pairs. */
 /* dead_work bit 0: issue the operations main.cpp never reads; bit 1: evaluate the E / F projection under encryption (F1);
- * bit 2: the all-token attention circuit of main_2.cpp (F4) */
+ * bit 2: the all-token attention circuit of main_2.cpp (F4); bit 3: packed mode -- the FFN on 128 rows per ciphertext through
+ * BSGS diagonal matrix products (LinformerForward::set_packed) */
 int flh_forward(flh_controller* c, const char* weights_dir, const char* input_dir, const char* tokens_dir, int token_limit, int dead_work,
                 int classes, double* logits, flh_checkpoint_fn sink, void* user, char* timing_names, int names_cap, double* timing_seconds,
                 int* n_timings, int* tokens);

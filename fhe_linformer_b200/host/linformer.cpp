@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <filesystem>
+#include <tuple>
 
 namespace flh {
 
@@ -65,7 +66,7 @@ Ctxt LinformerForward::attend_cls(const std::vector<Ctxt>& rows, const std::vect
     const Ptxt bk = fc_.read_plain_repeated_input(layer("selfAttn_WK_bias.txt"));        // M:180
 
     // The reference projects every row to a query (M:182) and then uses row 0 only (M:196).
-    const std::vector<Ctxt> queries = fc_.matmulRE(dead_work_ ? rows : std::vector<Ctxt>{rows[0]}, wq, bq);
+    const std::vector<Ctxt> queries = fc_.matmulRE(dead_work_ && !packed_ ? rows : std::vector<Ctxt>{rows[0]}, wq, bq);
     const Ctxt keys = fc_.wrapUpRepeated(fc_.matmulRE(xe, wk, bk));                     // M:183-185
     checkpoint("query_cls", queries[0]);
     checkpoint("keys_wrapped", keys);
@@ -126,6 +127,13 @@ std::vector<Ctxt> LinformerForward::self_output(const Ctxt& cls_context, const s
     for (size_t i = 1; i < rows.size(); ++i) out.push_back(zero->Clone());               // M:222-224
     const Ptxt wo = fc_.read_plain_input(layer("selfAttn_WO_weight.txt"), level);        // M:231
     const Ptxt bo = fc_.read_plain_expanded_input(layer("selfAttn_WO_bias.txt"), level + 1);   // M:232
+    if (packed_) {
+        // packed mode: W_O on the one row that carries attention output; the other rows go on as the fresh inputs they are
+        // (the reference adds W_O (x) Enc(0) to each of them, M:222-239: the same plaintext values)
+        std::vector<Ctxt> res(rows.begin(), rows.end());
+        res[0] = fc_.add(fc_.add(fc_.matmulCR({cls_context}, wo, nullptr)[0], bo), rows[0]);
+        return res;
+    }
     if (dead_work_) {
         out = fc_.matmulCR(out, wo, nullptr);                                            // M:235
     } else {
@@ -143,19 +151,89 @@ std::vector<Ctxt> LinformerForward::self_output(const Ctxt& cls_context, const s
 std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh) {
     if (rows.size() <= 128 || rows.size() > 256) throw std::invalid_argument("the circuit packs rows as 128 + (S - 128): need 129 <= S <= 256");
     const std::vector<Ctxt> first(rows.begin(), rows.begin() + 128), rest(rows.begin() + 128, rows.end());
-    Ctxt w0 = fc_.wrapUpExpanded(first), w1 = fc_.wrapUpExpanded(rest);                  // M:307-308 / M:392-393
+    // packed mode builds the same two wrapped ciphertexts from position masks alone (no rotate(-1) chain)
+    Ctxt w0 = packed_ ? wrap_rows_packed(first, 0) : fc_.wrapUpExpanded(first);          // M:307-308 / M:392-393
+    Ctxt w1 = packed_ ? wrap_rows_packed(rest, 0) : fc_.wrapUpExpanded(rest);
     if (!refresh) return {w0, w1};
     const double s = (double)rows.size();
     const double f = scalar(layer("ffn_" + which + "_c0.txt")) + scalar(layer("ffn_" + which + "_c1.txt")) / std::sqrt(s) +
                      scalar(layer("ffn_" + which + "_c2.txt")) / s;                      // M:292-297
-    const Ptxt a = fc_.read_plain_repeated_input(layer("ffn_" + which + "_a.txt"), (int)w0->GetLevel(), f);       // M:311
-    const Ptxt b = fc_.read_plain_repeated_input(layer("ffn_" + which + "_b.txt"), (int)w0->GetLevel() + 1, f);   // M:312
-    w0 = fc_.add(fc_.mult(w0, a), b);                                                    // M:314-315
-    w1 = fc_.add(fc_.mult(w1, a), b);                                                    // M:316-317
+    // (in packed mode the second half consists of fresh rows only and sits at a shallower level than the first: each half
+    // gets the plaintexts of its own level; in the reference's flow both levels coincide)
+    auto affine = [&](const Ctxt& c) {
+        const Ptxt a = fc_.read_plain_repeated_input(layer("ffn_" + which + "_a.txt"), (int)c->GetLevel(), f);       // M:311
+        const Ptxt b = fc_.read_plain_repeated_input(layer("ffn_" + which + "_b.txt"), (int)c->GetLevel() + 1, f);   // M:312
+        return fc_.add(fc_.mult(c, a), b);
+    };
+    w0 = affine(w0);                                                                     // M:314-315
+    w1 = affine(w1);                                                                     // M:316-317
     checkpoint(which + "_0", w0);
     checkpoint(which + "_1", w1);
     const std::vector<Ctxt> fresh = fc_.per_row({w0, w1}, [&](const Ctxt& c) { return fc_.bootstrap(c); });   // M:319-320, as one batch
     return {fresh[0], fresh[1]};
+}
+
+// ---- packed mode --------------------------------------------------------------------------------------------------------------
+// Expanded rows (slot 128 j + i = x_t[j] for every i) -> wrapped-expanded (slot 128 j + t = x_t[j]): keep column t of row t.  The
+// reference gets there with one mask at column 0 and a rotate(-1) Horner chain (F.cpp:1070-1084); the masks at column t need no
+// rotation at all.  Row 0 of the first half comes out of the attention block at a deeper level than the fresh rows: the fresh
+// ones are summed first so that only one level alignment happens.
+Ctxt LinformerForward::wrap_rows_packed(const std::vector<Ctxt>& rows, int) {
+    std::vector<Ctxt> fresh;
+    for (size_t t = 1; t < rows.size(); ++t) fresh.push_back(fc_.mask_mod_n(rows[t], 128, (int)t, 0));
+    const Ctxt head = fc_.mask_mod_n(rows[0], 128, 0, 0);
+    if (fresh.empty()) return head;
+    return fc_.add(head, fresh.size() == 1 ? fresh[0] : fc_.add(fresh));
+}
+
+// FFN on the two wrapped-expanded halves, never leaving that layout: 128 -> 512 as four packed_linear transforms (the four
+// 128-column blocks of W0, scaled by 1/8), GELU and bootstrap on the 2 x 4 hidden ciphertexts as one batched operand, 512 -> 128 as
+// four packed_linear transforms summed.  Replaces unwrapExpanded + matmulRElarge + generate_containers + unwrapRepeatedLarge +
+// matmulCRlarge + wrapUpExpanded (M:325-393; ~100 S rotations) by 8 BSGS products per half (~22 hoisted rotations each).
+std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, const Ctxt& half1) {
+    const double gelu_scale = 1.0 / 8.0;                                                 // M:334
+    const int slots = fc_.num_slots;
+    const Ctxt x = fc_.pack({half0, half1});
+    const std::vector<double> b0 = utils::read_values_from_file(layer("ffn_Wffn_0_bias.txt"));   // 512 values (M:345)
+    if (b0.size() < 512) throw std::runtime_error("ffn_Wffn_0_bias.txt: expected 512 values");
+    std::vector<Ctxt> hidden;
+    for (int b = 0; b < 4; ++b) {
+        const std::string name = "ffn_W0_transposed_block_" + std::to_string(b);
+        std::vector<double> f;
+        auto weight = [&](int j, int i) {
+            if (f.empty()) { f = utils::read_values_from_file(w(name + ".txt")); if (f.size() < 128 * 128) throw std::runtime_error(name + ": expected 128 x 128 values"); }
+            return f[(size_t)128 * j + i];                                               // y = x . F  (M:338-341)
+        };
+        Ctxt u = fc_.packed_linear(x, w(name), weight, gelu_scale);                      // plan cached per weight FILE
+        std::vector<double> bias((size_t)slots);
+        for (int i = 0; i < 128; ++i)
+            for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b0[(size_t)128 * b + i] * gelu_scale;
+        hidden.push_back(fc_.add(u, fc_.encode(bias, (int)u->GetLevel() + 1, slots)));   // product rescaled lazily: bias one level lower
+    }
+    checkpoint("packed_hidden_block0", fc_.unpack(hidden[0])[0]);
+    // M:360-364 on all 2 x 4 hidden ciphertexts at once
+    const Ctxt act = fc_.bootstrap(fc_.eval_gelu_function(fc_.pack(hidden), -1, 1, gelu_scale, 119));
+    const std::vector<Ctxt> parts = fc_.unpack(act);                                     // [block b][half h] -> index 2 b + h
+    checkpoint("packed_gelu_block0", parts[0]);
+    lap("Intermediate");
+    Ctxt sum;
+    for (int b = 0; b < 4; ++b) {
+        const std::string name = "ffn_W2_block_" + std::to_string(b);
+        std::vector<double> f;
+        auto weight = [&](int j, int i) {
+            if (f.empty()) { f = utils::read_values_from_file(w(name + ".txt")); if (f.size() < 128 * 128) throw std::runtime_error(name + ": expected 128 x 128 values"); }
+            return f[(size_t)128 * i + j];                                               // y = F . x  (M:373-376)
+        };
+        const Ctxt y = fc_.packed_linear(fc_.pack({parts[2 * b], parts[2 * b + 1]}), w(name), weight, 1.0);
+        sum = b == 0 ? y : fc_.add(sum, y);
+    }
+    const std::vector<double> b2 = utils::read_values_from_file(layer("ffn_Wffn_2_bias.txt"));   // M:378
+    std::vector<double> bias((size_t)slots);
+    for (int i = 0; i < 128; ++i)
+        for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b2.at((size_t)i);
+    sum = fc_.add(sum, fc_.encode(bias, (int)sum->GetLevel() + 1, slots));
+    const std::vector<Ctxt> halves = fc_.unpack(sum);
+    return {halves[0], halves[1]};
 }
 
 // ---- FFN: 128 -> 512 (scaled by 1/8 so GELU's argument lies in [-1, 1]), GELU, bootstrap, 512 -> 128 (M:325-380) ----------
@@ -240,20 +318,27 @@ Ctxt LinformerForward::encoder() {
     checkpoint("affine1_refreshed_0", half0);
     const Ctxt residual0 = half0->Clone(), residual1 = half1->Clone();                   // M:322-323
 
-    const std::vector<Ctxt> ffn = feed_forward(half0, half1, tokens_);
-    checkpoint("ffn_row0", ffn[0]);
-    auto [o0, o1] = affine_and_refresh(ffn, "affine2", false);
+    Ctxt o0, o1;
+    if (packed_) {
+        lap("Self-Output");
+        std::tie(o0, o1) = feed_forward_packed(half0, half1);
+        checkpoint("packed_ffn_0", o0);
+    } else {
+        const std::vector<Ctxt> ffn = feed_forward(half0, half1, tokens_);
+        checkpoint("ffn_row0", ffn[0]);
+        std::tie(o0, o1) = affine_and_refresh(ffn, "affine2", false);
+    }
     o0 = fc_.add(o0, residual0);                                                         // M:395
     o1 = fc_.add(o1, residual1);                                                         // M:396
-    const double s = (double)ffn.size();
+    const double s = (double)tokens_;
     const double f2 = scalar(layer("ffn_affine2_c0.txt")) + scalar(layer("ffn_affine2_c1.txt")) / std::sqrt(s) + scalar(layer("ffn_affine2_c2.txt")) / s;   // M:398-403
     const Ptxt a2 = fc_.read_plain_repeated_input(layer("ffn_affine2_a.txt"), (int)o0->GetLevel(), f2);       // M:407
     const Ptxt b2 = fc_.read_plain_repeated_input(layer("ffn_affine2_b.txt"), (int)o1->GetLevel() + 1, f2);   // M:408
     o0 = fc_.add(fc_.mult(o0, a2), b2);                                                  // M:410,413
     o1 = fc_.add(fc_.mult(o1, a2), b2);                                                  // M:411,414
     checkpoint("affine2_0", o0);
-    std::vector<Ctxt> final0 = fc_.unwrapExpanded(o0, dead_work_ ? 128 : 1);             // M:416 (only element 0 is used)
-    if (dead_work_) (void)fc_.unwrapExpanded(o1, tokens_ - 128);                         // M:417
+    std::vector<Ctxt> final0 = fc_.unwrapExpanded(o0, dead_work_ && !packed_ ? 128 : 1);  // M:416 (only element 0 is used)
+    if (dead_work_ && !packed_) (void)fc_.unwrapExpanded(o1, tokens_ - 128);             // M:417
     checkpoint("encoder_out", final0[0]);
     lap("Output");
     return final0[0];                                                                    // M:424 (the caller may save() it, M:422)

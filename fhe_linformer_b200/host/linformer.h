@@ -41,6 +41,12 @@ public:
     // up to 128 queries packed by matmulScores(vector)), 1/x fitted on [-1, 190000], W_O bias on every row, tanh scale 1/18,
     // plaintext class mask -- SURVEY.md F4
     void set_all_token_attention(bool on) { all_tokens_ = on; }
+    // true: packed mode (BASELINE north star: BSGS diagonal ct x pt matmul behind the FFN linears).  Same network, same weights,
+    // same logits up to CKKS noise; the rows stay in the wrapped-expanded layout (128 rows per ciphertext) from the first affine
+    // to the second, each 128 x 128 weight block is ONE FHEController::packed_linear per half instead of a (x) + 7-step ladder per
+    // row, and the unwrap / container / re-wrap round trips between them (F.cpp:1086-1205) disappear: ~1 k rotations per forward
+    // instead of ~21 k at S = 200.  Needs FHEController::generate_packed_keys().
+    void set_packed(bool on) { packed_ = on; }
 
     Ctxt encoder();                       // main.cpp:145-425
     Ctxt pooler(const Ctxt& encoded);     // main.cpp:427-451
@@ -65,6 +71,8 @@ private:
     std::vector<Ctxt> self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows);
     std::pair<Ctxt, Ctxt> affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh);
     std::vector<Ctxt> feed_forward(const Ctxt& half0, const Ctxt& half1, int rows);
+    std::pair<Ctxt, Ctxt> feed_forward_packed(const Ctxt& half0, const Ctxt& half1);
+    Ctxt wrap_rows_packed(const std::vector<Ctxt>& rows, int first_position);
 
     FHEController& fc_;
     LinformerFiles files_;
@@ -73,6 +81,7 @@ private:
     bool dead_work_ = true;
     bool encrypted_projection_ = false;
     bool all_tokens_ = false;
+    bool packed_ = false;
     std::vector<Ctxt> attend_all(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
     std::vector<Ctxt> project(const std::vector<Ctxt>& rows, const std::string& which);
     int tokens_ = 0;

@@ -234,6 +234,13 @@ def _sim_tail(s, cp, model, out, S, tanh_scale):
     w2 = [s.plain(model["W2"][:, 128 * b:128 * (b + 1)]) for b in range(4)]
     ffn = s.matmulCRlarge(quads, w2, s.expanded(model["b2"]))
     cp["ffn_row0"] = ffn[0]
+    # what the packed mode of host/linformer.cpp (BSGS products on the wrapped-expanded layout) holds at its own checkpoints: the same
+    # values, 128 rows per ciphertext -- slot 128 i + t = entry i of row t of the first half
+    xm = halves[0].reshape(128, 128).T                                        # [t][j]
+    pre = (xm @ model["W0_T"][:, :128] + model["b0"][:128]) / 8.0             # hidden units 0..127, scaled as the circuit scales them
+    cp["packed_hidden_block0"] = pre.T.reshape(-1)
+    cp["packed_gelu_block0"] = s.eval_gelu_function(pre.T.reshape(-1), -1, 1, 1 / 8., 119)
+    cp["packed_ffn_0"] = s.wrapUpExpanded(ffn[:128])
     # residual + affine2 (M:382-417)
     o = [s.wrapUpExpanded(ffn[:128]) + halves[0], s.wrapUpExpanded(ffn[128:]) + halves[1]]
     f2 = model["c2"][0] + model["c2"][1] / math.sqrt(S) + model["c2"][2] / S

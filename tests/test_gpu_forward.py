@@ -56,6 +56,34 @@ def test_lean_mode_gives_the_same_logits(setup):
     assert np.abs(lean - full).max() < 4e-4
 
 
+def test_packed_mode_matches_slot_simulator(setup):
+    """Packed mode (BASELINE north star: BSGS diagonal ct x pt matmul behind the FFN linears): 128 rows per ciphertext from the
+    first affine to the second, FHEController::packed_linear for every 128 x 128 weight block.  Same checkpoints, same logits
+    (<= 1e-3, same class) as the slot simulator of the reference circuit, with an order of magnitude fewer rotations."""
+    from oracle import linformer_sim as ls
+    fc, model, sample, dirs, _ = setup
+    fc.set_option("packed_keys", 1)
+    fc.ckks.ledger(True); fc.ckks.ledger_reset()
+    got = {}
+    logits, stages, S = fc.forward(dirs, packed=True, checkpoints=got)
+    led = fc.ckks.ledger_dump(); fc.ckks.ledger(False)
+    ref_cp = {}
+    ref = ls.sim_forward(model, sample, ref_cp)
+    for name in ("packed_hidden_block0", "packed_gelu_block0", "packed_ffn_0", "affine2_0", "encoder_out"):
+        assert name in got, name
+    for name, (slots, level) in got.items():
+        assert np.abs(slots - ref_cp[name]).max() < CHECKPOINT_TOL, name
+    assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
+    rotations = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
+    assert rotations < 2500, rotations          # 13 637 + bootstraps in the faithful circuit at S = 129
+    # a packed forward needs the keys of its transforms: a controller without them fails loudly instead of generating keys on the fly
+    from fhe_linformer_b200 import host
+    bare = host.FHEController(root=setup[4]).generate()
+    with pytest.raises(RuntimeError, match="no evaluation key"):
+        bare.forward(dirs, packed=True)
+    bare.close()
+
+
 def test_encrypted_projection_variant(setup):
     """X_E / X_F computed on the server from the encrypted rows (fl_linear_wsum) instead of uploaded by the client."""
     from oracle import linformer_sim as ls
