@@ -67,7 +67,8 @@ inline LimbSel sel_ext(int l, int L, int K) {
 // In-place negacyclic NTT of `batch` buffers of sel.n limbs each (buffers batch_stride words apart).
 void launch_ntt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, cudaStream_t s);
 // Inverse; multiplies by post[m] (Shoup pair post_sh[m]), indexed by modulus, instead of N^-1 when post != nullptr.
+// src != nullptr: out of place -- the input limbs are read from src (same limb slots, batches src_bs words apart), data receives the result.
 void launch_intt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, const u64* post,
-                 const u64* post_sh, cudaStream_t s);
+                 const u64* post_sh, cudaStream_t s, const u64* src = nullptr, size_t src_bs = 0);
 
 }  // namespace flk

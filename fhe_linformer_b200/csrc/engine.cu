@@ -200,6 +200,19 @@ const uint32_t* Engine::automorph_map(uint32_t g) {
     return d;
 }
 
+// Forward transform of the ModDown conversion tq ([polys][l][N] per batch element) with the finish -- (acc - tq) P^-1 + addends,
+// permuted by the automorphism of g -- folded into its last pass (launch_ntt_finish): tq is never written back in evaluation form.
+void Engine::ntt_finish(u64* tq, size_t tq_bs, const FinishArgs& fa, uint32_t g, int l, int polys, int B) {
+    const uint32_t* imap = nullptr;
+    if (g) {
+        uint32_t gi = 1;                                   // g^-1 mod 2N: the scatter map of sigma_g is the gather map of sigma_{g^-1}
+        for (int i = 0; i < 6; ++i) gi = gi * (2 - g * gi);
+        imap = automorph_map(gi & (uint32_t)(2 * P.N - 1));
+    }
+    NttFinish f{fa, imap, md_.pinv, md_.pinv_sh, l, polys};
+    launch_ntt_finish(T, tq, B, tq_bs, f, stream);
+}
+
 void Engine::automorph(u64* out, const u64* in, uint32_t g, int limbs) { launch_automorph(out, in, automorph_map(g), P.N, limbs, stream); }
 
 const KsLevel& Engine::ks_level(int l) {
@@ -272,9 +285,7 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     const size_t dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N, acc_bs = (size_t)2 * ext * N, tq_bs = (size_t)2 * l * N;
     // 1. digits to coefficient form, pre-scaled by (Q_d/q_i)^-1
     u64* dco = alloc(dco_bs * B);
-    if (B == 1) copy(dco, io.c, dco_bs);
-    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, io.c, io.c_bs * 8, dco_bs * 8, B, cudaMemcpyDeviceToDevice, stream));
-    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream);
+    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream, io.c, io.c_bs);   // reads c1 in place: no gather copy
     // 2. ModUp: basis-extend every digit to the limbs outside it, back to evaluation form
     u64* up = alloc(up_bs * B);
     launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
@@ -297,11 +308,8 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * B);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
-    LimbSel sq;
-    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
-    ntt_l2(tq, sq, B, tq_bs);
     FinishArgs fa{io.out, io.out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, io.add0, io.add0_bs, io.add1, io.add1_bs, io.plus, io.plus_bs};
-    launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, B, stream);
+    ntt_finish(tq, tq_bs, fa, g, l, 2, B);
     release(dco); release(up); release(acc); release(tq);
 }
 
@@ -382,9 +390,7 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
     const uint32_t* maps[kHoistMax];
     for (int k = 0; k < nk; ++k) maps[k] = automorph_map(gs[k]);
     u64* dco = alloc(dco_bs * B);
-    if (B == 1) copy(dco, c1, dco_bs);
-    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, c1, cs * 8, dco_bs * 8, B, cudaMemcpyDeviceToDevice, stream));
-    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream);
+    launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream, c1, cs);
     u64* up = alloc(up_bs * B);
     launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
     LimbSel su;
@@ -406,11 +412,8 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
     launch_intt(T, acc, sp, B, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * B);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, B, tq_bs, acc_bs, stream);
-    LimbSel sq;
-    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
-    launch_ntt(T, tq, sq, B, tq_bs, stream);
     FinishArgs fa{out, cs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, s0, dco_bs, self ? c1 : nullptr, cs, nullptr, 0};
-    launch_moddown_finish(T, md_, fa, nullptr, l, 2, B, stream);
+    ntt_finish(tq, tq_bs, fa, 0, l, 2, B);
     release(dco); release(up); release(acc); release(s0); release(tq);
     if (ledger_on) {
         // the ledger follows the reference's operation census, not the work done here: a hoisted group of
@@ -427,9 +430,7 @@ void Engine::modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l) {
     const int N = P.N, ext = l + P.K, beta = ks.beta;
     const size_t dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N;
     u64* dco = alloc(dco_bs * Bn);
-    if (Bn == 1) copy(dco, c, dco_bs);
-    else FLK_CUDA(cudaMemcpy2DAsync(dco, dco_bs * 8, c, c_bs * 8, dco_bs * 8, Bn, cudaMemcpyDeviceToDevice, stream));
-    launch_intt(T, dco, sel_range(0, l), Bn, dco_bs, ks.post, ks.post_sh, stream);
+    launch_intt(T, dco, sel_range(0, l), Bn, dco_bs, ks.post, ks.post_sh, stream, c, c_bs);
     launch_modup_conv(T, ks, up, dco, Bn, up_bs, dco_bs, stream);
     LimbSel su;
     for (int d = 0; d < beta; ++d) {
@@ -453,11 +454,8 @@ void Engine::moddown_acc(u64* out, size_t out_bs, u64* acc, int Bn, int l, const
     launch_intt(T, acc, sp, Bn, acc_bs, md_.post, md_.post_sh, stream);
     u64* tq = alloc(tq_bs * Bn);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 2, Bn, tq_bs, acc_bs, stream);
-    LimbSel sq;
-    for (int i = 0; i < 2 * l; ++i) sq.push(i % l, i);
-    launch_ntt(T, tq, sq, Bn, tq_bs, stream);
     FinishArgs fa{out, out_bs, acc, (size_t)ext * N, acc_bs, tq, tq_bs, add0, add0_bs, add1, add1_bs, plus, plus_bs};
-    launch_moddown_finish(T, md_, fa, g ? automorph_map(g) : nullptr, l, 2, Bn, stream);
+    ntt_finish(tq, tq_bs, fa, g, l, 2, Bn);
     release(tq);
 }
 
@@ -638,9 +636,8 @@ void Engine::moddown(u64* out, const u64* in_ext, int l) {
     launch_intt(T, acc, sp, 1, 0, md_.post, md_.post_sh, stream);
     u64* tq = alloc((size_t)l * N);
     launch_moddown_conv(T, md_, tq, acc + (size_t)l * N, (size_t)ext * N, l, 1, 1, 0, 0, stream);
-    ntt(tq, sel_range(0, l));
     FinishArgs fa{out, 0, acc, (size_t)ext * N, 0, tq, 0, nullptr, 0, nullptr, 0, nullptr, 0};
-    launch_moddown_finish(T, md_, fa, nullptr, l, 1, 1, stream);
+    ntt_finish(tq, 0, fa, 0, l, 1, 1);
     release(acc); release(tq);
 }
 

@@ -66,6 +66,7 @@ public:
 
     // --- primitives on device buffers (all asynchronous on `stream`) ---
     void ntt(u64* data, const LimbSel& sel, int batch = 1, size_t batch_stride = 0);
+    void ntt_finish(u64* tq, size_t tq_bs, const FinishArgs& fa, uint32_t g, int l, int polys, int B);   // NTT of the ModDown conversion + fused finish
     void intt(u64* data, const LimbSel& sel, int batch = 1, size_t batch_stride = 0);
     void ew(EwOp op, u64* out, const u64* a, const u64* b, int l, int polys, bool broadcast_b);
     void ew_sel(EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel);

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
 // acc{0,1}[b][t] = sum_d U_d[b][t] * evk_{b,a}[d][mod(t)].  A thread owns two adjacent coefficients (16-byte accesses) of one
 // extended limb for IPB ciphertexts of the batch, so every evaluation-key word it loads (the largest stream of a key switch)
 // is used IPB times.  The digit loop is unrolled (BETA is a template parameter) so all loads of a thread are in flight together.
-constexpr int kIpb = 4;
+constexpr int kIpb = 8;
 template <int BETA>
 __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                  const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,

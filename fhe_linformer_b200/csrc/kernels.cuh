@@ -102,6 +102,19 @@ struct FinishArgs {
 };
 void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishArgs& a, const uint32_t* map, int l, int polys, int batch,
                            cudaStream_t s, LimbRange limbs = kAllLimbs);
+// The same epilogue folded into the LAST pass of the forward transform of the ModDown conversion (ntt.cu): a thread finishes its 8
+// transformed words in registers -- (acc - word) P^-1 + addend -- and stores them through the INVERSE automorphism map (an
+// aligned 64-byte block goes to an aligned 64-byte block: bit-reversed order keeps blocks of 2^b together), so the transformed
+// conversion is never written to or re-read from HBM and the separate finish launch disappears.  a.tq is the work buffer of the
+// transform (its first pass still runs in place there).
+struct NttFinish {
+    FinishArgs a;
+    const uint32_t* imap;     // map of g^-1 (nullptr: no permutation)
+    const u64* pinv;          // [L] P^-1 mod q_i and Shoup companions
+    const u64* pinv_sh;
+    int l, polys;
+};
+void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, const NttFinish& f, cudaStream_t s);
 
 // out[o] = sum_t k[o][t] in[t] over operands of `rows` limb rows each (2 l for a ciphertext, 2 l B for a batched one):
 // in [n_in][rows][N], out [n_out][rows][N], k [n_out][n_in][l][2] = {residue, Shoup}

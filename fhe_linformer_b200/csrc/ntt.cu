@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "device_ctx.h"
+#include "kernels.cuh"
 #include "modarith.cuh"
 
 namespace flk {
@@ -175,7 +176,32 @@ __device__ __forceinline__ void sts_group(const u64* e, u64* sm, const SBase& b)
     }
 }
 
-template <int S2, bool FWD, int R>
+// what the last round of a forward chunk pass does with its 8 canonical results per thread
+struct StoreEpi {            // plain transform: four 16-byte stores
+    static constexpr bool kFinish = false;
+};
+struct FinishEpi {           // ModDown finish (kernels.cuh NttFinish): the results stay in registers
+    static constexpr bool kFinish = true;
+    u64* out; const u64* acc; const u64* add; const u64* plus; const uint32_t* imap;
+    u64 q, pinv, pinv_sh;
+    __device__ __forceinline__ void store(const u64* e, size_t p) const {
+        // two words at a time: the chunk kernel lives in 64 registers
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(acc + p + k);
+            uint2 to = imap ? *reinterpret_cast<const uint2*>(imap + p + k) : make_uint2((uint32_t)p + k, (uint32_t)p + k + 1);
+            u64 v0 = mul_shoup(submod(a.x, e[k], q), pinv, pinv_sh, q), v1 = mul_shoup(submod(a.y, e[k + 1], q), pinv, pinv_sh, q);
+            if (add) {
+                const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(add + p + k);
+                v0 = addmod(v0, d.x, q); v1 = addmod(v1, d.y, q);
+            }
+            if (plus) { v0 = addmod(v0, plus[to.x], q); v1 = addmod(v1, plus[to.y], q); }
+            out[to.x] = v0; out[to.y] = v1;
+        }
+    }
+};
+
+template <int S2, bool FWD, int R, bool WIDE, class EPI = StoreEpi>
 struct Rounds {
     using S = Sched<S2>;
     static constexpr int r = FWD ? R : S::NR - 1 - R;     // forward: wide strides first; inverse: narrow first
@@ -191,14 +217,15 @@ struct Rounds {
     // tw: this round's twiddles (already in flight / loaded).  Data: forward round 0 reads global memory directly,
     // inverse last round writes global memory directly; everything else goes through swizzled shared memory.
     __device__ static __forceinline__ void run(u64* __restrict__ a, u64* sm, int tid, u32 chunk, int logN, const ulonglong2* tab,
-                                               ulonglong2* tw, u64 q, u64 nq, u64 q4, u64 qinv64, bool wide) {
+                                               ulonglong2* tw, u64 q, u64 nq, u64 q4, u64 qinv64, const EPI& epi = EPI(), const u64* __restrict__ src = nullptr) {
         u64 e[8];
         if constexpr (FWD && FIRST) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) e[k] = a[tid + k * S::NT];
         } else if constexpr (!FWD && FIRST) {
             // the inverse starts with the unit-stride round: a thread's 8 values are contiguous in global memory
-            const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a + tid * 8);
+            // (out of place when src is given: the digits of a key switch are read where the ciphertext lies)
+            const ulonglong2* in = reinterpret_cast<const ulonglong2*>((src ? src : a) + tid * 8);
 #pragma unroll
             for (int k = 0; k < 4; ++k) { const ulonglong2 v = in[k]; e[2 * k] = v.x; e[2 * k + 1] = v.y; }
         } else {
@@ -208,47 +235,50 @@ struct Rounds {
 #pragma unroll
         for (int h = 0; h < G::G; ++h) {
             if (FWD) {
-                if (wide) ct_block<LOG, true>(e + h * G::E, tw + h * G::TW, nq, q4);
-                else ct_block<LOG, false>(e + h * G::E, tw + h * G::TW, nq, q4);
+                ct_block<LOG, WIDE>(e + h * G::E, tw + h * G::TW, nq, q4);
             } else {
                 gs_block<LOG>(e + h * G::E, tw + h * G::TW, nq, q4);
             }
         }
         if constexpr (FWD && LAST) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) e[k] = wide ? final_reduce<true>(e[k], q, q4, nq, qinv64) : final_reduce<false>(e[k], q, q4, nq, qinv64);
+            for (int k = 0; k < 8; ++k) e[k] = final_reduce<WIDE>(e[k], q, q4, nq, qinv64);
         }
         if constexpr (!LAST) {
             // prefetch the next round's twiddles so their L2 latency overlaps the exchange and the barrier
-            Rounds<S2, FWD, R + 1>::load_twiddles(tw, tab, tid, chunk, logN);
+            Rounds<S2, FWD, R + 1, WIDE, EPI>::load_twiddles(tw, tab, tid, chunk, logN);
         }
         if constexpr (!FWD && LAST) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) a[tid + k * S::NT] = e[k];    // lazy < 4q, consumed by the column pass
         } else if constexpr (FWD && LAST) {
-            // unit-stride round: the thread's 8 results are contiguous, four 16-byte stores
-            ulonglong2* out = reinterpret_cast<ulonglong2*>(a + tid * 8);
+            if constexpr (EPI::kFinish) {
+                epi.store(e, (size_t)chunk * S::C + (size_t)tid * 8);
+            } else {
+                // unit-stride round: the thread's 8 results are contiguous, four 16-byte stores
+                ulonglong2* out = reinterpret_cast<ulonglong2*>(a + tid * 8);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = make_ulonglong2(e[2 * k], e[2 * k + 1]);
+                for (int k = 0; k < 4; ++k) out[k] = make_ulonglong2(e[2 * k], e[2 * k + 1]);
+            }
         } else {
 #pragma unroll
             for (int h = 0; h < G::G; ++h) sts_group<LOG, ULOG, 0>(e + h * G::E, sm, SBase(G::base(tid, h)));
             // A round only exchanges values inside aligned groups of 2^max(ULOG, ULOG_next) threads (the thread that reads
             // index hi' U + lo' + k U/8 next round finds it written by threads (hi'/8) U + lo' + k U/8 of this round), so the
             // barrier shrinks with the stride: whole CTA, then a named barrier per group, then a warp.
-            constexpr int NEXT_ULOG = Rounds<S2, FWD, R + 1>::ULOG;
+            constexpr int NEXT_ULOG = Rounds<S2, FWD, R + 1, WIDE, EPI>::ULOG;
             constexpr int SCOPE = 1 << (ULOG > NEXT_ULOG ? ULOG : NEXT_ULOG);
             if constexpr (SCOPE >= S::NT) __syncthreads();
             else if constexpr (SCOPE <= 32) __syncwarp();
             else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / SCOPE), "n"(SCOPE) : "memory");
         }
-        if constexpr (!LAST) Rounds<S2, FWD, R + 1>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q4, qinv64, wide);
+        if constexpr (!LAST) Rounds<S2, FWD, R + 1, WIDE, EPI>::run(a, sm, tid, chunk, logN, tab, tw, q, nq, q4, qinv64, epi, src);
     }
 };
 
 template <int S2, bool FWD>
 __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kernel(u64* __restrict__ data, DevTables T, LimbSel sel,
-                                                                                    size_t batch_stride) {
+                                                                                    size_t batch_stride, const u64* __restrict__ src, size_t src_bs) {
     using S = Sched<S2>;
     constexpr int C = S::C;
     __shared__ u64 sm[C + C / 8];
@@ -256,29 +286,59 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_kern
     const u32 chunk = blockIdx.x;
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + (size_t)chunk * C;
     const u64 q = T.q[m], nq = 0 - q, q4 = q << 2, qinv64 = T.mu_hi[m];
-    const bool wide = is_wide(q);
     const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
     ulonglong2 tw[7];
-    Rounds<S2, FWD, 0>::load_twiddles(tw, tab, tid, chunk, T.logN);
-    Rounds<S2, FWD, 0>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, wide);
+    Rounds<S2, FWD, 0, false>::load_twiddles(tw, tab, tid, chunk, T.logN);
+    // the limb's width (60-bit P limbs keep a conditional subtraction per butterfly) is uniform per CTA: two straight-line bodies
+    // instead of a branch inside every round.  The inverse does not depend on it.
+    // inverse only: read the first round from src (same limb slots, its own batch stride), everything else works on data
+    const u64* sa = (!FWD && src) ? src + (size_t)blockIdx.z * src_bs + (size_t)sel.pos[limb] * T.N + (size_t)chunk * C : nullptr;
+    if (FWD && is_wide(q)) Rounds<S2, FWD, 0, true>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64);
+    else Rounds<S2, FWD, 0, false>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, StoreEpi(), sa);
+}
+
+// chunk pass of the forward transform of the ModDown conversion with the finish folded into its last round (Q limbs only: narrow
+// path unless the first modulus is wide)
+template <int S2>
+__global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_finish_kernel(u64* __restrict__ data, DevTables T, size_t batch_stride, NttFinish f) {
+    using S = Sched<S2>;
+    constexpr int C = S::C;
+    __shared__ u64 sm[C + C / 8];
+    const int slot = blockIdx.y, poly = slot / f.l, i = slot - poly * f.l, tid = threadIdx.x, b = blockIdx.z;
+    const u32 chunk = blockIdx.x;
+    u64* a = data + (size_t)b * batch_stride + (size_t)slot * T.N + (size_t)chunk * C;
+    const u64 q = T.q[i], nq = 0 - q, q4 = q << 2, qinv64 = T.mu_hi[i];
+    const ulonglong2* tab = T.tw2 + (size_t)i * T.N;
+    FinishEpi epi;
+    const size_t lo = (size_t)i * T.N;
+    epi.out = f.a.out + (size_t)b * f.a.out_bs + (size_t)slot * T.N;
+    epi.acc = f.a.acc + (size_t)b * f.a.acc_bs + (size_t)poly * f.a.acc_ps + lo;
+    const u64* addp = poly == 0 ? f.a.add0 : f.a.add1;
+    epi.add = addp ? addp + (size_t)b * (poly == 0 ? f.a.add0_bs : f.a.add1_bs) + lo : nullptr;
+    epi.plus = f.a.plus ? f.a.plus + (size_t)b * f.a.plus_bs + (size_t)slot * T.N : nullptr;
+    epi.imap = f.imap; epi.q = q; epi.pinv = f.pinv[i]; epi.pinv_sh = f.pinv_sh[i];
+    ulonglong2 tw[7];
+    Rounds<S2, true, 0, false, FinishEpi>::load_twiddles(tw, tab, tid, chunk, T.logN);
+    if (is_wide(q)) Rounds<S2, true, 0, true, FinishEpi>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, epi);
+    else Rounds<S2, true, 0, false, FinishEpi>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, epi);
 }
 
 template <int S2, bool FWD>
-void launch_chunk_s(const DevTables& t, u64* data, const LimbSel& sel, dim3 grid, size_t bs, cudaStream_t s) {
+void launch_chunk_s(const DevTables& t, u64* data, const LimbSel& sel, dim3 grid, size_t bs, cudaStream_t s, const u64* src, size_t src_bs) {
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(ntt_chunk_kernel<S2, FWD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    ntt_chunk_kernel<S2, FWD><<<grid, Sched<S2>::NT, 0, s>>>(data, t, sel, bs);
+    ntt_chunk_kernel<S2, FWD><<<grid, Sched<S2>::NT, 0, s>>>(data, t, sel, bs, src, src_bs);
 }
 
 template <bool FWD>
-void launch_chunk(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t bs, cudaStream_t s) {
+void launch_chunk(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t bs, cudaStream_t s, const u64* src = nullptr, size_t src_bs = 0) {
     const int S2 = t.logN - kRadix1Log;
     dim3 grid(1u << kRadix1Log, sel.n, batch);
     switch (S2) {
-#define FLK_CASE(X) case X: launch_chunk_s<X, FWD>(t, data, sel, grid, bs, s); break;
+#define FLK_CASE(X) case X: launch_chunk_s<X, FWD>(t, data, sel, grid, bs, s, src, src_bs); break;
         FLK_CASE(6) FLK_CASE(7) FLK_CASE(8) FLK_CASE(9) FLK_CASE(10) FLK_CASE(11) FLK_CASE(12)
 #undef FLK_CASE
         default: throw std::invalid_argument("unsupported ring dimension (logN must be 10..16)");
@@ -294,192 +354,37 @@ void launch_column(const DevTables& t, u64* data, const LimbSel& sel, int batch,
 }
 
 
-// ======================= radix-16 two-kernel transform (logN >= 12) =======================
-// N = 256 x R (R = 2^S2, S2 = logN - 8).  Every thread works on radix-16 register blocks (32 butterflies on 16 values), so a
-// value is touched by one global load, one shared-memory exchange and one global store per kernel:
-//   head kernel : the 8 widest-stride stages on a tile of 256 rows x 16 adjacent columns.  Round A takes rows 16k + r
-//                 (k = 0..15) per thread, round B rows 16r + j after a 32 KiB shared-memory exchange; both rounds move
-//                 whole 128-byte row segments per half-warp.  The 15 round-A twiddles are the same for every thread.
-//   tail kernel : the remaining S2 stages inside each contiguous row, 4096 contiguous words per CTA.  Round A strides
-//                 16..R/2 (elements 16k + i), round B the last four stages on 16 contiguous words per thread; the exchange
-//                 buffer is padded by one word per 16 (address 17 b + j) so both rounds are bank-conflict free.
-// The inverse runs the same rounds backwards with Gentleman-Sande blocks (tail first, then head with the n^-1 scaling).
-constexpr int kTile = 16;
-
-template <bool FWD>
-__global__ void __launch_bounds__(256, 2) ntt_head_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride,
-                                                          const u64* __restrict__ post, const u64* __restrict__ post_sh) {
-    __shared__ u64 tile[256 * kTile];
-    const int limb = blockIdx.y, m = sel.m[limb];
-    const size_t cols = (size_t)(T.N >> 8);
-    const int c = threadIdx.x & 15, r = threadIdx.x >> 4;
-    u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + (size_t)blockIdx.x * kTile + c;
-    const u64 q = T.q[m], nq = 0 - q, q4 = q << 2;
-    const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
-    u64 e[16];
-    ulonglong2 t[15];
-    if (FWD) {
-        load_tw<4>(t, tab, 1);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = a[(size_t)(16 * k + r) * cols];
-        if (is_wide(q)) ct_block<4, true>(e, t, nq, q4); else ct_block<4, false>(e, t, nq, q4);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) tile[(16 * k + r) * kTile + c] = e[k];
-        load_tw<4>(t, tab, 16 + r);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) e[j] = tile[(16 * r + j) * kTile + c];
-        if (is_wide(q)) ct_block<4, true>(e, t, nq, q4); else ct_block<4, false>(e, t, nq, q4);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a[(size_t)(16 * r + j) * cols] = e[j];   // lazy: < 8q (wide) or < 33q (narrow)
-    } else {
-        load_tw<4>(t, tab, 16 + r);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) e[j] = a[(size_t)(16 * r + j) * cols];   // < 4q from the tail kernel
-        gs_block<4>(e, t, nq, q4);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) tile[(16 * r + j) * kTile + c] = e[j];
-        load_tw<4>(t, tab, 1);
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) e[k] = tile[(16 * k + r) * kTile + c];
-        gs_block<4>(e, t, nq, q4);
-        const u64 w = post ? post[m] : T.ninv[m], ws = post ? post_sh[m] : T.ninv_sh[m];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) a[(size_t)(16 * k + r) * cols] = mul_shoup(e[k], w, ws, q);
-    }
-}
-
-template <int S2, bool FWD>
-__global__ void __launch_bounds__(256, 2) ntt_tail_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride) {
-    constexpr int R = 1 << S2, LOGA = S2 - 4, EA = 1 << LOGA, GA = 16 / EA, RP = R + R / 16;
-    __shared__ u64 sm[4096 + 256];
-    const int limb = blockIdx.y, m = sel.m[limb], tid = threadIdx.x;
-    const u32 chunk = blockIdx.x;
-    u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + (size_t)chunk * 4096;
-    const u64 q = T.q[m], nq = 0 - q, q4 = q << 2, qinv64 = T.mu_hi[m];
-    const bool wide = is_wide(q);
-    const ulonglong2* tab = (FWD ? T.tw2 : T.itw2) + (size_t)m * T.N;
-    const u32 jb = (1u << (T.logN - 4)) + chunk * 256u + (u32)tid;   // round B: block of 16 contiguous words
-    u64 e[16];
-    if (FWD) {
-        // round A: GA groups of EA elements 16k + i of one row
-        if constexpr (LOGA > 0) {
-            ulonglong2 t[GA * (EA - 1)];
-#pragma unroll
-            for (int h = 0; h < GA; ++h) {
-                const int g = h * 256 + tid, row = g >> 4, i = g & 15;
-                load_tw<LOGA>(t + h * (EA - 1), tab, 256u + chunk * (4096 / R) + (u32)row);
-#pragma unroll
-                for (int k = 0; k < EA; ++k) e[h * EA + k] = a[row * R + 16 * k + i];
-            }
-#pragma unroll
-            for (int h = 0; h < GA; ++h) {
-                if (wide) ct_block<LOGA, true>(e + h * EA, t + h * (EA - 1), nq, q4); else ct_block<LOGA, false>(e + h * EA, t + h * (EA - 1), nq, q4);
-            }
-        } else {
-#pragma unroll
-            for (int h = 0; h < 16; ++h) e[h] = a[h * 256 + tid];
-        }
-#pragma unroll
-        for (int h = 0; h < GA; ++h) {
-            const int g = h * 256 + tid, row = g >> 4, i = g & 15;
-#pragma unroll
-            for (int k = 0; k < EA; ++k) sm[row * RP + 17 * k + i] = e[h * EA + k];
-        }
-        ulonglong2 tb[15];
-        load_tw<4>(tb, tab, jb);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) e[j] = sm[17 * tid + j];
-        if (wide) ct_block<4, true>(e, tb, nq, q4); else ct_block<4, false>(e, tb, nq, q4);
-        ulonglong2* o = reinterpret_cast<ulonglong2*>(a + 16 * tid);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            ulonglong2 v;
-            v.x = wide ? final_reduce<true>(e[2 * j], q, q4, nq, qinv64) : final_reduce<false>(e[2 * j], q, q4, nq, qinv64);
-            v.y = wide ? final_reduce<true>(e[2 * j + 1], q, q4, nq, qinv64) : final_reduce<false>(e[2 * j + 1], q, q4, nq, qinv64);
-            o[j] = v;
-        }
-    } else {
-        ulonglong2 tb[15];
-        load_tw<4>(tb, tab, jb);
-        const ulonglong2* in = reinterpret_cast<const ulonglong2*>(a + 16 * tid);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const ulonglong2 v = in[j]; e[2 * j] = v.x; e[2 * j + 1] = v.y; }
-        gs_block<4>(e, tb, nq, q4);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sm[17 * tid + j] = e[j];
-        if constexpr (LOGA > 0) {
-            ulonglong2 t[GA * (EA - 1)];
-#pragma unroll
-            for (int h = 0; h < GA; ++h) load_tw<LOGA>(t + h * (EA - 1), tab, 256u + chunk * (4096 / R) + (u32)((h * 256 + tid) >> 4));
-            __syncthreads();
-#pragma unroll
-            for (int h = 0; h < GA; ++h) {
-                const int g = h * 256 + tid, row = g >> 4, i = g & 15;
-#pragma unroll
-                for (int k = 0; k < EA; ++k) e[h * EA + k] = sm[row * RP + 17 * k + i];
-                gs_block<LOGA>(e + h * EA, t + h * (EA - 1), nq, q4);
-#pragma unroll
-                for (int k = 0; k < EA; ++k) a[row * R + 16 * k + i] = e[h * EA + k];   // lazy < 4q, consumed by the head kernel
-            }
-        } else {
-            __syncthreads();
-#pragma unroll
-            for (int h = 0; h < 16; ++h) { const int g = h * 256 + tid; a[g] = sm[(g >> 4) * RP + (g & 15)]; }
-        }
-    }
-}
-
-template <bool FWD>
-void launch_head(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t bs, const u64* post, const u64* post_sh, cudaStream_t s) {
-    dim3 grid((t.N >> 8) / kTile, sel.n, batch);
-    ntt_head_kernel<FWD><<<grid, 256, 0, s>>>(data, t, sel, bs, post, post_sh);
-}
-template <bool FWD>
-void launch_tail(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t bs, cudaStream_t s) {
-    dim3 grid(t.N / 4096, sel.n, batch);
-    switch (t.logN - 8) {
-#define FLK_CASE(X) case X: ntt_tail_kernel<X, FWD><<<grid, 256, 0, s>>>(data, t, sel, bs); break;
-        FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
-#undef FLK_CASE
-        default: throw std::invalid_argument("radix-16 transform: logN must be 12..16");
-    }
-}
-// The radix-16 pair executes 25 % fewer instructions per butterfly (23 vs 31) but holds 128 registers per thread (4 warps per
-// sub-partition) and measured no faster on B200 (993 vs 1022 GB/s at N = 2^16, 2.37 s vs 2.22 s for the forward at N = 2^15):
-// it stays selectable (FLK_NTT_RADIX16=1) as the base for the asynchronous-prefetch version, the default is the
-// column + chunk pair.
-bool use_radix16(const DevTables& t) {
-    static const bool on = [] { const char* e = std::getenv("FLK_NTT_RADIX16"); return e && e[0] == '1'; }();
-    return on && t.logN >= 12;
-}
-
 }  // namespace
 
 void launch_ntt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, cudaStream_t s) {
     if (sel.n == 0 || batch == 0) return;
-    if (use_radix16(t)) {
-        launch_head<true>(t, data, sel, batch, batch_stride, nullptr, nullptr, s);
-        launch_tail<true>(t, data, sel, batch, batch_stride, s);
-    } else {
-        launch_column<true>(t, data, sel, batch, batch_stride, nullptr, nullptr, s);
-        launch_chunk<true>(t, data, sel, batch, batch_stride, s);
+    launch_column<true>(t, data, sel, batch, batch_stride, nullptr, nullptr, s);
+    launch_chunk<true>(t, data, sel, batch, batch_stride, s);
+    FLK_CUDA(cudaGetLastError());
+}
+
+void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, const NttFinish& f, cudaStream_t s) {
+    if (batch == 0) return;
+    LimbSel sq;
+    for (int i = 0; i < f.polys * f.l; ++i) sq.push(i % f.l, i);
+    launch_column<true>(t, tq, sq, batch, tq_bs, nullptr, nullptr, s);
+    const int S2 = t.logN - kRadix1Log;
+    const dim3 grid(1u << kRadix1Log, f.polys * f.l, batch);
+    switch (S2) {
+#define FLK_CASE(X) case X: { static bool cfg = false; if (!cfg) { cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cfg = true; } \
+                              ntt_chunk_finish_kernel<X><<<grid, Sched<X>::NT, 0, s>>>(tq, t, tq_bs, f); } break;
+        FLK_CASE(6) FLK_CASE(7) FLK_CASE(8) FLK_CASE(9) FLK_CASE(10) FLK_CASE(11) FLK_CASE(12)
+#undef FLK_CASE
+        default: throw std::invalid_argument("unsupported ring dimension (logN must be 10..16)");
     }
     FLK_CUDA(cudaGetLastError());
 }
 
 void launch_intt(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t batch_stride, const u64* post,
-                 const u64* post_sh, cudaStream_t s) {
+                 const u64* post_sh, cudaStream_t s, const u64* src, size_t src_bs) {
     if (sel.n == 0 || batch == 0) return;
-    if (use_radix16(t)) {
-        launch_tail<false>(t, data, sel, batch, batch_stride, s);
-        launch_head<false>(t, data, sel, batch, batch_stride, post, post_sh, s);
-    } else {
-        launch_chunk<false>(t, data, sel, batch, batch_stride, s);
-        launch_column<false>(t, data, sel, batch, batch_stride, post, post_sh, s);
-    }
+    launch_chunk<false>(t, data, sel, batch, batch_stride, s, src, src_bs);
+    launch_column<false>(t, data, sel, batch, batch_stride, post, post_sh, s);
     FLK_CUDA(cudaGetLastError());
 }
 
