@@ -184,15 +184,28 @@ struct FinishEpi {           // ModDown finish (kernels.cuh NttFinish): the resu
     static constexpr bool kFinish = true;
     u64* out; const u64* acc; const u64* add; const u64* plus; const uint32_t* imap;
     u64 q, pinv, pinv_sh;
+    const u64* s_acc; const u64* s_add;     // this thread's 8 accumulator / addend words, staged in shared memory by cp.async at kernel start
+    // the operands of the finish do not depend on the transform: fetch them asynchronously before the first round, so their HBM
+    // latency is spent under twelve stages of butterflies instead of at the very end of the CTA
+    __device__ __forceinline__ void prefetch(u64* sa, u64* sd, size_t p) {
+        s_acc = sa; s_add = sd;
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(sa + k)), "l"(acc + p + k));
+            if (add) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(sd + k)), "l"(add + p + k));
+        }
+        asm volatile("cp.async.commit_group;");
+    }
     __device__ __forceinline__ void store(const u64* e, size_t p) const {
+        asm volatile("cp.async.wait_all;" ::: "memory");   // each thread reads back only what it fetched itself: no barrier
         // two words at a time: the chunk kernel lives in 64 registers
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
-            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(acc + p + k);
+            const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(s_acc + k);
             uint2 to = imap ? *reinterpret_cast<const uint2*>(imap + p + k) : make_uint2((uint32_t)p + k, (uint32_t)p + k + 1);
             u64 v0 = mul_shoup(submod(a.x, e[k], q), pinv, pinv_sh, q), v1 = mul_shoup(submod(a.y, e[k + 1], q), pinv, pinv_sh, q);
             if (add) {
-                const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(add + p + k);
+                const ulonglong2 d = *reinterpret_cast<const ulonglong2*>(s_add + k);
                 v0 = addmod(v0, d.x, q); v1 = addmod(v1, d.y, q);
             }
             if (plus) { v0 = addmod(v0, plus[to.x], q); v1 = addmod(v1, plus[to.y], q); }
@@ -303,7 +316,8 @@ template <int S2>
 __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_finish_kernel(u64* __restrict__ data, DevTables T, size_t batch_stride, NttFinish f) {
     using S = Sched<S2>;
     constexpr int C = S::C;
-    __shared__ u64 sm[C + C / 8];
+    extern __shared__ __align__(16) u64 dsm[];    // [C + C/8] exchange buffer, [C] accumulator words, [C] addend words
+    u64* sm = dsm;
     const int slot = blockIdx.y, poly = slot / f.l, i = slot - poly * f.l, tid = threadIdx.x, b = blockIdx.z;
     const u32 chunk = blockIdx.x;
     u64* a = data + (size_t)b * batch_stride + (size_t)slot * T.N + (size_t)chunk * C;
@@ -317,6 +331,7 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_fini
     epi.add = addp ? addp + (size_t)b * (poly == 0 ? f.a.add0_bs : f.a.add1_bs) + lo : nullptr;
     epi.plus = f.a.plus ? f.a.plus + (size_t)b * f.a.plus_bs + (size_t)slot * T.N : nullptr;
     epi.imap = f.imap; epi.q = q; epi.pinv = f.pinv[i]; epi.pinv_sh = f.pinv_sh[i];
+    epi.prefetch(dsm + (C + C / 8) + tid * 8, dsm + (C + C / 8) + C + tid * 8, (size_t)chunk * C + (size_t)tid * 8);
     ulonglong2 tw[7];
     Rounds<S2, true, 0, false, FinishEpi>::load_twiddles(tw, tab, tid, chunk, T.logN);
     if (is_wide(q)) Rounds<S2, true, 0, true, FinishEpi>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, epi);
@@ -371,8 +386,11 @@ void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, con
     const int S2 = t.logN - kRadix1Log;
     const dim3 grid(1u << kRadix1Log, f.polys * f.l, batch);
     switch (S2) {
-#define FLK_CASE(X) case X: { static bool cfg = false; if (!cfg) { cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cfg = true; } \
-                              ntt_chunk_finish_kernel<X><<<grid, Sched<X>::NT, 0, s>>>(tq, t, tq_bs, f); } break;
+#define FLK_CASE(X) case X: { constexpr size_t shm = (size_t)((1 << X) + (1 << X) / 8 + 2 * (1 << X)) * 8;                                                      \
+                              static bool cfg = false;                                                                                                     \
+                              if (!cfg) { FLK_CUDA(cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));       \
+                                          cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cfg = true; } \
+                              ntt_chunk_finish_kernel<X><<<grid, Sched<X>::NT, shm, s>>>(tq, t, tq_bs, f); } break;
         FLK_CASE(6) FLK_CASE(7) FLK_CASE(8) FLK_CASE(9) FLK_CASE(10) FLK_CASE(11) FLK_CASE(12)
 #undef FLK_CASE
         default: throw std::invalid_argument("unsupported ring dimension (logN must be 10..16)");
