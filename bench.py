@@ -305,6 +305,55 @@ def run_b200(a):
     for s in scratch:
         s.free()
 
+    # ---- N > 1 only: ONE EvalRotate split across the ranks by limb (the optional limb-sharded key switch, all-gathers over NVLink) ----
+    sharded_blk = None
+    if world > 1:
+        from fhe_linformer_b200 import sharded
+        sharded.register_signatures(e.lib)
+        dev = torch.device("cuda", local)
+        rs = np.random.default_rng(7)                          # the same operands on every rank
+        ct1 = np.stack([np.stack([rs.integers(0, int(q[m]), N, dtype=np.uint64) for m in range(l)]) for _ in range(2)])
+        evk1 = e.to_dev(rs.integers(0, 1 << 50, (e.dnum, 2, e.L + e.K, N), dtype=np.uint64))
+        d1, t1 = e.to_dev(ct1), sharded.to_tensor(ct1, dev)
+        o1 = e.buf(d1.shape)
+        want = e.rotate(d1, g, evk1).download()
+
+        def timed_ms(fn, reps=20):
+            for _ in range(3):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(reps):
+                fn()
+            a1.record(stream); e.sync(); torch.cuda.synchronize()
+            tt = torch.tensor([a0.elapsed_time(a1) / reps], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        rows = {}
+        ok_all = True
+        for name, gd in (("digits recomputed by every rank", False), ("digits all-gathered", True)):
+            ks = sharded.ShardedKeySwitch(e, l, sharded.DistComm(), device=dev, gather_digits=gd)
+            ks.rotate(t1, g, evk1)
+            got1 = ks.gather_result(); e.sync(); torch.cuda.synchronize()
+            ok_all = ok_all and bool((got1.cpu().numpy().view(np.uint64) == want).all())
+            rows[name] = {"us": timed_ms(lambda: ks.rotate(t1, g, evk1)) * 1e3, "MB_received_per_rank": ks.exchanged_bytes() / 1e6}
+            if not gd:
+                rows["... plus an all-gather of the result limbs"] = {"us": timed_ms(lambda: (ks.rotate(t1, g, evk1), ks.gather_result())) * 1e3}
+                comm = sharded.DistComm()
+                xchg_us = timed_ms(lambda: comm.all_gather(ks.states[0].pshare)) * 1e3
+        single_us = timed_ms(lambda: e.rotate(d1, g, evk1, out=o1)) * 1e3
+        okt = torch.tensor([1.0 if ok_all else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        best = min(v["us"] for k, v in rows.items() if not k.startswith("..."))
+        sharded_blk = {"ranks": world, "ring": f"N=2^{a.logN}, l={l}", "bit_exact_vs_single_gpu": bool(okt.item() > 0.5), "single_gpu_us": single_us,
+                       "sharded": rows, "latency_ratio_single_over_sharded": single_us / best, "special_limb_all_gather_alone_us": xchg_us,
+                       "note": "one EvalRotate (no batching), limbs of Q_l u P split across the ranks, result left limb-sharded; CUDA events on the engine "
+                               "stream, max over ranks; fhe_linformer_b200/sharded.py"}
+        for x in (d1, o1, evk1):
+            x.free()
+
     # ---- e2e: same metric through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region) ----
     ngroups = len(ins)
     pin_in = [torch.empty(tuple(x.shape), dtype=torch.int64).pin_memory() for x in ins]
@@ -397,6 +446,8 @@ def run_b200(a):
             line["cpu_baseline"] = cpu
         if fwd:
             line["forward"] = fwd
+        if sharded_blk:
+            line["sharded_keyswitch"] = sharded_blk
         emit(line)
     if world > 1:
         dist.destroy_process_group()

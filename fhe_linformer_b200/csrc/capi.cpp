@@ -159,6 +159,9 @@ int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_
 }
 
 int fl_raw_ks_digits(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l) { FL_TRY(c->eng->ks_digits(dco, poly, l)) }
+int fl_raw_ks_digits_part(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l, int first, int count) {
+    FL_TRY(c->eng->ks_digits_part(dco, poly, l, first, count))
+}
 int fl_raw_ks_modup(fl_ctx* c, uint64_t* up, const uint64_t* dco, int l, int first, int count) { FL_TRY(c->eng->ks_modup_part(up, dco, l, first, count)) }
 int fl_raw_ks_inner(fl_ctx* c, uint64_t* acc, const uint64_t* up, const uint64_t* poly, const uint64_t* evk, int l, int first, int count) {
     FL_TRY(c->eng->ks_inner_part(acc, up, poly, evk, l, first, count))

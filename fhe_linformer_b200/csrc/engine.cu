@@ -336,10 +336,14 @@ void Engine::rotate_batch(u64* out, const u64* ct, int l, uint32_t g, const u64*
 // G ranks hold the same input polynomial and split the l + K limbs of Q_l u P between them (sharded.py).  Every stage is
 // limb-wise independent except the two base conversions, which need all source limbs: the digits (cheap, recomputed by every
 // rank) and the P limbs of the accumulators (exchanged over NVLink between ks_pcoef_part and ks_moddown_part).
-void Engine::ks_digits(u64* dco, const u64* c, int l) {
+void Engine::ks_digits(u64* dco, const u64* c, int l) { ks_digits_part(dco, c, l, 0, l); }
+// digits first .. first + count - 1 only (a rank's share when the digit limbs are exchanged instead of recomputed)
+void Engine::ks_digits_part(u64* dco, const u64* c, int l, int first, int count) {
+    if (count <= 0) return;
     const KsLevel& ks = ks_level(l);
-    copy(dco, c, (size_t)l * P.N);
-    launch_intt(T, dco, sel_range(0, l), 1, 0, ks.post, ks.post_sh, stream);
+    LimbSel s;
+    for (int i = first; i < first + count; ++i) s.push(i, i);
+    launch_intt(T, dco, s, 1, 0, ks.post, ks.post_sh, stream, c, 0);
 }
 void Engine::ks_modup_part(u64* up, const u64* dco, int l, int first, int count) {
     const KsLevel& ks = ks_level(l);

@@ -90,6 +90,7 @@ public:
     void mul_relin(u64* out, const u64* a, const u64* b, int l, const u64* evk);
     void mul_relin_batch(u64* out, const u64* a, const u64* b, int l, const u64* evk, int B, size_t b_bs);   // a, out: [B][2][l][N]
     // limb-sharded key switch: one stage each, restricted to [first, first + count) of the extended basis (engine.cu)
+    void ks_digits_part(u64* dco, const u64* c, int l, int first, int count);
     void ks_digits(u64* dco, const u64* c, int l);
     void ks_modup_part(u64* up, const u64* dco, int l, int first, int count);
     void ks_inner_part(u64* acc, const u64* up, const u64* c, const u64* evk, int l, int first, int count);

@@ -84,6 +84,7 @@ int fl_raw_mul_plain(fl_ctx* c, uint64_t* out, const uint64_t* ct, const uint64_
  * dco [l][N], up [beta][l+K][N], acc [2][l+K][N], tq [2][l][N], out [2][l][N].  Between fl_raw_ks_pcoef and
  * fl_raw_ks_moddown the ranks exchange the P limbs of acc (coefficient form), after fl_raw_ks_moddown the limbs of out. ---- */
 int fl_raw_ks_digits(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l);                                   /* scaled INTT of the digits */
+int fl_raw_ks_digits_part(fl_ctx* c, uint64_t* dco, const uint64_t* poly, int l, int first, int count);        /* ... of limbs in range only */
 int fl_raw_ks_modup(fl_ctx* c, uint64_t* up, const uint64_t* dco, int l, int first, int count);                /* ModUp of targets in range */
 int fl_raw_ks_inner(fl_ctx* c, uint64_t* acc, const uint64_t* up, const uint64_t* poly, const uint64_t* evk, int l, int first, int count);
 int fl_raw_ks_pcoef(fl_ctx* c, uint64_t* acc, int l, int first, int count);   /* first, count: range inside the K special limbs */

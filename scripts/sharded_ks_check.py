@@ -19,8 +19,11 @@ evk = e.to_dev(evk_h); d_ct = e.to_dev(ct); t_ct = sharded.to_tensor(ct, dev)
 g = e.galois(1)
 want = e.rotate(d_ct, g, evk).download()
 ks = sharded.ShardedKeySwitch(e, l, sharded.DistComm(), device=dev)
-got = ks.rotate(t_ct, g, evk); e.sync(); torch.cuda.synchronize()
+ks.rotate(t_ct, g, evk); got = ks.gather_result(); e.sync(); torch.cuda.synchronize()
 ok = bool((got.cpu().numpy().view(np.uint64) == want).all())
+ks_g = sharded.ShardedKeySwitch(e, l, sharded.DistComm(), device=dev, gather_digits=True)
+ks_g.rotate(t_ct, g, evk); got_g = ks_g.gather_result(); e.sync(); torch.cuda.synchronize()
+ok = ok and bool((got_g.cpu().numpy().view(np.uint64) == want).all())
 stream = torch.cuda.ExternalStream(e.stream(), device=dev)
 def timed(fn, reps=20):
     for _ in range(3): fn()
@@ -35,7 +38,14 @@ def timed(fn, reps=20):
 out = e.buf(d_ct.shape)
 single = timed(lambda: e.rotate(d_ct, g, evk, out=out))
 shard_ms = timed(lambda: ks.rotate(t_ct, g, evk))
+shard_g_ms = timed(lambda: ks_g.rotate(t_ct, g, evk))
+full_ms = timed(lambda: (ks.rotate(t_ct, g, evk), ks.gather_result()))
+# what the exchanges alone cost: the same all-gathers without any kernel
+comm = sharded.DistComm()
+xchg_ms = timed(lambda: comm.all_gather(ks.states[0].pshare))
 if rank == 0:
-    print("limb-sharded EvalRotate N=2^%d l=%d over %d GPUs: bit-exact=%s  single-GPU %.1f us  sharded %.1f us  (latency x%.2f; %.1f MB exchanged per rank)"
-          % (logN, l, world, ok, single * 1e3, shard_ms * 1e3, single / shard_ms, ks.exchanged_bytes() / 1e6), flush=True)
+    print("limb-sharded EvalRotate N=2^%d l=%d over %d GPUs: bit-exact=%s  single-GPU %.1f us | sharded, result left limb-sharded: %.1f us (x%.2f, %.1f MB received per rank)"
+          " | digits all-gathered too: %.1f us (x%.2f, %.1f MB) | + all-gather of the result: %.1f us (x%.2f) | the special-limb all-gather alone: %.1f us"
+          % (logN, l, world, ok, single * 1e3, shard_ms * 1e3, single / shard_ms, ks.exchanged_bytes() / 1e6, shard_g_ms * 1e3, single / shard_g_ms,
+             ks_g.exchanged_bytes() / 1e6, full_ms * 1e3, single / full_ms, xchg_ms * 1e3), flush=True)
 dist.destroy_process_group()

@@ -20,10 +20,16 @@ def test_sharded_rotation_is_bit_exact(world):
         ct = np.stack([np.stack([rng.integers(0, int(e.moduli[m]), e.N, dtype=np.uint64) for m in range(l)]) for _ in range(2)])
         g = e.galois(3)
         want = e.rotate(e.to_dev(ct), g, evk).download()
-        ks = sharded.ShardedKeySwitch(e, l, sharded.LocalComm(world), device=dev)
-        got = ks.rotate(sharded.to_tensor(ct, dev), g, evk)
-        e.sync(); torch.cuda.synchronize()
-        assert (got.cpu().numpy().view(np.uint64) == want).all(), (world, l)
+        for gather_digits in (False, True):                  # digits recomputed by every rank / transformed in shares and all-gathered
+            ks = sharded.ShardedKeySwitch(e, l, sharded.LocalComm(world), device=dev, gather_digits=gather_digits)
+            ks.rotate(sharded.to_tensor(ct, dev), g, evk)
+            got = ks.gather_result()
+            e.sync(); torch.cuda.synchronize()
+            assert (got.cpu().numpy().view(np.uint64) == want).all(), (world, l, gather_digits)
+            # the result stays limb-sharded: each rank's buffer holds exactly its own limbs of it
+            for st in ks.states:
+                mine = st.out[:, st.q_first:st.q_first + st.q_count].cpu().numpy().view(np.uint64)
+                assert (mine == want[:, st.q_first:st.q_first + st.q_count]).all()
         # every limb of the extended basis belongs to exactly one rank
         owned = sorted(t for st in ks.states for first, count in st.ranges() for t in range(first, first + count))
         assert owned == list(range(l + e.K))

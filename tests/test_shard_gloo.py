@@ -64,3 +64,36 @@ def test_limb_ranges_of_the_sharded_key_switch_cover_the_extended_basis():
                 st = sharded._RankState(eng, l, r, world, torch.device("cpu"))
                 owned += [t for first, count in st.ranges() for t in range(first, first + count)]
             assert sorted(owned) == list(range(l + 7)), (l, world)
+
+
+def _gather_worker(rank, world, port, q):
+    """The exchange of the limb-sharded key switch on CPU tensors: DistComm.all_gather of padded shares + sharded.assemble."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fhe_linformer_b200 import sharded
+    comm = sharded.DistComm()
+    ok = True
+    for total, lead in ((7, 2), (28, 2), (5, 1), (1, 2)):            # K special limbs / l digit limbs over the ranks, ragged splits included
+        sizes, pad = sharded.share_sizes(total, world)
+        mine = shard.my_units(total, rank, world)
+        full = torch.arange(lead * total * 4, dtype=torch.int64).reshape(lead, total, 4) * 7 + 3     # what every rank must end with
+        share = torch.zeros((lead, pad, 4), dtype=torch.int64)
+        share[:, :len(mine)] = full[:, mine.start:mine.stop]
+        got = sharded.assemble(comm.all_gather(share), total, world, 1)
+        ok = ok and bool((got == full).all())
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_of_limb_shares_with_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs: p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
