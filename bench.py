@@ -295,7 +295,7 @@ def run_b200(a):
     ntt_gbs = ntt_bytes / (ntt_ms * 1e-3) / 1e9
     traffic = None
     try:   # DRAM bytes per launch of the same kernel pair from the committed ncu capture (scaled to this limb count)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["ntt_pass_pair_2x28_limbs_per_ciphertext"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["ntt_pass_pair_2x28_limbs_per_ciphertext"]
         if a.logN == 16:
             traffic = tj["dram_bytes_per_launch"] * l / 28.0 * G
     except Exception:
@@ -418,7 +418,7 @@ def run_b200(a):
             fwd.pop("_ledger", None)
 
     if rank == 0:
-        launches_per_group = 12         # kernels per batched call: 4 NTT pass pairs (8) + modup / inner product / moddown conv / finish (4); plus 1 D2D copy
+        launches_per_group = 11         # kernels per batched call: 4 transform pass pairs (8; the last one carries the ModDown finish) + ModUp conversion, key inner product, ModDown conversion
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
