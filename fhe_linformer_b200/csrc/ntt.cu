@@ -184,20 +184,31 @@ struct FinishEpi {           // ModDown finish (kernels.cuh NttFinish): the resu
     static constexpr bool kFinish = true;
     u64* out; const u64* acc; const u64* add; const u64* plus; const uint32_t* imap;
     u64 q, pinv, pinv_sh;
-    const u64* s_acc; const u64* s_add;     // this thread's 8 accumulator / addend words, staged in shared memory by cp.async at kernel start
-    // the operands of the finish do not depend on the transform: fetch them asynchronously before the first round, so their HBM
-    // latency is spent under twelve stages of butterflies instead of at the very end of the CTA
-    __device__ __forceinline__ void prefetch(u64* sa, u64* sd, size_t p) {
-        s_acc = sa; s_add = sd;
-#pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(sa + k)), "l"(acc + p + k));
-            if (add) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((u32)__cvta_generic_to_shared(sd + k)), "l"(add + p + k));
+    const u64* s_acc; const u64* s_add;     // this thread's 8 accumulator / addend words in the CTA's shared-memory staging area
+    u32 mbar;                               // shared-memory address of the mbarrier the bulk copies complete on
+    // The operands of the finish do not depend on the transform: the chunk's accumulator and addend words (contiguous, C words each)
+    // are fetched by the TMA engine -- one 1-D bulk copy each (cp.async.bulk, UBLKCP), issued by one thread before the first round and
+    // completing on an mbarrier -- so their HBM latency is spent under twelve stages of butterflies and no thread issues a load for them.
+    __device__ __forceinline__ void prefetch(u64* sa, u64* sd, u64* bar, size_t chunk_first, int chunk_words, int tid) {
+        s_acc = sa + tid * 8; s_add = sd + tid * 8;
+        mbar = (u32)__cvta_generic_to_shared(bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;");
+        __syncthreads();
+        if (tid == 0) {
+            const u32 bytes = (u32)chunk_words * 8u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(add ? 2u * bytes : bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((u32)__cvta_generic_to_shared(sa)),
+                         "l"(acc + chunk_first), "r"(bytes), "r"(mbar) : "memory");
+            if (add)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((u32)__cvta_generic_to_shared(sd)),
+                             "l"(add + chunk_first), "r"(bytes), "r"(mbar) : "memory");
+        }
     }
     __device__ __forceinline__ void store(const u64* e, size_t p) const {
-        asm volatile("cp.async.wait_all;" ::: "memory");   // each thread reads back only what it fetched itself: no barrier
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(mbar) : "memory");
         // two words at a time: the chunk kernel lives in 64 registers
 #pragma unroll
         for (int k = 0; k < 8; k += 2) {
@@ -316,7 +327,7 @@ template <int S2>
 __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_finish_kernel(u64* __restrict__ data, DevTables T, size_t batch_stride, NttFinish f) {
     using S = Sched<S2>;
     constexpr int C = S::C;
-    extern __shared__ __align__(16) u64 dsm[];    // [C + C/8] exchange buffer, [C] accumulator words, [C] addend words
+    extern __shared__ __align__(16) u64 dsm[];    // [C + C/8] exchange buffer, [C] accumulator words, [C] addend words, mbarrier
     u64* sm = dsm;
     const int slot = blockIdx.y, poly = slot / f.l, i = slot - poly * f.l, tid = threadIdx.x, b = blockIdx.z;
     const u32 chunk = blockIdx.x;
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(Sched<S2>::NT, Sched<S2>::MINB) ntt_chunk_fini
     epi.add = addp ? addp + (size_t)b * (poly == 0 ? f.a.add0_bs : f.a.add1_bs) + lo : nullptr;
     epi.plus = f.a.plus ? f.a.plus + (size_t)b * f.a.plus_bs + (size_t)slot * T.N : nullptr;
     epi.imap = f.imap; epi.q = q; epi.pinv = f.pinv[i]; epi.pinv_sh = f.pinv_sh[i];
-    epi.prefetch(dsm + (C + C / 8) + tid * 8, dsm + (C + C / 8) + C + tid * 8, (size_t)chunk * C + (size_t)tid * 8);
+    epi.prefetch(dsm + (C + C / 8), dsm + (C + C / 8) + C, dsm + (C + C / 8) + 2 * C, (size_t)chunk * C, C, tid);
     ulonglong2 tw[7];
     Rounds<S2, true, 0, false, FinishEpi>::load_twiddles(tw, tab, tid, chunk, T.logN);
     if (is_wide(q)) Rounds<S2, true, 0, true, FinishEpi>::run(a, sm, tid, chunk, T.logN, tab, tw, q, nq, q4, qinv64, epi);
@@ -386,7 +397,7 @@ void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, con
     const int S2 = t.logN - kRadix1Log;
     const dim3 grid(1u << kRadix1Log, f.polys * f.l, batch);
     switch (S2) {
-#define FLK_CASE(X) case X: { constexpr size_t shm = (size_t)((1 << X) + (1 << X) / 8 + 2 * (1 << X)) * 8;                                                      \
+#define FLK_CASE(X) case X: { constexpr size_t shm = (size_t)((1 << X) + (1 << X) / 8 + 2 * (1 << X) + 2) * 8;                                                      \
                               static bool cfg = false;                                                                                                     \
                               if (!cfg) { FLK_CUDA(cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));       \
                                           cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cfg = true; } \
