@@ -154,3 +154,31 @@ def test_first_use_of_a_slot_count_from_two_threads():
     assert not fails, fails
     assert len(errs) == 2 and max(errs.values()) < 1e-6
     for c in ctxs: c.close()
+
+
+def test_veneer_sequential_ladder_limb_exact(tmp_path):
+    """Through the FHEController veneer with batch_rows = false and hoist_ladders = false, rotsum(c, 8, 128) is the reference's loop
+    r = r + EvalRotate(r, 128 * 2^i) (FHEController.cpp:829-837), and its limbs are the CPU restatement's, at the reference ring."""
+    from fhe_linformer_b200 import host
+    from oracle.oracle import Oracle
+    seed = 4242
+    fc = host.FHEController(root=str(tmp_path), key_seed=seed, batch_rows=0, hoist_ladders=0).generate(rotations=[128, 256, 512])
+    c = fc.ckks
+    o = Oracle(logN=15, L=28, dnum=4)
+    sk = o.gen_sk(seed, h=192)                             # SPARSE_TERNARY as the controller generates it
+    assert (c.export_sk() == sk).all()
+    l = 27
+    rng = np.random.default_rng(9)
+    q = [int(x) for x in o.moduli]
+    ct = np.stack([np.stack([rng.integers(0, q[m], o.N, dtype=np.uint64) for m in range(l)]) for _ in range(2)])
+    got = fc.invoke("rotsum", [c.import_elem(ct, 1, float(o.sf[1]), o.N // 2)], ints=[8, 128])[0].export()
+    ref = ct.copy()
+    for i in range(3):
+        g = o.galois(128 << i)
+        rot = o.rotate(ref, g, o.gen_galois_key(seed + 1000 + g, sk, g))
+        ref = np.stack([o.add(ref[0], rot[0], list(range(l))), o.add(ref[1], rot[1], list(range(l)))])
+    assert (got == ref).all()
+    # a rotation index without a key is an error, as from OpenFHE's EvalRotate -- the veneer no longer makes keys on demand
+    with pytest.raises(RuntimeError, match="no evaluation key"):
+        fc.invoke("rotate", [c.import_elem(ct, 1, float(o.sf[1]), o.N // 2)], ints=[11111])   # not a bootstrap index either
+    fc.close()
