@@ -18,6 +18,7 @@ _SIGS = {
     "fl_keys_save": (ci, [vp, C.c_char_p]), "fl_keys_load": (ci, [vp, C.c_char_p]),
     "fl_encode": (ci, [vp, vp, vp, ci, ci, ci, C.POINTER(vp)]),
     "fl_encrypt": (ci, [vp, vp, C.POINTER(vp)]), "fl_encrypt_seeded": (ci, [vp, vp, u64, C.POINTER(vp)]),
+    "fl_encrypt_many": (ci, [vp, vp, ci, C.POINTER(vp)]),
     "fl_decrypt": (ci, [vp, vp, vp, vp, ci]), "fl_decode": (ci, [vp, vp, vp, vp, ci]),
     "fl_add": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_sub": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_mul": (ci, [vp, vp, vp, C.POINTER(vp)]),
     "fl_add_many": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_mul_many": (ci, [vp, vp, ci, C.POINTER(vp)]),
@@ -148,6 +149,11 @@ class CKKS(Engine):
         if seed is None:
             return self._out(self.lib.fl_encrypt, p.h)
         return self._out(self.lib.fl_encrypt_seeded, p.h, seed)
+
+    def encrypt_many(self, plaintexts):
+        """Encrypt of several plaintexts of one level in one batched call; returns the list of ciphertexts."""
+        arr = (vp * len(plaintexts))(*[p.h for p in plaintexts])
+        return self.unpack(self._out(self.lib.fl_encrypt_many, arr, len(plaintexts)))
 
     def decrypt(self, ct, slots=None, complex_out=False):
         slots = slots or ct.slots

@@ -248,6 +248,13 @@ int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, i
     })
 }
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out) { FL_TRY(*out = wrap(c->sch->encrypt(p->e))) }
+int fl_encrypt_many(fl_ctx* c, const fl_pt* const* pts, int n, fl_ct** out) {
+    FL_TRY({
+        std::vector<const Elem*> v((size_t)n);
+        for (int i = 0; i < n; ++i) v[i] = &pts[i]->e;
+        *out = wrap(c->sch->encrypt_many(v));
+    })
+}
 int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out) { FL_TRY(*out = wrap(c->sch->encrypt_seeded(p->e, seed))) }
 static void split(const std::vector<cplx>& v, double* re, double* im) {
     for (size_t i = 0; i < v.size(); ++i) { re[i] = v[i].real(); if (im) im[i] = v[i].imag(); }

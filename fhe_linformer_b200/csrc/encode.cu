@@ -47,11 +47,12 @@ __global__ void __launch_bounds__(kThreads) sample_limbs_kernel(u64* __restrict_
 // the same two samplers from ChaCha20 key stream: coefficient j takes block j of stream `nonce` (every limb of the polynomial
 // recomputes the block, so all limbs hold the same small integer)
 __global__ void __launch_bounds__(kThreads) sample_limbs_csprng_kernel(u64* __restrict__ dst, ChaChaKey key, u64 nonce, int kind, DevTables T,
-                                                                       LimbSel sel) {
+                                                                       LimbSel sel, size_t batch_stride) {
     const int j = blockIdx.x * kThreads + threadIdx.x, limb = blockIdx.y;
     if (j >= T.N) return;
+    dst += (size_t)blockIdx.z * batch_stride;      // polynomial z of a batch is stream nonce + z
     uint32_t blk[16];
-    chacha20_block(key, (u64)j, nonce, blk);
+    chacha20_block(key, (u64)j, nonce + (u64)blockIdx.z, blk);
     const int v = kind == 0 ? ternary_of(chacha_u64(blk, 0)) : gauss_of(chacha_u64(blk, 0), chacha_u64(blk, 1) & 1);
     const u64 q = T.q[sel.m[limb]];
     dst[(size_t)sel.pos[limb] * T.N + j] = v >= 0 ? (u64)v : q - (u64)(-v);
@@ -170,8 +171,9 @@ void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const 
     uniform_limbs_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, ss, t, sel);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s) {
-    sample_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, key, nonce, kind, t, sel);
+void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s, int batch,
+                                size_t batch_stride) {
+    sample_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), sel.n, batch), kThreads, 0, s>>>(dst, key, nonce, kind, t, sel, batch_stride);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s) {

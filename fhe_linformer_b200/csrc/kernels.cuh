@@ -149,7 +149,9 @@ void launch_sample_limbs(const DevTables& t, u64* dst, u64 seed, int kind, const
 void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const LimbSel& sel, cudaStream_t s);
 // the production samplers: ChaCha20 key stream (chacha.cuh), block j of stream `nonce` per coefficient; uniform limb i uses stream nonce + i
 struct ChaChaKey;
-void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s);
+// (batch polynomials batch_stride words apart: polynomial z is stream nonce + z)
+void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s, int batch = 1,
+                                size_t batch_stride = 0);
 void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s);
 // special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd);
 // kext > 0 appends the residues modulo the first kext special limbs (plaintexts in the extended basis Q_l u P)

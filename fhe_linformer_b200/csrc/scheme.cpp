@@ -474,6 +474,43 @@ Elem Scheme::encrypt_seeded(const Elem& pt, u64 seed) { return encrypt_with(pt, 
 // encryptions, in this or any other process, share randomness
 Elem Scheme::encrypt(const Elem& pt) { return encrypt_with(pt, false, 0); }
 
+// Encrypt(pk, pt_b) for B plaintexts of one level as ONE batched operand: the ternary / Gaussian polynomials of all of them come
+// out of one sampler launch each (ChaCha20 stream per polynomial), one batched transform, one batched product / sum per component --
+// a dozen launches in all instead of a dozen per ciphertext (a forward encrypts S + 64 rows: FHEController.cpp:628-649 per file).
+Elem Scheme::encrypt_many(const std::vector<const Elem*>& pts) {
+    if (!pk_) throw std::runtime_error("Encrypt: no public key");
+    if (pts.empty()) throw std::invalid_argument("Encrypt: no plaintexts");
+    const Elem& f = *pts[0];
+    for (const Elem* p : pts)
+        if (p->ncomp != 1 || p->batch != 1 || p->l != f.l || p->deg != f.deg || p->scale != f.scale || p->slots != f.slots)
+            throw std::invalid_argument("Encrypt (batched): plaintexts must share level, degree, scale and slot count");
+    const int B = (int)pts.size(), l = f.l, N = P.N;
+    const size_t pl = (size_t)l * N, pkl = (size_t)P.L * N, cs = 2 * pl;
+    const LimbSel sel = sel_range(0, l);
+    Elem ct = make(2, l, f.deg, f.scale, f.slots, B);
+    u64* v = eng.alloc(pl * B);
+    u64* e = eng.alloc(pl * B);
+    u64* t = eng.alloc(pl * B);
+    auto sample = [&](u64* dst, int kind) {
+        launch_sample_limbs_csprng(eng.T, dst, rng_keys_[(int)Use::Encrypt], rng_stream_, kind, sel, eng.stream, B, pl);
+        rng_stream_ += (u64)B;
+        eng.ntt(dst, sel, B, pl);
+    };
+    sample(v, 0);
+    sample(e, 1);
+    // c0 = pk0 v + e0 + pt
+    launch_ew(eng.T, EwOp::Mul, t, v, pk_, sel, 1, B, pl, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, t, t, e, sel, 1, B, pl, pl, 0, eng.stream);
+    for (int b = 0; b < B; ++b) launch_ew(eng.T, EwOp::Add, ct.data() + (size_t)b * cs, t + (size_t)b * pl, pts[b]->data(), sel, 1, 1, 0, 0, 0, eng.stream);
+    // c1 = pk1 v + e1
+    sample(e, 1);
+    launch_ew(eng.T, EwOp::Mul, t, v, pk_ + pkl, sel, 1, B, pl, 0, 0, eng.stream);
+    launch_ew(eng.T, EwOp::Add, t, t, e, sel, 1, B, pl, pl, 0, eng.stream);
+    FLK_CUDA(cudaMemcpy2DAsync(ct.data() + pl, cs * 8, t, pl * 8, pl * 8, B, cudaMemcpyDeviceToDevice, eng.stream));
+    eng.release(v); eng.release(e); eng.release(t);
+    return ct;
+}
+
 Elem Scheme::encrypt_with(const Elem& pt, bool seeded, u64 seed) {
     if (!pk_) throw std::runtime_error("Encrypt: no public key");
     if (pt.ncomp != 1) throw std::invalid_argument("Encrypt: plaintext expected");

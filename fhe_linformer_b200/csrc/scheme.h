@@ -96,6 +96,7 @@ public:
     Elem encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg);   // explicit limb count / scale
     Elem encrypt(const Elem& pt);
     Elem encrypt_seeded(const Elem& pt, u64 seed);
+    Elem encrypt_many(const std::vector<const Elem*>& pts);   // one batched operand holding Encrypt(pt_b), b < pts.size()
     void decrypt(const Elem& ct, cplx* out, int slots);
     void decode(const Elem& pt, cplx* out, int slots);
 

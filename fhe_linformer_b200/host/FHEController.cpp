@@ -474,6 +474,30 @@ Ptxt FHEController::read_plain_repeated_512_input(const string& filename, int le
 Ctxt FHEController::read_expanded_input(const string& filename, double scale) {
     return encrypt(stretch(read_values_from_file(filename), 128, 128, 128, scale), 0, num_slots);
 }
+vector<Ctxt> FHEController::encrypt_many(const vector<Ptxt>& plaintexts) {
+    if (plaintexts.empty()) return {};
+    if (!batch_rows) {
+        vector<Ctxt> out;
+        for (const Ptxt& p : plaintexts) out.push_back(encrypt_ptxt(p));
+        return out;
+    }
+    vector<Ctxt> out;
+    for (size_t first = 0; first < plaintexts.size(); first += (size_t)max_rows_per_batch) {
+        const size_t last = std::min(plaintexts.size(), first + (size_t)max_rows_per_batch);
+        vector<const fl_elem*> h;
+        for (size_t i = first; i < last; ++i) h.push_back(plaintexts[i]->handle());
+        fl_elem* e = nullptr;
+        need(fl_encrypt_many(ctx_, h.data(), (int)h.size(), &e), "Encrypt");
+        const vector<Ctxt> part = unpack(wrap(e));
+        out.insert(out.end(), part.begin(), part.end());
+    }
+    return out;
+}
+vector<Ctxt> FHEController::read_expanded_inputs(const vector<string>& filenames, double scale) {
+    vector<Ptxt> pts;
+    for (const string& f : filenames) pts.push_back(read_plain_expanded_input(f, 0, scale));
+    return encrypt_many(pts);
+}
 Ptxt FHEController::read_plain_expanded_input(const string& filename, int level, double scale) {
     return encode(stretch(read_values_from_file(filename), 128, 128, 128, scale), level, num_slots);
 }

@@ -167,6 +167,8 @@ public:
     Rows unpack(const Ctxt& packed) const;                           // zero-copy views of a batched operand
     Rows per_row(const Rows& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const;   // run a per-row recipe on batches
     Rows settle_rows(const Rows& rows) const;                        // pending FLEXIBLEAUTO rescales of many rows, as one batch
+    Rows encrypt_many(const vector<Ptxt>& plaintexts);                // Encrypt of many plaintexts of one level as one batched call
+    Rows read_expanded_inputs(const vector<string>& filenames, double scale = 1);   // read_expanded_input for a list of files, encrypted together
     Ctxt shifted_sum(Rows items, int stride);                        // sum_i rot(items[i], stride * i) as a tree of batched rotations
     Rows all_shifts(const Ctxt& c, int count);                       // rot(c, t), t < count, by batched doubling
     // out[o] = sum_t weights[o][t] * rows[t] (+ bias[o]): the Linformer E / F projection on the row ciphertexts

@@ -37,10 +37,11 @@ void LinformerForward::lap(const std::string& name) {
 }
 
 std::vector<Ctxt> LinformerForward::load_expanded(const std::string& dir, const std::string& stem, int count) {
-    std::vector<Ctxt> rows;
-    rows.reserve(count);
-    for (int i = 0; i < count; ++i) rows.push_back(fc_.read_expanded_input(dir + "/" + stem + std::to_string(i) + ".txt"));
-    return rows;
+    // M:159-173 encrypts file by file; the rows are independent, so they are encoded one by one and encrypted as one batch
+    std::vector<std::string> files;
+    files.reserve(count);
+    for (int i = 0; i < count; ++i) files.push_back(dir + "/" + stem + std::to_string(i) + ".txt");
+    return fc_.read_expanded_inputs(files);
 }
 
 // ---- Linformer projection under encryption (F1): row i of X_E is sum_t E[i][t] rows[t] + E_b[i], still in the Expanded layout --

@@ -134,6 +134,8 @@ int fl_keys_load(fl_ctx* c, const char* path);   /* merges whatever records the 
 /* MakeCKKSPackedPlaintext(vec, 1, level, nullptr, slots) F.cpp:353; im may be NULL */
 int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out);
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out);                         /* Encrypt F.cpp:380 */
+/* the same for n plaintexts of one level in a dozen launches: *out is ONE batched operand (fl_batch_slice gives ciphertext i) */
+int fl_encrypt_many(fl_ctx* c, const fl_pt* const* pts, int n, fl_ct** out);
 /* TEST ONLY: fixed encryption randomness (v, e0, e1 from SplitMix64(seed)) for the limb-exact parity tests */
 int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out);
 int fl_decrypt(fl_ctx* c, const fl_ct* a, double* re, double* im, int slots);   /* Decrypt + GetRealPackedValue F.cpp:389,402 */

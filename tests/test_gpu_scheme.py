@@ -182,3 +182,20 @@ def test_veneer_sequential_ladder_limb_exact(tmp_path):
     with pytest.raises(RuntimeError, match="no evaluation key"):
         fc.invoke("rotate", [c.import_elem(ct, 1, float(o.sf[1]), o.N // 2)], ints=[11111])   # not a bootstrap index either
     fc.close()
+
+
+def test_batched_encryption(ctx):
+    """fl_encrypt_many: every ciphertext of the batch decrypts to its own plaintext and carries its own randomness."""
+    o, c, seed, sk, pk = ctx
+    n = o.N // 2
+    rng = np.random.default_rng(6)
+    vs = [rng.uniform(-1, 1, n) for _ in range(5)]
+    cts = c.encrypt_many([c.encode(v, level=1) for v in vs])
+    assert len(cts) == 5
+    for v, ct in zip(vs, cts):
+        assert ct.level == 1 and np.abs(c.decrypt(ct) - v).max() < 1e-7
+    same = c.encrypt_many([c.encode(vs[0], level=0)] * 3)            # one plaintext three times: three different ciphertexts
+    a, b, d = (x.export() for x in same)
+    assert (a != b).mean() > 0.99 and (a != d).mean() > 0.99 and (b != d).mean() > 0.99
+    with pytest.raises(RuntimeError):
+        c.encrypt_many([c.encode(vs[0], level=0), c.encode(vs[1], level=2)])   # mixed levels
