@@ -212,8 +212,10 @@ std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, c
         hidden.push_back(fc_.add(u, fc_.encode(bias, (int)u->GetLevel() + 1, slots)));   // product rescaled lazily: bias one level lower
     }
     checkpoint("packed_hidden_block0", fc_.unpack(hidden[0])[0]);
-    // M:360-364 on all 2 x 4 hidden ciphertexts at once
-    const Ctxt act = fc_.bootstrap(fc_.eval_gelu_function(fc_.pack(hidden), -1, 1, gelu_scale, 119));
+    // GELU (M:362) on all 2 x 4 hidden ciphertexts at once.  The reference refreshes every container right here (M:363) because its
+    // unwrap / W2 / re-wrap chain still costs five levels; the packed chain needs two (W2, affine2), so the refresh moves behind
+    // the second affine, where ONE ciphertext (the half that holds the CLS row) is left to bootstrap instead of eight.
+    const Ctxt act = fc_.eval_gelu_function(fc_.pack(hidden), -1, 1, gelu_scale, 119);
     const std::vector<Ctxt> parts = fc_.unpack(act);                                     // [block b][half h] -> index 2 b + h
     checkpoint("packed_gelu_block0", parts[0]);
     lap("Intermediate");
@@ -338,6 +340,7 @@ Ctxt LinformerForward::encoder() {
     o0 = fc_.add(fc_.mult(o0, a2), b2);                                                  // M:410,413
     o1 = fc_.add(fc_.mult(o1, a2), b2);                                                  // M:411,414
     checkpoint("affine2_0", o0);
+    if (packed_) o0 = fc_.bootstrap(o0);                                                  // the refresh of M:363, moved here (see feed_forward_packed)
     std::vector<Ctxt> final0 = fc_.unwrapExpanded(o0, dead_work_ && !packed_ ? 128 : 1);  // M:416 (only element 0 is used)
     if (dead_work_ && !packed_) (void)fc_.unwrapExpanded(o1, tokens_ - 128);             // M:417
     checkpoint("encoder_out", final0[0]);
