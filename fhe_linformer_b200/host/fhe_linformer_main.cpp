@@ -23,11 +23,13 @@ bool has_flag(int argc, char** argv, const std::string& flag) {
 int main(int argc, char** argv) {
     if (argc < 2) {
         std::cout << "Encrypted Linformer text classifier (B200 CKKS engine).\n\nUsage: fhe_linformer [--generate_keys [--secure]] [--verbose]\n"
-                     "       [--root DIR] [--tokens DIR] [--lean] [--resume]\n\n--generate_keys  create context, key pair, relinearisation, rotation and bootstrapping keys under <root>/keys\n"
+                     "       [--root DIR] [--tokens DIR] [--lean] [--packed] [--resume]\n\n--generate_keys  create context, key pair, relinearisation, rotation and bootstrapping keys under <root>/keys\n"
                      "--verbose        per-stage timings and decrypted intermediates\n--root DIR       parent of keys/ weights-20NG/ input/ checkpoint/ (default ..)\n"
                      "--tokens DIR     folder with input_<i>.txt token embeddings (default <root>/tokens)\n--lean           skip operations whose results the circuit never reads\n"
                      "--encrypted-projection  compute the Linformer E/F projections on the server from the encrypted rows\n"
                      "--all-tokens     attention for every row (the circuit of the reference's main_2.cpp)\n"
+                     "--packed         feed-forward block on 128 rows per ciphertext through BSGS diagonal products (same logits, ~4x faster);\n"
+                     "                 give it to --generate_keys as well so that the keys of the packed transforms are written\n"
                      "--resume         start from <root>/checkpoint/encodered.bin instead of running the encoder\n";
         return 0;
     }
@@ -42,7 +44,13 @@ int main(int argc, char** argv) {
         for (int i = 0; i <= 13; ++i) rotations.push_back(1 << i);
         for (int i = 0; i <= 6; ++i) rotations.push_back(-(1 << i));
         rotations.push_back(-512);
-        controller.generate_bootstrapping_and_rotation_keys(rotations, 16384, true, "rotation_keys.txt");
+        if (has_flag(argc, argv, "--packed")) {
+            controller.generate_bootstrapping_keys(16384);
+            controller.generate_packed_keys();                                  // stored with the other automorphism keys below
+            controller.generate_rotation_keys(rotations, true, "rotation_keys.txt");
+        } else {
+            controller.generate_bootstrapping_and_rotation_keys(rotations, 16384, true, "rotation_keys.txt");
+        }
         return 0;
     }
     const bool verbose = has_flag(argc, argv, "--verbose");
@@ -55,6 +63,7 @@ int main(int argc, char** argv) {
     forward.set_dead_work(!has_flag(argc, argv, "--lean"));
     forward.set_encrypted_projection(has_flag(argc, argv, "--encrypted-projection"));
     forward.set_all_token_attention(has_flag(argc, argv, "--all-tokens"));
+    forward.set_packed(has_flag(argc, argv, "--packed"));
     Ctxt encoded;
     if (has_flag(argc, argv, "--resume")) {
         encoded = controller.load_ciphertext(root + "/checkpoint/encodered.bin");
