@@ -136,7 +136,9 @@ template <int BETA>
 __global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
                                                                  const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,
                                                                  size_t up_bs, size_t c_bs, int t_first) {
-    const int t = t_first + blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * kIpb;
+    // grid (coefficients, batch groups, limbs): CTAs are issued x, then y, then z, so all batch groups of one limb run back to back
+    // and that limb's key words (2 beta x N, streamed from HBM once) are served from L2 to every group after the first
+    const int t = t_first + blockIdx.z, l = ks.l, ext = l + T.K, b0 = blockIdx.y * kIpb;
     const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
@@ -189,7 +191,10 @@ __global__ void __launch_bounds__(kThreads, KPR_MAX > 1 ? 4 : 1) inner_product_m
                                                                        MultiKeys mk, DevTables T, KsLevel ks, int batch, size_t acc_bs, size_t up_bs,
                                                                        size_t c_bs) {
     constexpr int IPB = 2;
-    const int t = blockIdx.y, l = ks.l, ext = l + T.K, b0 = blockIdx.z * IPB;
+    // grid (coefficients, batch groups, limbs): for one limb the nk keys' words (nk x 2 beta x N) and the limb of every ciphertext's
+    // extended digits stay in L2 while all batch groups gather from them (the batch used to be the slowest grid dimension: every
+    // group re-streamed the keys from HBM, 15 GB per launch at batch 64)
+    const int t = blockIdx.z, l = ks.l, ext = l + T.K, b0 = blockIdx.y * IPB;
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
@@ -538,7 +543,7 @@ void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange rg) {
     if (rg.count < 0) rg = LimbRange{0, ks.l + t.K};
     if (rg.count == 0) return;
-    const dim3 grid(cdiv(t.N / 2, kThreads), rg.count, (batch + kIpb - 1) / kIpb);
+    const dim3 grid(cdiv(t.N / 2, kThreads), (batch + kIpb - 1) / kIpb, rg.count);
     switch (ks.beta) {
 #define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch, acc_bs, up_bs, c_bs, rg.first); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
@@ -553,7 +558,7 @@ void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc,
     MultiKeys mk{};
     mk.n = nk;
     for (int k = 0; k < nk; ++k) { mk.evk[k] = evks[k]; mk.map[k] = maps[k]; }
-    const dim3 grid(cdiv(t.N, kThreads), ks.l + t.K, (batch + 1) / 2);
+    const dim3 grid(cdiv(t.N, kThreads), (batch + 1) / 2, ks.l + t.K);
     static const bool group = [] { const char* e = std::getenv("FLK_IPM_GROUP"); return !e || e[0] != '0'; }();
     switch (ks.beta) {
 #define FLK_CASE(X) case X: if (group) inner_product_multi_kernel<X, 8><<<grid, kThreads, 0, s>>>(acc, up, c_eval, mk, t, ks, batch, acc_bs, up_bs, c_bs); \
