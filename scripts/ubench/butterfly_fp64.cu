@@ -27,6 +27,24 @@ __device__ __forceinline__ u64 shoup_lazy4(u64 a, u64 w, u64 ws, u64 nq) {
         : "=l"(r) : "l"(a), "l"(w), "l"(ws), "l"(nq));
     return r;
 }
+// variant: Shoup companion scaled to 2^63, the three high partial products chained through multiply-add addends (no carry adds);
+// the quotient is in units of 2q (nq = -2q), result in [0, 8q)
+__device__ __forceinline__ u64 shoup63_lazy8(u64 a, u64 w, u64 ws63, u64 n2q) {
+    u64 r;
+    asm("{\n\t.reg .u32 yl, yh, wl, wh, sl, sh, nl, nh, t1, ml, mh, ql, qh, c, zr;\n\t.reg .u64 mid, h, p, z;\n\t"
+        "mov.b64 {yl, yh}, %1; mov.b64 {wl, wh}, %2; mov.b64 {sl, sh}, %3; mov.b64 {nl, nh}, %4;\n\t"
+        "mul.wide.u32 mid, yl, sh;\n\tmad.wide.u32 mid, yh, sl, mid;\n\t"
+        "mov.b64 {ml, mh}, mid; mov.u32 zr, 0; mov.b64 z, {mh, zr};\n\t"
+        "mad.wide.u32 h, yh, sh, z;\n\tmov.b64 {ql, qh}, h;\n\t"
+        "mul.wide.u32 p, yl, wl;\n\tmad.wide.u32 p, ql, nl, p;\n\tmov.b64 {c, t1}, p;\n\t"
+        "mad.lo.u32 t1, yl, wh, t1;\n\tmad.lo.u32 t1, yh, wl, t1;\n\tmad.lo.u32 t1, ql, nh, t1;\n\tmad.lo.u32 t1, qh, nl, t1;\n\t"
+        "mov.b64 %0, {c, t1};\n\t}"
+        : "=l"(r) : "l"(a), "l"(w), "l"(ws63), "l"(n2q));
+    return r;
+}
+__device__ __forceinline__ void bf_int63(u64& x, u64& y, u64 w, u64 ws, u64 n2q, u64 q8) {
+    const u64 v = shoup63_lazy8(y, w, ws, n2q); const u64 u = x; x = u + v; y = u - v + q8;
+}
 __device__ __forceinline__ void bf_int(u64& x, u64& y, u64 w, u64 ws, u64 nq, u64 q4) {
     const u64 v = shoup_lazy4(y, w, ws, nq); const u64 u = x; x = u + v; y = u - v + q4;
 }
@@ -67,6 +85,15 @@ __device__ __forceinline__ void radix8_int(u64* e, const u64* w, const u64* ws, 
             for (int j = 0; j < half; ++j) bf_int(e[g * 2 * half + j], e[g * 2 * half + half + j], w[(1 << s) - 1 + g], ws[(1 << s) - 1 + g], nq, q4);
     }
 }
+__device__ __forceinline__ void radix8_int63(u64* e, const u64* w, const u64* ws, u64 n2q, u64 q8) {
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { const int half = 4 >> s;
+#pragma unroll
+        for (int g = 0; g < (1 << s); ++g)
+#pragma unroll
+            for (int j = 0; j < half; ++j) bf_int63(e[g * 2 * half + j], e[g * 2 * half + half + j], w[(1 << s) - 1 + g], ws[(1 << s) - 1 + g], n2q, q8);
+    }
+}
 template <int CORR> __device__ __forceinline__ void radix8_f64(double* e, const double* w, const double* wi, const FMod& m) {
 #pragma unroll
     for (int s = 0; s < 3; ++s) { const int half = 4 >> s;
@@ -80,7 +107,7 @@ template <int CORR> __device__ __forceinline__ void radix8_f64(double* e, const 
 // MODE 0: all warps integer; 1: all warps FP64 (CORR); 2: warps with (wid>>2)&1 integer, the others FP64
 template <int MODE, int CORR> __global__ void k_bf(u64* out, long long* cyc, u64 w0, u64 ws0, u64 q, double pd, int it_int, int it_f64) {
     const int wid = threadIdx.x >> 5;
-    const bool do_int = MODE == 0 || (MODE == 2 && ((wid >> 2) & 1));
+    const bool do_int = MODE == 0 || MODE == 3 || (MODE == 2 && ((wid >> 2) & 1));
     u64 acc = 0;
     __syncthreads();
     const long long t0 = clock64();
@@ -89,7 +116,8 @@ template <int MODE, int CORR> __global__ void k_bf(u64* out, long long* cyc, u64
         for (int i = 0; i < 8; ++i) e[i] = threadIdx.x * 8 + i + w0;
         for (int i = 0; i < 7; ++i) { w[i] = w0 + i * 977; ws[i] = ws0 + i * 131; }
         const u64 nq = 0 - q, q4 = q << 2;
-        for (int it = 0; it < it_int; ++it) radix8_int(e, w, ws, nq, q4);
+        if (MODE == 3) for (int it = 0; it < it_int; ++it) radix8_int63(e, w, ws, nq << 1, q << 3);
+        else for (int it = 0; it < it_int; ++it) radix8_int(e, w, ws, nq, q4);
         for (int i = 0; i < 8; ++i) acc += e[i];
     } else {
         double e[8], w[7], wi[7];
@@ -161,7 +189,7 @@ template <int MODE, int CORR> void bf(const char* name, int threads, int bps, in
     const double cyc = mean_cycles(blocks);
     const double warps = (double)bps * threads / 32 / 4;
     double nbf;   // warp-butterflies per sub-partition
-    if (MODE == 0) nbf = warps * it_int * 12.0; else if (MODE == 1) nbf = warps * it_f64 * 12.0; else nbf = warps / 2 * (it_int + it_f64) * 12.0;
+    if (MODE == 0 || MODE == 3) nbf = warps * it_int * 12.0; else if (MODE == 1) nbf = warps * it_f64 * 12.0; else nbf = warps / 2 * (it_int + it_f64) * 12.0;
     const double mhz = 1965.0;   // event time -> cycles needs a clock; printed beside the in-kernel count
     printf("%-34s %4d thr x %d CTA/SM  it_int %5d it_f64 %5d : %6.2f cycles per warp-butterfly per SMSP (warp 0 clock64), %6.2f by event time at %.0f MHz, %.3f ms\n",
            name, threads, bps, it_int, it_f64, cyc / nbf, ms * 1e-3 * mhz * 1e6 / nbf, mhz, ms);
@@ -172,6 +200,8 @@ int main() {
     pipe<5>("IADD (add.u32)", 1); pipe<6>("DFMA + IMAD", 2); pipe<7>("DFMA + IADD", 2); pipe<8>("DFMA + IMAD + IADD", 3); pipe<9>("IMAD + IADD", 2);
     pipe<10>("I2F.F64.S64 + DADD", 2); pipe<11>("2 FP64 + IMAD + IMAD.WIDE", 4);
     bf<0, 0>("integer Shoup (PTX)", 512, 1, 2000, 0); bf<0, 0>("integer Shoup (PTX)", 512, 2, 2000, 0); bf<0, 0>("integer Shoup (PTX)", 1024, 2, 2000, 0);
+    bf<3, 0>("integer Shoup, 2^63 companion", 512, 2, 2000, 0); bf<3, 0>("integer Shoup, 2^63 companion", 1024, 2, 2000, 0); bf<0, 0>("integer Shoup (PTX)", 1024, 2, 2000, 0);
+    bf<3, 0>("integer Shoup, 2^63 companion", 1024, 2, 4000, 0); bf<0, 0>("integer Shoup (PTX)", 1024, 2, 4000, 0);
     bf<1, 0>("FP64, ALU-assisted correction", 512, 1, 0, 2000); bf<1, 0>("FP64, ALU-assisted correction", 512, 2, 0, 2000); bf<1, 0>("FP64, ALU-assisted correction", 1024, 2, 0, 2000);
     bf<1, 1>("FP64, FP64-only correction", 512, 2, 0, 2000);
     bf<1, 2>("FP64, no correction (floor)", 512, 2, 0, 2000);
