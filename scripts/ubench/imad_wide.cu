@@ -22,6 +22,12 @@ template <int OP> __global__ void k(u64* out, u32 c0, u32 c1, int iters) {
                            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(c1));
                            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(b[i]) : "r"(a[i]), "r"(c0));
                            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(c0)); }               // IMAD.WIDE + 3 LOP3 (ALU)
+            if (OP == 8) { asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(x[i]) : "r"((u32)x[i]), "r"((u32)(x[i] >> 32) | 1u));
+                           asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(c1));
+                           asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(b[i]) : "r"(a[i]), "r"(c0)); }               // IMAD.WIDE without addend + 2 LOP3
+            if (OP == 9) { u64 t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b[i]));
+                           asm volatile("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(((u32*)&x[i])[0]), "+r"(((u32*)&x[i])[1]) : "r"((u32)t), "r"((u32)(t >> 32)));
+                           asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"((u32)x[i]), "r"(c1)); }                  // mul.wide + separate 64-bit accumulate (2 adds) + 1 LOP3
             if (OP == 6) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(c1));
                            asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(b[i]) : "r"(a[i]), "r"(c0)); }               // 2 LOP3
             if (OP == 7) { asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(c1));
@@ -48,6 +54,7 @@ int main() {
     run<0>("IMAD (mad.lo.u32)", 1, it); run<0>("IMAD (mad.lo.u32)", 1, it);
     run<1>("IMAD.WIDE.U32 + 64-bit addend", 1, it); run<2>("IMAD.WIDE.U32 (mul.wide)", 1, it); run<3>("IMAD.HI.U32", 1, it);
     run<4>("IMAD.WIDE + IMAD", 2, it); run<6>("2 LOP3", 2, it); run<7>("IMAD + LOP3", 2, it); run<5>("IMAD.WIDE + 3 LOP3", 4, it);
+    run<8>("IMAD.WIDE (no addend) + 2 LOP3", 3, it); run<9>("mul.wide + add.cc/addc + LOP3", 4, it);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
