@@ -234,7 +234,10 @@ Elem Scheme::bootstrap(const Elem& in) {
         eng.rescale(r.data(), ct.data(), 2, 2 * ct.batch);
         ct = r;
     } else {
-        post_fix = P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));   // no limb to spend: fix the scale after StC
+        // No limb to spend on the pre-scaling: the missing factor a = sf0 2^-corr / scale is applied inside EvalMod at no level.
+        // The Chebyshev series is linear in its coefficients and each double-angle step maps b y to b^2 (2 y^2 - 1) when its
+        // constant is b^2 instead of 1, so coefficients scaled by a^(1/2^R) leave EvalMod's output scaled by exactly a.
+        post_fix = P.sf[0] / (ct.scale * std::ldexp(1.0, bp.corr));
     }
     // ---- ModRaise: centred coefficients mod q0 -> all L limbs
     const int B = ct.batch;   // a batched operand is bootstrapped as one: every stage below is a single launch per batch
@@ -270,10 +273,13 @@ Elem Scheme::bootstrap(const Elem& in) {
     auto eval_mod = [&](const Elem& x) {
         std::vector<double> cf = bp.cheb;
         cf[0] *= 0.5;
+        double beta = std::pow(post_fix, std::ldexp(1.0, -bp.R));
+        for (double& c : cf) c *= beta;
         Elem y = cheby_ps(x, cf);
         for (int r = 0; r < bp.R; ++r) {
             Elem sq = square(y);
-            y = add_const(add(sq, sq), -1.0);
+            beta *= beta;
+            y = add_const(add(sq, sq), -beta);
         }
         return y;
     };
@@ -286,7 +292,6 @@ Elem Scheme::bootstrap(const Elem& in) {
     pt.mark("evalmod");
     // ---- SlotsToCoeffs
     for (auto& st : bp.stc) y = apply_stage(*this, st, y, n);
-    if (post_fix != 1.0) y = mult_const(y, post_fix);
     pt.mark("stc");
     return y;
 }

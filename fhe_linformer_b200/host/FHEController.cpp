@@ -210,7 +210,7 @@ vector<int> FHEController::derived_rotations(const vector<int>& listed) const {
 // does -- so the layer is the sum over k < 128 of diag_k (x) rot(x, 128 k) with diag_k[128 i + t] = W[(i + k) mod 128][i]:
 // a diagonal matrix product, evaluated by Engine::linear_transform with 16 baby x 8 giant steps (double hoisting).
 namespace {
-fl_lt* plan_packed(fl_ctx* ctx, int slots, const std::function<double(int, int)>& weight, double scale) {
+fl_lt* plan_packed(fl_ctx* ctx, int slots, const std::function<double(int, int)>& weight, double scale, const vector<double>* column_scale = nullptr) {
     const int D = 128;
     vector<int> shifts(D);
     vector<double> re((size_t)D * slots, 0.0);
@@ -219,7 +219,7 @@ fl_lt* plan_packed(fl_ctx* ctx, int slots, const std::function<double(int, int)>
         double* d = re.data() + (size_t)k * slots;
         for (int i = 0; i < D; ++i) {
             const double v = scale * weight((i + k) % D, i);
-            for (int t = 0; t < D; ++t) d[D * i + t] = v;
+            for (int t = 0; t < D; ++t) d[D * i + t] = column_scale ? v * (*column_scale)[(size_t)t] : v;
         }
     }
     fl_lt* lt = nullptr;
@@ -228,10 +228,12 @@ fl_lt* plan_packed(fl_ctx* ctx, int slots, const std::function<double(int, int)>
 }
 }  // namespace
 
-Ctxt FHEController::packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale) {
+Ctxt FHEController::packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale,
+                                   const vector<double>* column_scale) {
     if (num_slots != 128 * 128) throw std::invalid_argument("packed_linear: the wrapped-expanded layout needs 128 x 128 slots");
+    if (column_scale && column_scale->size() < 128) throw std::invalid_argument("packed_linear: column_scale needs 128 values");
     auto it = packed_.find(name);
-    if (it == packed_.end()) it = packed_.emplace(name, plan_packed(ctx_, num_slots, weight, scale)).first;
+    if (it == packed_.end()) it = packed_.emplace(name, plan_packed(ctx_, num_slots, weight, scale, column_scale)).first;
     int rots[64];
     const int nr = fl_lt_rotations(ctx_, it->second, rots, 64);
     for (int i = 0; i < nr && i < 64; ++i) require_rotation_key(rots[i]);

@@ -179,7 +179,11 @@ public:
     // the result holds y_t = x_t W for every t in the same layout: ONE baby-step/giant-step transform over the 128 diagonals
     // 128 k (fl_lt_apply, ~22 hoisted rotations) instead of one (x) + 7-step ladder per vector (F.cpp:869-883, 982-996).
     // weight(j, i) = W[j][i] with y_i = sum_j x_j W[j][i]; `name` keys the cached plan (plaintext diagonals follow x's level).
-    Ctxt packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale = 1.0);
+    // column_scale (optional, 128 values): output column t (the vector of position t) is additionally scaled by column_scale[t] --
+    // a slot-wise factor of the wrapped-expanded layout folded into the diagonals (e.g. the position-indexed second affine, or a
+    // column mask); it belongs to the plan, so give such a plan its own name.
+    Ctxt packed_linear(const Ctxt& x, const string& name, const std::function<double(int, int)>& weight, double scale = 1.0,
+                       const vector<double>* column_scale = nullptr);
     void generate_packed_keys();                                     // rotation keys of the packed transforms (before any packed forward)
     vector<int> derived_rotations(const vector<int>& listed) const;  // extra indices the batched / hoisted recipes use for a key list
     double rotation_key_bytes() const;                               // device memory held by automorphism keys

@@ -3,6 +3,9 @@
 // the line each step follows is cited as M:<line>.  Slot layouts are those of SURVEY.md section 3.3.
 #include "linformer.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <cmath>
 #include <filesystem>
 #include <tuple>
@@ -25,6 +28,8 @@ double LinformerForward::scalar(const std::string& path) const {
 }
 
 void LinformerForward::checkpoint(const std::string& name, const Ctxt& c) {
+    static const bool trace = std::getenv("FLH_TRACE_LEVELS") != nullptr;
+    if (trace) std::fprintf(stderr, "  [levels] %-28s level %2d  noise degree %d\n", name.c_str(), (int)c->GetLevel(), (int)c->GetNoiseScaleDeg());
     if (sink_) sink_(name, fc_.decrypt_tovector(c, fc_.num_slots), (int)c->GetLevel());
 }
 
@@ -154,7 +159,8 @@ std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctx
     const std::vector<Ctxt> first(rows.begin(), rows.begin() + 128), rest(rows.begin() + 128, rows.end());
     // packed mode builds the same two wrapped ciphertexts from position masks alone (no rotate(-1) chain)
     Ctxt w0 = packed_ ? wrap_rows_packed(first, 0) : fc_.wrapUpExpanded(first);          // M:307-308 / M:392-393
-    Ctxt w1 = packed_ ? wrap_rows_packed(rest, 0) : fc_.wrapUpExpanded(rest);
+    const bool first_half_only = packed_ && !dead_work_;      // packed + lean: nothing downstream reads the second half (see encoder())
+    Ctxt w1 = first_half_only ? Ctxt() : packed_ ? wrap_rows_packed(rest, 0) : fc_.wrapUpExpanded(rest);
     if (!refresh) return {w0, w1};
     const double s = (double)rows.size();
     const double f = scalar(layer("ffn_" + which + "_c0.txt")) + scalar(layer("ffn_" + which + "_c1.txt")) / std::sqrt(s) +
@@ -167,8 +173,9 @@ std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctx
         return fc_.add(fc_.mult(c, a), b);
     };
     w0 = affine(w0);                                                                     // M:314-315
-    w1 = affine(w1);                                                                     // M:316-317
     checkpoint(which + "_0", w0);
+    if (first_half_only) return {fc_.bootstrap(w0), Ctxt()};
+    w1 = affine(w1);                                                                     // M:316-317
     checkpoint(which + "_1", w1);
     const std::vector<Ctxt> fresh = fc_.per_row({w0, w1}, [&](const Ctxt& c) { return fc_.bootstrap(c); });   // M:319-320, as one batch
     return {fresh[0], fresh[1]};
@@ -191,10 +198,11 @@ Ctxt LinformerForward::wrap_rows_packed(const std::vector<Ctxt>& rows, int) {
 // 128-column blocks of W0, scaled by 1/8), GELU and bootstrap on the 2 x 4 hidden ciphertexts as one batched operand, 512 -> 128 as
 // four packed_linear transforms summed.  Replaces unwrapExpanded + matmulRElarge + generate_containers + unwrapRepeatedLarge +
 // matmulCRlarge + wrapUpExpanded (M:325-393; ~100 S rotations) by 8 BSGS products per half (~22 hoisted rotations each).
-std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, const Ctxt& half1) {
+std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, const Ctxt& half1, const std::vector<double>* cls_column_scale) {
     const double gelu_scale = 1.0 / 8.0;                                                 // M:334
     const int slots = fc_.num_slots;
-    const Ctxt x = fc_.pack({half0, half1});
+    const int halves = cls_column_scale ? 1 : 2;                                         // lean tail: the half with the CLS row only
+    const Ctxt x = halves == 1 ? half0 : fc_.pack({half0, half1});
     const std::vector<double> b0 = utils::read_values_from_file(layer("ffn_Wffn_0_bias.txt"));   // 512 values (M:345)
     if (b0.size() < 512) throw std::runtime_error("ffn_Wffn_0_bias.txt: expected 512 values");
     std::vector<Ctxt> hidden;
@@ -211,12 +219,12 @@ std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, c
             for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b0[(size_t)128 * b + i] * gelu_scale;
         hidden.push_back(fc_.add(u, fc_.encode(bias, (int)u->GetLevel() + 1, slots)));   // product rescaled lazily: bias one level lower
     }
-    checkpoint("packed_hidden_block0", fc_.unpack(hidden[0])[0]);
+    checkpoint("packed_hidden_block0", halves == 1 ? hidden[0] : fc_.unpack(hidden[0])[0]);
     // GELU (M:362) on all 2 x 4 hidden ciphertexts at once.  The reference refreshes every container right here (M:363) because its
     // unwrap / W2 / re-wrap chain still costs five levels; the packed chain needs two (W2, affine2), so the refresh moves behind
     // the second affine, where ONE ciphertext (the half that holds the CLS row) is left to bootstrap instead of eight.
     const Ctxt act = fc_.eval_gelu_function(fc_.pack(hidden), -1, 1, gelu_scale, 119);
-    const std::vector<Ctxt> parts = fc_.unpack(act);                                     // [block b][half h] -> index 2 b + h
+    const std::vector<Ctxt> parts = fc_.unpack(act);                                     // [block b][half h] -> index halves b + h
     checkpoint("packed_gelu_block0", parts[0]);
     lap("Intermediate");
     Ctxt sum;
@@ -227,16 +235,21 @@ std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, c
             if (f.empty()) { f = utils::read_values_from_file(w(name + ".txt")); if (f.size() < 128 * 128) throw std::runtime_error(name + ": expected 128 x 128 values"); }
             return f[(size_t)128 * i + j];                                               // y = F . x  (M:373-376)
         };
-        const Ctxt y = fc_.packed_linear(fc_.pack({parts[2 * b], parts[2 * b + 1]}), w(name), weight, 1.0);
+        // lean tail (cls_column_scale): only the half that holds the CLS row goes through W2, with the second affine's factor and
+        // the column mask folded into the diagonals (one plan per value of the factor: it depends on S through c1, c2)
+        const Ctxt y = cls_column_scale
+                           ? fc_.packed_linear(parts[b], w(name) + "@cls*" + std::to_string((*cls_column_scale)[0]), weight, 1.0, cls_column_scale)
+                           : fc_.packed_linear(fc_.pack({parts[2 * b], parts[2 * b + 1]}), w(name), weight, 1.0);
         sum = b == 0 ? y : fc_.add(sum, y);
     }
     const std::vector<double> b2 = utils::read_values_from_file(layer("ffn_Wffn_2_bias.txt"));   // M:378
     std::vector<double> bias((size_t)slots);
     for (int i = 0; i < 128; ++i)
-        for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b2.at((size_t)i);
+        for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b2.at((size_t)i) * (cls_column_scale ? (*cls_column_scale)[(size_t)t] : 1.0);
     sum = fc_.add(sum, fc_.encode(bias, (int)sum->GetLevel() + 1, slots));
-    const std::vector<Ctxt> halves = fc_.unpack(sum);
-    return {halves[0], halves[1]};
+    if (cls_column_scale) return {sum, Ctxt()};
+    const std::vector<Ctxt> out = fc_.unpack(sum);
+    return {out[0], out[1]};
 }
 
 // ---- FFN: 128 -> 512 (scaled by 1/8 so GELU's argument lies in [-1, 1]), GELU, bootstrap, 512 -> 128 (M:325-380) ----------
@@ -319,12 +332,34 @@ Ctxt LinformerForward::encoder() {
     checkpoint("attended_row1", attended[1]);
     auto [half0, half1] = affine_and_refresh(attended, "affine1", true);
     checkpoint("affine1_refreshed_0", half0);
-    const Ctxt residual0 = half0->Clone(), residual1 = half1->Clone();                   // M:322-323
+    const Ctxt residual0 = half0->Clone(), residual1 = half1 ? half1->Clone() : Ctxt();  // M:322-323
 
     Ctxt o0, o1;
+    if (packed_ && !dead_work_) {
+        // Packed AND lean: from W2 on only the CLS row is read (M:416-424), i.e. column 0 of the first half.  The second affine --
+        // (ffn + h) a + b with a, b indexed by position t -- and the column mask of unwrapExpanded(., 1) are folded into the W2
+        // diagonals and into one plaintext product of the residual, so the chain GELU (7 levels) + W2 + pooler product fits the levels
+        // left after the first refresh: the pooler's own bootstrap (M:441) is the only other one of the forward (3 instead of 10).
+        lap("Self-Output");
+        const double sl = (double)tokens_;
+        const double f2l = scalar(layer("ffn_affine2_c0.txt")) + scalar(layer("ffn_affine2_c1.txt")) / std::sqrt(sl) + scalar(layer("ffn_affine2_c2.txt")) / sl;   // M:398-403
+        const std::vector<double> a = utils::read_values_from_file(layer("ffn_affine2_a.txt")), b = utils::read_values_from_file(layer("ffn_affine2_b.txt"));
+        std::vector<double> col(128, 0.0);
+        col[0] = a.at(0) * f2l;                                                          // R(a)[128 j + t] = a[t] meets column t = 0
+        std::vector<double> am((size_t)fc_.num_slots, 0.0), bm((size_t)fc_.num_slots, 0.0);
+        for (int j = 0; j < 128; ++j) { am[(size_t)128 * j] = col[0]; bm[(size_t)128 * j] = b.at(0) * f2l; }
+        Ctxt y = feed_forward_packed(half0, half1, &col).first;                          // a[0] f (W2 g + b2) on column 0
+        const Ctxt res = fc_.mult(residual0, fc_.encode(am, (int)residual0->GetLevel(), fc_.num_slots));   // a[0] f h on column 0
+        y = fc_.add(fc_.add(y, res), fc_.encode(bm, (int)y->GetLevel() + 1, fc_.num_slots));
+        checkpoint("packed_affine2_cls", y);
+        const Ctxt cls = fc_.repeat(y, 128);                                             // F.cpp:1086-1100 for index 0: replicate the kept column
+        checkpoint("encoder_out", cls);
+        lap("Output");
+        return cls;
+    }
     if (packed_) {
         lap("Self-Output");
-        std::tie(o0, o1) = feed_forward_packed(half0, half1);
+        std::tie(o0, o1) = feed_forward_packed(half0, half1, nullptr);
         checkpoint("packed_ffn_0", o0);
     } else {
         const std::vector<Ctxt> ffn = feed_forward(half0, half1, tokens_);

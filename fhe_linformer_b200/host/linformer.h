@@ -71,7 +71,7 @@ private:
     std::vector<Ctxt> self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows);
     std::pair<Ctxt, Ctxt> affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh);
     std::vector<Ctxt> feed_forward(const Ctxt& half0, const Ctxt& half1, int rows);
-    std::pair<Ctxt, Ctxt> feed_forward_packed(const Ctxt& half0, const Ctxt& half1);
+    std::pair<Ctxt, Ctxt> feed_forward_packed(const Ctxt& half0, const Ctxt& half1, const std::vector<double>* cls_column_scale);
     Ctxt wrap_rows_packed(const std::vector<Ctxt>& rows, int first_position);
 
     FHEController& fc_;

@@ -246,6 +246,7 @@ def _sim_tail(s, cp, model, out, S, tanh_scale):
     f2 = model["c2"][0] + model["c2"][1] / math.sqrt(S) + model["c2"][2] / S
     o = [h * s.repeated(model["a2"], f2) + s.repeated(model["b2n"], f2) for h in o]
     cp["affine2_0"] = o[0]
+    cp["packed_affine2_cls"] = s.mask_mod_n(o[0], 128, 0)       # packed + lean keeps the CLS column only (affine and mask folded into W2)
     enc = s.unwrapExpanded(o[0], 1)[0]
     cp["encoder_out"] = enc
     # pooler (M:427-451)

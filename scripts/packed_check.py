@@ -22,6 +22,16 @@ for _ in range(3):
 led = fc.ckks.ledger_dump(); fc.ckks.ledger(False)
 print("packed: %.3f s/sample (%s) err %.2e; rotations %d" % (sorted(ts)[1], " ".join("%.3f" % x for x in ts), np.abs(lg[:8] - ref[:8]).max(), sum(n for k, (n, _) in led.items() if k.startswith("rotate@")) // 3))
 print("   stages", {k: round(v, 3) for k, v in st.items()})
+cps = {}
+lgl, stl, _ = fc.forward(dirs, packed=True, dead_work=False, checkpoints=cps)
+print("packed+lean first: err %.2e class %d" % (np.abs(lgl[:8] - ref[:8]).max(), np.argmax(lgl[:8])))
+for k, (v, lvl) in cps.items():
+    if k.startswith(("packed", "encoder", "pooler")): print("  cp %-24s level %2d  max|v| %.3f" % (k, lvl, np.abs(v).max()))
+ts = []
+for _ in range(3):
+    t = time.time(); lgl, stl, _ = fc.forward(dirs, packed=True, dead_work=False); ts.append(time.time() - t)
+print("packed+lean: %.3f s/sample (%s) err %.2e" % (sorted(ts)[1], " ".join("%.3f" % x for x in ts), np.abs(lgl[:8] - ref[:8]).max()))
+print("   stages", {k: round(v, 3) for k, v in stl.items()})
 fc.forward(dirs, dead_work=True)
 ts = []
 for _ in range(2):

@@ -76,6 +76,18 @@ def test_packed_mode_matches_slot_simulator(setup):
     assert np.abs(logits - ref).max() < LOGIT_TOL and int(np.argmax(logits)) == int(np.argmax(ref))
     rotations = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))
     assert rotations < 2500, rotations          # 13 637 + bootstraps in the faithful circuit at S = 129
+    # packed + lean: only what the logits read -- the half with the CLS row through the FFN, the second affine and the column mask
+    # folded into the W2 diagonals, no refresh between GELU and the pooler (whose own bootstrap then runs on the last limb)
+    fc.ckks.ledger(True); fc.ckks.ledger_reset()
+    got_lean = {}
+    lean, _, _ = fc.forward(dirs, packed=True, dead_work=False, checkpoints=got_lean)
+    led_lean = fc.ckks.ledger_dump(); fc.ckks.ledger(False)
+    assert "packed_affine2_cls" in got_lean and "affine2_0" not in got_lean
+    for name, (slots, level) in got_lean.items():
+        assert np.abs(slots - ref_cp[name]).max() < CHECKPOINT_TOL, name
+    assert np.abs(lean - ref).max() < LOGIT_TOL and int(np.argmax(lean)) == int(np.argmax(ref))
+    rotations_lean = sum(n for k, (n, _) in led_lean.items() if k.startswith("rotate@"))
+    assert rotations_lean < rotations, (rotations_lean, rotations)      # one bootstrap and the second half's transforms fewer
     # a packed forward needs the keys of its transforms: a controller without them fails loudly instead of generating keys on the fly
     from fhe_linformer_b200 import host
     bare = host.FHEController(root=setup[4]).generate()

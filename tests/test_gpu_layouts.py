@@ -223,3 +223,26 @@ def test_bootstrap_with_openfhe_evalmod_conventions(monkeypatch):
     assert float(np.abs(c.decrypt(b) - v).max()) < 2e-4
     monkeypatch.delenv("FLK_BOOT_OPENFHE")
     c.close()
+
+
+def test_bootstrap_of_a_ciphertext_on_its_last_limb():
+    """A ciphertext with a single limb left has no limb for the pre-scaling; the missing factor is carried through EvalMod
+    (coefficients and double-angle constants), so the refresh lands on the same level as from any other level and is as exact.
+    The packed + lean forward relies on it (the pooler's refresh happens on the last limb there)."""
+    from fhe_linformer_b200 import CKKS
+    c = CKKS(logN=13, L=24, dnum=4, sparse_h=64)
+    c.keygen(); c.gen_mult_key()
+    n = c.N // 2
+    c.bootstrap_setup((3, 3), n)
+    c.bootstrap_keygen(n)
+    v = np.random.default_rng(9).uniform(-1, 1, n)
+    ref = c.bootstrap(c.encrypt(v, level=c.L - 2))
+    last = c.bootstrap(c.encrypt(v, level=c.L - 1))
+    assert last.level == ref.level, (last.level, ref.level)
+    assert float(np.abs(c.decrypt(last) - v).max()) < 2e-4
+    # a pending rescale that ends on the last limb takes the same route
+    prod = c.mult(c.encrypt(v, level=c.L - 2), c.encode(np.full(n, 0.5), level=c.L - 2))
+    got = c.bootstrap(prod)
+    assert got.level == ref.level
+    assert float(np.abs(c.decrypt(got) - 0.5 * v).max()) < 2e-4
+    c.close()
