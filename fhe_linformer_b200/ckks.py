@@ -17,6 +17,7 @@ _SIGS = {
     "fl_import_keys": (ci, [vp, vp, vp]), "fl_import_evk": (ci, [vp, u32, vp]),
     "fl_keys_save": (ci, [vp, C.c_char_p]), "fl_keys_load": (ci, [vp, C.c_char_p]),
     "fl_encode": (ci, [vp, vp, vp, ci, ci, ci, C.POINTER(vp)]),
+    "fl_encode_many": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(vp)]),
     "fl_encrypt": (ci, [vp, vp, C.POINTER(vp)]), "fl_encrypt_seeded": (ci, [vp, vp, u64, C.POINTER(vp)]),
     "fl_encrypt_many": (ci, [vp, vp, ci, C.POINTER(vp)]),
     "fl_decrypt": (ci, [vp, vp, vp, vp, ci]), "fl_decode": (ci, [vp, vp, vp, vp, ci]),
@@ -144,6 +145,13 @@ class CKKS(Engine):
         im = np.ascontiguousarray(v.imag, np.float64) if np.iscomplexobj(v) else None
         return self._out(self.lib.fl_encode, _ptr(re), _ptr(im) if im is not None else None, len(re), level, slots)
 
+    def encode_many(self, rows, level=0, slots=None):
+        """Several real vectors of one length as ONE batched plaintext (fl_encode_many); unpack() gives the elements."""
+        m = np.ascontiguousarray(np.asarray(rows, np.float64))
+        if m.ndim != 2: raise ValueError("encode_many: a 2-D array of real rows expected")
+        slots = slots or self.N // 2
+        return self._out(self.lib.fl_encode_many, _ptr(m), m.shape[0], m.shape[1], level, slots)
+
     def encrypt(self, x, level=0, slots=None, seed=None):
         p = x if isinstance(x, Elem) else self.encode(x, level, slots)
         if seed is None:
@@ -152,6 +160,7 @@ class CKKS(Engine):
 
     def encrypt_many(self, plaintexts):
         """Encrypt of several plaintexts of one level in one batched call; returns the list of ciphertexts."""
+        if isinstance(plaintexts, Elem): plaintexts = [plaintexts]          # one batched plaintext (encode_many)
         arr = (vp * len(plaintexts))(*[p.h for p in plaintexts])
         return self.unpack(self._out(self.lib.fl_encrypt_many, arr, len(plaintexts)))
 

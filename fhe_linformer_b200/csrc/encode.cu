@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kThreads) fft_inv_stage_kernel(double* __restr
                                                                  const double* __restrict__ cim) {
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= n / 2) return;
+    re += (size_t)blockIdx.y * n; im += (size_t)blockIdx.y * n;      // one slot vector of the batch per grid row
     const int lenh = len >> 1, j = t % lenh, i = (t / lenh) * len;
     const uint32_t idx = inv_twiddle_index(rot, j, len, 4u * n);
     inv_butterfly(re[i + j], im[i + j], re[i + j + lenh], im[i + j + lenh], cre[idx], cim[idx]);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kFftBlock / 2) fft_inv_block_kernel(double* __
                                                                       const uint32_t* __restrict__ rot, const double* __restrict__ cre,
                                                                       const double* __restrict__ cim) {
     __shared__ double sr[kFftBlock], si[kFftBlock];
+    re += (size_t)blockIdx.y * n; im += (size_t)blockIdx.y * n;
     const int base = blockIdx.x * first_len, t = threadIdx.x;
     for (int k = t; k < first_len; k += blockDim.x) { sr[k] = re[base + k]; si[k] = im[base + k]; }
     __syncthreads();
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(kThreads) encode_finish_kernel(u64* __restrict
                                                                  int slots, int log_slots, int gap, double scale, DevTables T, int l, int kext) {
     const int t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= 2 * slots) return;
+    re += (size_t)blockIdx.y * slots; im += (size_t)blockIdx.y * slots; dst += (size_t)blockIdx.y * (l + kext) * T.N;
     const int i = t < slots ? t : t - slots;
     const int src = log_slots ? (int)(__brev((unsigned)i) >> (32 - log_slots)) : 0;
     const double x = (t < slots ? re : im)[src];
@@ -182,16 +185,17 @@ void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& 
     uniform_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), sel.n), kThreads, 0, s>>>(dst, key, nonce, t, sel);
     FLK_CUDA(cudaGetLastError());
 }
+// batch > 1: re / im hold `batch` slot vectors back to back (each `slots` long), dst `batch` plaintexts back to back
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,
-                   const double* cim, cudaStream_t s, int kext) {
+                   const double* cim, cudaStream_t s, int kext, int batch) {
     int log_slots = 0;
     while ((1 << log_slots) < slots) ++log_slots;
     int len = slots;
-    for (; len > kFftBlock; len >>= 1) fft_inv_stage_kernel<<<cdiv(slots / 2, kThreads), kThreads, 0, s>>>(re, im, slots, len, rot, cre, cim);
-    if (len >= 2) fft_inv_block_kernel<<<slots / len, std::max(32, std::min(len / 2, kFftBlock / 2)), 0, s>>>(re, im, slots, len, rot, cre, cim);
+    for (; len > kFftBlock; len >>= 1) fft_inv_stage_kernel<<<dim3(cdiv(slots / 2, kThreads), batch), kThreads, 0, s>>>(re, im, slots, len, rot, cre, cim);
+    if (len >= 2) fft_inv_block_kernel<<<dim3(slots / len, batch), std::max(32, std::min(len / 2, kFftBlock / 2)), 0, s>>>(re, im, slots, len, rot, cre, cim);
     const int gap = (t.N / 2) / slots;
-    if (gap > 1) FLK_CUDA(cudaMemsetAsync(dst, 0, (size_t)(l + kext) * t.N * 8, s));
-    encode_finish_kernel<<<cdiv((size_t)2 * slots, kThreads), kThreads, 0, s>>>(dst, re, im, slots, log_slots, gap, scale, t, l, kext);
+    if (gap > 1) FLK_CUDA(cudaMemsetAsync(dst, 0, (size_t)batch * (l + kext) * t.N * 8, s));
+    encode_finish_kernel<<<dim3(cdiv((size_t)2 * slots, kThreads), batch), kThreads, 0, s>>>(dst, re, im, slots, log_slots, gap, scale, t, l, kext);
     FLK_CUDA(cudaGetLastError());
 }
 

@@ -156,6 +156,6 @@ void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& 
 // special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd);
 // kext > 0 appends the residues modulo the first kext special limbs (plaintexts in the extended basis Q_l u P)
 void launch_encode(const DevTables& t, u64* dst, double* re, double* im, int slots, double scale, int l, const uint32_t* rot, const double* cre,
-                   const double* cim, cudaStream_t s, int kext = 0);
+                   const double* cim, cudaStream_t s, int kext = 0, int batch = 1);
 
 }  // namespace flk

@@ -2,7 +2,9 @@
 // and Chebyshev series (EvalChebyshevFunction, FHEController.cpp:486,1319-1335) with a depth-optimal
 // baby-step / giant-step (Paterson-Stockmeyer) schedule: depth ceil(log2(deg+1)), the same budget OpenFHE's
 // EvalChebyshevSeriesPS needs (reference table Utils.h:127-153).
+#include <algorithm>
 #include <cmath>
+#include <functional>
 
 #include "scheme.h"
 
@@ -75,7 +77,57 @@ Elem Scheme::inner_linear(const std::vector<Elem>& T, const std::vector<double>&
     return weighted_sum(terms, w);
 }
 
+// Products of independent pairs as ONE batched EvalMult per group of operands that share level, degree and scale (one tensor
+// product, one relinearisation for the whole group).  At the sizes of the forward (N = 2^15, a dozen limbs, one ciphertext) a
+// key switch is a string of launches that each fill a fraction of the chip, so n products in one call cost little more than one.
+// b may hold a single element: it multiplies all.  With `align` every side is first brought to the deepest level among its
+// elements (what EvalMult would do pairwise when the partner is that deep anyway); without it nothing is adjusted here, so no
+// product lands deeper than its own EvalMult would put it.
+std::vector<Elem> Scheme::mult_each(std::vector<Elem> a, std::vector<Elem> b, bool align) {
+    const size_t n = a.size();
+    if (b.size() != n && b.size() != 1) throw std::invalid_argument("mult_each: operand counts differ");
+    std::vector<Elem> out(n);
+    if (n == 0) return out;
+    auto deepen = [&](std::vector<Elem>& v) {
+        size_t ref = 0;
+        for (size_t i = 1; i < v.size(); ++i)
+            if (v[i].l < v[ref].l || (v[i].l == v[ref].l && v[i].deg > v[ref].deg)) ref = i;
+        const Elem target = v[ref];
+        for (Elem& e : v)
+            if (e.l != target.l || e.deg != target.deg) { Elem r = target; adjust_pair(e, r); }
+    };
+    if (align) { deepen(a); deepen(b); }
+    auto same = [](const Elem& x, const Elem& y) { return x.l == y.l && x.deg == y.deg && x.scale == y.scale && x.batch == y.batch && x.slots == y.slots; };
+    std::vector<char> done(n, 0);
+    for (size_t first = 0; first < n; ++first) {
+        if (done[first]) continue;
+        std::vector<size_t> grp;
+        for (size_t i = first; i < n; ++i)
+            if (!done[i] && same(a[i], a[first]) && (b.size() == 1 || same(b[i], b[first]))) { grp.push_back(i); done[i] = 1; }
+        if (grp.size() == 1) { out[first] = mult(a[first], b[b.size() == 1 ? 0 : first]); continue; }
+        std::vector<Elem> ga, gb;
+        const int each = a[first].batch;
+        for (size_t i : grp) {
+            ga.push_back(a[i]);
+            if (b.size() > 1) gb.push_back(b[i]);
+            else if (each > 1) gb.push_back(b[0]);       // a batched multiplier is repeated; a single one is broadcast by EvalMult
+        }
+        const Elem prod = mult(pack(ga), gb.empty() ? b[0] : pack(gb));
+        const size_t words = (size_t)each * prod.words_each(P.N);
+        for (size_t g = 0; g < grp.size(); ++g) {
+            Elem& o = out[grp[g]];
+            o = prod;
+            o.off = prod.off + g * words;
+            o.batch = each;
+        }
+    }
+    return out;
+}
+
 // Chebyshev series sum c[i] T_i(x) (true coefficients, c[0] not halved), x already mapped to [-1,1].
+// Level-synchronous Paterson-Stockmeyer: the baby steps of one depth (T_i, 2^(d-1) < i <= 2^d) are independent and go
+// through mult_each together, and so do the products q T_g of all nodes at one height of the recursive split; a degree-300
+// series is 12 batched EvalMult calls instead of 49 single ones, on the same tree and with the same level budget.
 Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
     std::vector<double> c = c_in;
     const int n = poly_degree(c);
@@ -84,14 +136,41 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
     int D = 0;
     while ((1 << D) < n + 1) ++D;
     const int kl = (D + 1) / 2, k = 1 << kl, m = D - kl;
-    // baby steps T_1 .. T_k  (depth ceil(log2 i))
+    // baby steps T_1 .. T_k  (depth ceil(log2 i)): T_i = 2 T_a T_b - T_(b-a) with a = floor(i/2), b = i - a, so b - a is 0 or 1
     std::vector<Elem> T(k + 1);
     T[1] = x;
-    for (int i = 2; i <= k; ++i) {
-        const int a = i / 2, b = i - a;
-        Elem p = mult(T[a], T[b]);
-        p = add(p, p);
-        T[i] = a == b ? add_const(p, -1.0) : sub(p, T[1]);
+    if (T[1].deg == 2) rescale_inplace(T[1]);
+    for (int lo = 1; lo < k; lo *= 2) {
+        std::vector<Elem> as, bs;
+        for (int i = lo + 1; i <= std::min(2 * lo, k); ++i) { as.push_back(T[i / 2]); bs.push_back(T[i - i / 2]); }
+        std::vector<Elem> prod = mult_each(as, bs, true);
+        // doubling and the pending rescale on the whole round at once when it came back as one batch
+        bool one = prod.size() > 1;
+        for (size_t j = 1; j < prod.size() && one; ++j)
+            one = prod[j].mem == prod[0].mem && prod[j].off == prod[0].off + j * (size_t)prod[0].batch * prod[0].words_each(P.N);
+        Elem all;
+        if (one) {
+            all = prod[0];
+            all.batch = prod[0].batch * (int)prod.size();
+            all = add(all, all);
+            rescale_inplace(all);
+        }
+        Elem t1;                                                 // T_1 at the level of this round, adjusted once
+        for (size_t j = 0; j < prod.size(); ++j) {
+            const int i = lo + 1 + (int)j;
+            Elem p;
+            if (one) {
+                p = all;
+                p.off = all.off + j * (size_t)prod[0].batch * all.words_each(P.N);
+                p.batch = prod[0].batch;
+            } else {
+                p = add(prod[j], prod[j]);
+                rescale_inplace(p);
+            }
+            if (i % 2 == 0) { T[i] = add_const(p, -1.0); continue; }
+            if (!t1.valid()) { t1 = T[1]; Elem r = p; adjust_pair(t1, r); }
+            T[i] = sub(p, t1);
+        }
     }
     // giant steps T_{k 2^j}
     std::vector<Elem> Gs(m + 1);
@@ -102,39 +181,61 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
         Gs[j] = add_const(p, -1.0);
     }
     ps_settled_.clear(); ps_aligned_.clear();   // per-evaluation caches of inner_linear
-    // recursive split p = q T_g + r
-    struct Rec {
-        Scheme* s; const std::vector<Elem>& T; const std::vector<Elem>& Gs; int k;
-        Elem run(const std::vector<double>& p, int j, double& c0) {
-            const int d = poly_degree(p);
-            if (j == 0 || d < k) {          // baby polynomial (deg < k)
-                c0 = p.empty() ? 0.0 : p[0];
-                return s->inner_linear(T, p, std::min(d, k - 1));
-            }
-            const int g = k << (j - 1);
-            if (d < g) return run(p, j - 1, c0);
-            std::vector<double> q(d - g + 1, 0.0), r(g, 0.0);
-            for (int i = 0; i < g && i <= d; ++i) r[i] = p[i];
-            q[0] = p[g];
-            for (int i = g + 1; i <= d; ++i) { q[i - g] = 2.0 * p[i]; r[2 * g - i] -= p[i]; }
-            double q0 = 0, r0 = 0;
-            Elem qe = run(q, j - 1, q0);
-            Elem re = run(r, j - 1, r0);
-            // (qe + q0) * T_g + re + r0
-            Elem prod;
-            if (qe.valid()) {
-                Elem qq = negligible(q0) ? qe : s->add_const(qe, q0);
-                prod = s->mult(qq, Gs[j - 1]);
-            } else if (!negligible(q0)) {
-                prod = s->mult_const(Gs[j - 1], q0);
-            }
-            c0 = r0;
-            if (prod.valid() && re.valid()) return s->add(prod, re);
-            return prod.valid() ? prod : re;
+    // recursive split p = q T_g + r, g = k 2^(j-1), laid out as a tree first and evaluated height by height
+    struct Node { std::vector<double> p; int j = 0, q = -1, r = -1; double c0 = 0; Elem val; };
+    std::vector<Node> nodes;
+    std::function<int(const std::vector<double>&, int)> build = [&](const std::vector<double>& p, int j) -> int {
+        const int d = poly_degree(p);
+        if (j == 0 || d < k) {                   // baby polynomial (deg < k)
+            Node nd; nd.p = p; nd.j = 0;
+            nodes.push_back(std::move(nd));
+            return (int)nodes.size() - 1;
         }
-    } rec{this, T, Gs, k};
-    double c0 = 0;
-    Elem res = rec.run(c, m, c0);
+        const int g = k << (j - 1);
+        if (d < g) return build(p, j - 1);
+        std::vector<double> q(d - g + 1, 0.0), r(g, 0.0);
+        for (int i = 0; i < g && i <= d; ++i) r[i] = p[i];
+        q[0] = p[g];
+        for (int i = g + 1; i <= d; ++i) { q[i - g] = 2.0 * p[i]; r[2 * g - i] -= p[i]; }
+        const int qi = build(q, j - 1), ri = build(r, j - 1);
+        Node nd; nd.j = j; nd.q = qi; nd.r = ri;
+        nodes.push_back(std::move(nd));
+        return (int)nodes.size() - 1;
+    };
+    const int root = build(c, m);
+    for (Node& nd : nodes) {
+        if (nd.j != 0) continue;
+        const int d = poly_degree(nd.p);
+        nd.c0 = nd.p.empty() ? 0.0 : nd.p[0];
+        nd.val = inner_linear(T, nd.p, std::min(d, k - 1));
+    }
+    for (int h = 1; h <= m; ++h) {
+        std::vector<int> with_q;                 // nodes of this height whose quotient is a ciphertext: (q + q0) T_g in one call
+        std::vector<Elem> qs;
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            if (nodes[i].j != h) continue;
+            const Node& q = nodes[nodes[i].q];
+            if (!q.val.valid()) continue;
+            with_q.push_back((int)i);
+            qs.push_back(negligible(q.c0) ? q.val : add_const(q.val, q.c0));
+        }
+        const std::vector<Elem> prods = mult_each(qs, {Gs[h - 1]}, false);
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            Node& nd = nodes[i];
+            if (nd.j != h) continue;
+            const Node& q = nodes[nd.q];
+            const Node& r = nodes[nd.r];
+            Elem prod;
+            const auto at = std::find(with_q.begin(), with_q.end(), (int)i);
+            if (at != with_q.end()) prod = prods[(size_t)(at - with_q.begin())];
+            else if (!negligible(q.c0)) prod = mult_const(Gs[h - 1], q.c0);
+            nd.c0 = r.c0;
+            if (prod.valid() && r.val.valid()) nd.val = add(prod, r.val);
+            else nd.val = prod.valid() ? prod : r.val;
+        }
+    }
+    double c0 = nodes[root].c0;
+    Elem res = nodes[root].val;
     ps_settled_.clear(); ps_aligned_.clear();
     if (!res.valid()) res = mult_const(x, 0.0);
     return negligible(c0) ? res : add_const(res, c0);

@@ -431,6 +431,28 @@ Elem Scheme::encode(const cplx* vals, int n, int level, int slots, int deg) {
     return encode_at(vals, n, P.L - level, scale, slots, deg);
 }
 
+// B real slot vectors (n values each, row-major) -> ONE batched plaintext: one upload, one special FFT, one finish and one
+// transform for all of them instead of seven launches and a staged copy per vector (a forward encodes S + 64 input rows).
+// Element b is bit-identical to encode_real(vals + b n, ...): same kernels, one more grid dimension.
+Elem Scheme::encode_many_real(const double* vals, int B, int n, int level, int slots) {
+    if (level < 0 || level >= P.L) throw std::invalid_argument("encode: level out of range");
+    if (B < 1) throw std::invalid_argument("encode (batched): no vectors");
+    const int Nh = P.N / 2, l = P.L - level;
+    if (slots < 1 || slots > Nh || (slots & (slots - 1))) throw std::invalid_argument("encode: slots must be a power of two <= N/2");
+    if (n < 0 || n > slots) throw std::invalid_argument("encode (batched): more values than slots");
+    DevFft& f = dev_fft(slots);
+    const size_t each = (size_t)slots;
+    double* d = (double*)eng.alloc(2 * each * B);                 // [B][slots] real parts, then [B][slots] imaginary parts (zero)
+    FLK_CUDA(cudaMemsetAsync(d, 0, 2 * each * B * sizeof(double), eng.stream));
+    // the source is the caller's (pageable) memory: the runtime stages it and returns once it has been read
+    FLK_CUDA(cudaMemcpy2DAsync(d, each * sizeof(double), vals, (size_t)n * sizeof(double), (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, eng.stream));
+    Elem e = make(1, l, 1, P.sf[level], slots, B);
+    launch_encode(eng.T, e.data(), d, d + each * B, slots, P.sf[level], l, f.rot, f.cre, f.cim, eng.stream, 0, B);
+    eng.ntt(e.data(), sel_range(0, l), B, (size_t)l * P.N);
+    eng.release((u64*)d);
+    return e;
+}
+
 Elem Scheme::encode_real(const double* vals, int n, int level, int slots) {
     std::vector<cplx> v(n);
     for (int i = 0; i < n; ++i) v[i] = cplx(vals[i], 0.0);
@@ -481,10 +503,11 @@ Elem Scheme::encrypt_many(const std::vector<const Elem*>& pts) {
     if (!pk_) throw std::runtime_error("Encrypt: no public key");
     if (pts.empty()) throw std::invalid_argument("Encrypt: no plaintexts");
     const Elem& f = *pts[0];
+    const bool one_batched = pts.size() == 1 && f.batch > 1;      // a batched plaintext (encode_many_real) instead of a list
     for (const Elem* p : pts)
-        if (p->ncomp != 1 || p->batch != 1 || p->l != f.l || p->deg != f.deg || p->scale != f.scale || p->slots != f.slots)
+        if (p->ncomp != 1 || (p->batch != 1 && !one_batched) || p->l != f.l || p->deg != f.deg || p->scale != f.scale || p->slots != f.slots)
             throw std::invalid_argument("Encrypt (batched): plaintexts must share level, degree, scale and slot count");
-    const int B = (int)pts.size(), l = f.l, N = P.N;
+    const int B = one_batched ? f.batch : (int)pts.size(), l = f.l, N = P.N;
     const size_t pl = (size_t)l * N, pkl = (size_t)P.L * N, cs = 2 * pl;
     const LimbSel sel = sel_range(0, l);
     Elem ct = make(2, l, f.deg, f.scale, f.slots, B);
@@ -501,7 +524,14 @@ Elem Scheme::encrypt_many(const std::vector<const Elem*>& pts) {
     // c0 = pk0 v + e0 + pt
     launch_ew(eng.T, EwOp::Mul, t, v, pk_, sel, 1, B, pl, 0, 0, eng.stream);
     launch_ew(eng.T, EwOp::Add, t, t, e, sel, 1, B, pl, pl, 0, eng.stream);
-    for (int b = 0; b < B; ++b) launch_ew(eng.T, EwOp::Add, ct.data() + (size_t)b * cs, t + (size_t)b * pl, pts[b]->data(), sel, 1, 1, 0, 0, 0, eng.stream);
+    bool contiguous = true;                                       // slices of one batched plaintext, in order: one launch adds them all
+    for (int b = 1; b < B && !one_batched && contiguous; ++b) contiguous = pts[b]->data() == pts[0]->data() + (size_t)b * pl;
+    if (contiguous) {
+        FLK_CUDA(cudaMemcpy2DAsync(ct.data(), cs * 8, t, pl * 8, pl * 8, B, cudaMemcpyDeviceToDevice, eng.stream));
+        launch_ew(eng.T, EwOp::Add, ct.data(), ct.data(), f.data(), sel, 1, B, cs, pl, 0, eng.stream);
+    } else {
+        for (int b = 0; b < B; ++b) launch_ew(eng.T, EwOp::Add, ct.data() + (size_t)b * cs, t + (size_t)b * pl, pts[b]->data(), sel, 1, 1, 0, 0, 0, eng.stream);
+    }
     // c1 = pk1 v + e1
     sample(e, 1);
     launch_ew(eng.T, EwOp::Mul, t, v, pk_ + pkl, sel, 1, B, pl, 0, 0, eng.stream);

@@ -92,6 +92,7 @@ public:
 
     // ---- encode / encrypt / decrypt (MakeCKKSPackedPlaintext F.cpp:353, Encrypt :380, Decrypt :389) ----
     Elem encode(const cplx* vals, int n, int level, int slots, int deg = 1);
+    Elem encode_many_real(const double* vals, int B, int n, int level, int slots);   // one batched plaintext
     Elem encode_real(const double* vals, int n, int level, int slots);
     Elem encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg);   // explicit limb count / scale
     Elem encrypt(const Elem& pt);
@@ -183,6 +184,7 @@ private:
     Elem binary(const Elem& a, const Elem& b, bool subtract);
     // evaluation helpers
     Elem cheby_ps(const Elem& x, const std::vector<double>& c);
+    std::vector<Elem> mult_each(std::vector<Elem> a, std::vector<Elem> b, bool align);   // independent products as one batched EvalMult
     Elem inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto);
     std::vector<Elem> ps_settled_;                          // inner_linear caches, valid during one cheby_ps evaluation
     std::map<std::pair<int, int>, Elem> ps_aligned_;

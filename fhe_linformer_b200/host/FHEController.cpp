@@ -496,9 +496,31 @@ vector<Ctxt> FHEController::encrypt_many(const vector<Ptxt>& plaintexts) {
     return out;
 }
 vector<Ctxt> FHEController::read_expanded_inputs(const vector<string>& filenames, double scale) {
-    vector<Ptxt> pts;
-    for (const string& f : filenames) pts.push_back(read_plain_expanded_input(f, 0, scale));
-    return encrypt_many(pts);
+    if (!batch_rows) {
+        vector<Ptxt> pts;
+        for (const string& f : filenames) pts.push_back(read_plain_expanded_input(f, 0, scale));
+        return encrypt_many(pts);
+    }
+    // all rows of a chunk as one batched plaintext (one upload, one encoding) and one batched encryption
+    vector<Ctxt> out;
+    for (size_t first = 0; first < filenames.size(); first += (size_t)max_rows_per_batch) {
+        const size_t last = std::min(filenames.size(), first + (size_t)max_rows_per_batch), count = last - first;
+        vector<double> slots(count * (size_t)num_slots);
+        for (size_t i = 0; i < count; ++i) {
+            const vector<double> v = stretch(read_values_from_file(filenames[first + i]), 128, 128, 128, scale);
+            std::copy(v.begin(), v.begin() + std::min(v.size(), (size_t)num_slots), slots.begin() + i * (size_t)num_slots);
+        }
+        fl_elem* pt = nullptr;
+        need(fl_encode_many(ctx_, slots.data(), (int)count, num_slots, 0, num_slots, &pt), "MakeCKKSPackedPlaintext");
+        const fl_elem* one[1] = {pt};
+        fl_elem* ct = nullptr;
+        const int rc = fl_encrypt_many(ctx_, one, 1, &ct);
+        fl_elem_free(pt);
+        need(rc, "Encrypt");
+        const vector<Ctxt> part = unpack(wrap(ct));
+        out.insert(out.end(), part.begin(), part.end());
+    }
+    return out;
 }
 Ptxt FHEController::read_plain_expanded_input(const string& filename, int level, double scale) {
     return encode(stretch(read_values_from_file(filename), 128, 128, 128, scale), level, num_slots);

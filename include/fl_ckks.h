@@ -133,8 +133,12 @@ int fl_keys_load(fl_ctx* c, const char* path);   /* merges whatever records the 
 
 /* MakeCKKSPackedPlaintext(vec, 1, level, nullptr, slots) F.cpp:353; im may be NULL */
 int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, int slots, fl_pt** out);
+/* `count` real vectors (n values each, row-major in re) -> ONE batched plaintext in one upload and five launches; element i is
+   bit-identical to fl_encode(re + i n, NULL, n, ...).  The read_*_input loops of a forward (F.cpp:628-649 per file) go through it. */
+int fl_encode_many(fl_ctx* c, const double* re, int count, int n, int level, int slots, fl_pt** out);
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out);                         /* Encrypt F.cpp:380 */
-/* the same for n plaintexts of one level in a dozen launches: *out is ONE batched operand (fl_batch_slice gives ciphertext i) */
+/* the same for n plaintexts of one level in a dozen launches: *out is ONE batched operand (fl_batch_slice gives ciphertext i).
+   n = 1 with a batched plaintext (fl_encode_many) encrypts every element of it. */
 int fl_encrypt_many(fl_ctx* c, const fl_pt* const* pts, int n, fl_ct** out);
 /* TEST ONLY: fixed encryption randomness (v, e0, e1 from SplitMix64(seed)) for the limb-exact parity tests */
 int fl_encrypt_seeded(fl_ctx* c, const fl_pt* p, uint64_t seed, fl_ct** out);

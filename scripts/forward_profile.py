@@ -4,14 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fhe_linformer_b200 import synth, host
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 129
-packed = len(sys.argv) > 2 and sys.argv[2] == "packed"
+packed = len(sys.argv) > 2 and sys.argv[2].startswith("packed")
+lean = len(sys.argv) > 2 and sys.argv[2].endswith("lean")
 model = synth.make_model(n_classes=8); sample = synth.make_sample(model, S - 1, seed=5)
 root = tempfile.mkdtemp(prefix="flb200_"); dirs = synth.write_files(root, model, sample)
 fc = host.FHEController(root=root).generate()
 if packed: fc.set_option("packed_keys", 1)
-fc.forward(dirs, packed=packed); fc.forward(dirs, packed=packed)                    # warm-up
+fc.forward(dirs, packed=packed, dead_work=not lean); fc.forward(dirs, packed=packed, dead_work=not lean)                    # warm-up
 fc.ckks.prof(True); fc.ckks.prof_dump()
-t = time.time(); logits, stages, toks = fc.forward(dirs, packed=packed); dt = time.time() - t
+t = time.time(); logits, stages, toks = fc.forward(dirs, packed=packed, dead_work=not lean); dt = time.time() - t
 p = fc.ckks.prof_dump()
 print("forward S=%d: %.3f s  stages %s" % (toks, dt, {k: round(v, 3) for k, v in stages.items()}))
 tot_g = sum(v[1] for v in p.values()); tot_h = sum(v[2] for v in p.values())

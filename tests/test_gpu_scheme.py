@@ -199,3 +199,16 @@ def test_batched_encryption(ctx):
     assert (a != b).mean() > 0.99 and (a != d).mean() > 0.99 and (b != d).mean() > 0.99
     with pytest.raises(RuntimeError):
         c.encrypt_many([c.encode(vs[0], level=0), c.encode(vs[1], level=2)])   # mixed levels
+    # fl_encode_many: the batched plaintext holds, element by element, exactly the limbs of the single encodings (short
+    # rows are zero-padded like fl_encode's), and encrypts as one operand
+    rows = np.stack([v[: n // 2] for v in vs])
+    many = c.encode_many(rows, level=2)
+    parts = c.unpack(many)
+    assert len(parts) == 5
+    for r, pt in zip(rows, parts):
+        assert (pt.export() == c.encode(r, level=2).export()).all()
+    for r, ct in zip(rows, c.encrypt_many(many)):
+        assert np.abs(c.decrypt(ct)[: n // 2] - r).max() < 1e-7 and np.abs(c.decrypt(ct)[n // 2:]).max() < 1e-7
+    got = c.encrypt_many(parts[1:4])                                            # slices of a batched plaintext: the contiguous path
+    for r, ct in zip(rows[1:4], got):
+        assert np.abs(c.decrypt(ct)[: n // 2] - r).max() < 1e-7
