@@ -386,8 +386,9 @@ __global__ void __launch_bounds__(kThreads) moddown_finish_kernel(u64* __restric
 // every input word is read n_out / kOt times.  k: [n_out][n_in][l] residues with Shoup companions ([.][.][.][2]).
 constexpr int kOt = 8;
 // rows = polynomials x limbs of one operand (2 l for a ciphertext, 2 l B for a batched one): limb = row mod l
-__global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out, const u64* __restrict__ in, const ulonglong2* __restrict__ k,
-                                                           DevTables T, int l, int rows, int n_in, int n_out) {
+// ptrs != nullptr: input t starts at ptrs[t] (operands scattered over the pool) instead of in + t * rows * N
+__global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out, const u64* __restrict__ in, const u64* const* __restrict__ ptrs,
+                                                           const ulonglong2* __restrict__ k, DevTables T, int l, int rows, int n_in, int n_out) {
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     const int limb = blockIdx.y % l, o0 = blockIdx.z * kOt;
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out
 #pragma unroll
     for (int o = 0; o < kOt; ++o) acc[o] = 0;
     for (int t = 0; t < n_in; ++t) {
-        const u64 x = in[(size_t)t * ct + poly_off];
+        const u64 x = ptrs ? ptrs[t][poly_off] : in[(size_t)t * ct + poly_off];
 #pragma unroll
         for (int o = 0; o < kOt; ++o) {
             if (o0 + o < n_out) {
@@ -614,9 +615,10 @@ void launch_gather_multi(const DevTables& t, u64* out, const GatherArgs& g, int 
     gather_multi_kernel<<<dim3(cdiv(t.N, kThreads), rows, batch), kThreads, 0, s>>>(out, g, t, l, rows_per_poly, out_bs, src_bs);
     FLK_CUDA(cudaGetLastError());
 }
-void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s) {
-    lincomb_kernel<<<dim3(cdiv(t.N, kThreads), rows, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, reinterpret_cast<const ulonglong2*>(k), t, l,
-                                                                                               rows, n_in, n_out);
+void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s,
+                    const u64* const* in_ptrs) {
+    lincomb_kernel<<<dim3(cdiv(t.N, kThreads), rows, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, in_ptrs, reinterpret_cast<const ulonglong2*>(k),
+                                                                                               t, l, rows, n_in, n_out);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {

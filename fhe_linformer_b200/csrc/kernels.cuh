@@ -118,7 +118,9 @@ void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, con
 
 // out[o] = sum_t k[o][t] in[t] over operands of `rows` limb rows each (2 l for a ciphertext, 2 l B for a batched one):
 // in [n_in][rows][N], out [n_out][rows][N], k [n_out][n_in][l][2] = {residue, Shoup}
-void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s);
+// in_ptrs (device array of n_in pointers), when given, replaces the contiguous `in`
+void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, int l, int rows, int n_in, int n_out, cudaStream_t s,
+                    const u64* const* in_ptrs = nullptr);
 
 // ---- rescale ----
 struct RsConst {

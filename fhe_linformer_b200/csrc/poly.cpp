@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <functional>
+#include <map>
 
 #include "scheme.h"
 
@@ -28,6 +29,7 @@ std::vector<double> Scheme::chebyshev_coefficients(double (*f)(double, void*), v
 
 namespace {
 bool negligible(double c) { return std::fabs(c) < 1e-300; }
+bool same_shape(const Elem& x, const Elem& y) { return x.l == y.l && x.deg == y.deg && x.scale == y.scale && x.batch == y.batch && x.slots == y.slots; }
 int poly_degree(const std::vector<double>& c) {
     int d = (int)c.size() - 1;
     while (d > 0 && negligible(c[d])) --d;
@@ -35,46 +37,103 @@ int poly_degree(const std::vector<double>& c) {
 }
 }  // namespace
 
-// sum_{i<=upto} c[i] T[i]; T[0] is the constant 1 (T[0] unused).  Returns an invalid Elem when everything is zero
-// except possibly c[0], which the caller adds as a constant.
-// sum_{1 <= i <= upto} c[i] T[i] as ONE kernel (weighted_sum) instead of a scalar multiplication, a rescale and an addition per
-// term: the terms a combination uses are brought to the deepest level among them (never deeper, so no level is wasted) and
-// to one scale -- OpenFHE's EvalChebyshevSeriesPS aligns levels the same way before its EvalLinearWSum.  `settled` holds
-// T[i] after its pending rescale, `aligned` caches (i, target limbs) -> adjusted copy, so each polynomial is adjusted once
-// per target level rather than once per use.
-Elem Scheme::inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto) {
-    std::vector<int> idx;
-    std::vector<double> w;
-    for (int i = 1; i <= upto && i < (int)c.size(); ++i) {
-        if (negligible(c[i])) continue;
-        idx.push_back(i);
-        w.push_back(c[i]);
+// elements [g * each, (g + 1) * each) of a batched operand, as a view
+Elem Scheme::part_of(const Elem& all, size_t g, int each) const {
+    Elem e = all;
+    e.off = all.off + g * (size_t)each * all.words_each(P.N);
+    e.batch = each;
+    return e;
+}
+
+// Sums of independent pairs, one batched EvalAdd per group of pairs that share their shapes (the level adjustment of the
+// shallower side, a scalar product and a rescale, then happens once per group instead of once per pair).
+std::vector<Elem> Scheme::add_each(const std::vector<Elem>& a, const std::vector<Elem>& b) {
+    const size_t n = a.size();
+    if (b.size() != n) throw std::invalid_argument("add_each: operand counts differ");
+    std::vector<Elem> out(n);
+    std::vector<char> done(n, 0);
+    for (size_t first = 0; first < n; ++first) {
+        if (done[first]) continue;
+        std::vector<size_t> grp;
+        for (size_t i = first; i < n; ++i)
+            if (!done[i] && same_shape(a[i], a[first]) && same_shape(b[i], b[first])) { grp.push_back(i); done[i] = 1; }
+        if (grp.size() == 1) { out[first] = add(a[first], b[first]); continue; }
+        std::vector<Elem> ga, gb;
+        for (size_t i : grp) { ga.push_back(a[i]); gb.push_back(b[i]); }
+        const Elem sum = add(pack(ga), pack(gb));
+        for (size_t g = 0; g < grp.size(); ++g) out[grp[g]] = part_of(sum, g, a[first].batch);
     }
-    if (idx.empty()) return Elem();
+    return out;
+}
+
+// Baby polynomials sum_{1 <= i <= upto} c[i] T[i] (T[0] is the constant 1: c[0] is left to the caller), ALL of an evaluation at
+// once.  The terms a combination uses are brought to the deepest level among them (never deeper, so no level is wasted) and to
+// one scale -- OpenFHE's EvalChebyshevSeriesPS aligns levels the same way before its EvalLinearWSum -- and every group of
+// polynomials that ends up on the same level is ONE kernel (weighted_sums: the 2^m baby polynomials of a Paterson-Stockmeyer
+// tree share their terms) instead of a scalar multiplication, a rescale and an addition per term.  `settled` holds T[i] after
+// its pending rescale, `aligned` caches (i, target limbs) -> adjusted copy, so each T[i] is adjusted once per target level.
+// An entry of the result is invalid when its polynomial has no term beyond c[0].
+std::vector<Elem> Scheme::inner_linear_many(const std::vector<Elem>& T, const std::vector<const std::vector<double>*>& polys, int kmax) {
+    std::vector<Elem> out(polys.size());
     if (ps_settled_.size() != T.size()) { ps_settled_.assign(T.size(), Elem()); ps_aligned_.clear(); }
-    int deepest = idx[0];
-    for (int i : idx) {
+    auto settled = [&](int i) -> const Elem& {
         if (!ps_settled_[i].valid()) {
             ps_settled_[i] = T[i];
             if (ps_settled_[i].deg == 2) rescale_inplace(ps_settled_[i]);
         }
-        if (ps_settled_[i].l < ps_settled_[deepest].l) deepest = i;
+        return ps_settled_[i];
+    };
+    // the level each polynomial lands on: that of the deepest term it uses
+    std::map<int, std::vector<size_t>> by_limbs;
+    for (size_t p = 0; p < polys.size(); ++p) {
+        const std::vector<double>& c = *polys[p];
+        int limbs = 0;
+        for (int i = 1; i <= kmax && i < (int)c.size(); ++i)
+            if (!negligible(c[i])) limbs = limbs ? std::min(limbs, settled(i).l) : settled(i).l;
+        if (limbs) by_limbs[limbs].push_back(p);
     }
-    const Elem& ref = ps_settled_[deepest];
-    std::vector<Elem> terms;
-    for (int i : idx) {
-        const Elem& si = ps_settled_[i];
-        if (si.l == ref.l && si.scale == ref.scale) { terms.push_back(si); continue; }
-        auto key = std::make_pair(i, ref.l);
-        auto it = ps_aligned_.find(key);
-        if (it == ps_aligned_.end()) {
-            Elem a = si, r = ref;
-            adjust_pair(a, r);
-            it = ps_aligned_.emplace(key, a).first;
+    for (const auto& grp : by_limbs) {
+        const int limbs = grp.first;
+        std::vector<int> idx;                              // union of the terms the group uses
+        for (int i = 1; i <= kmax; ++i)
+            for (size_t p : grp.second)
+                if (i < (int)polys[p]->size() && !negligible((*polys[p])[i])) { idx.push_back(i); break; }
+        int deepest = -1;
+        for (int i : idx)
+            if (settled(i).l == limbs) { deepest = i; break; }
+        const Elem ref = settled(deepest);
+        // terms above the target level are adjusted to it -- all those that share a level in one go (T_(2^(d-1)+1) .. T_(2^d) do)
+        std::vector<int> todo;
+        for (int i : idx) {
+            const Elem& si = settled(i);
+            if (!(si.l == ref.l && si.scale == ref.scale) && !ps_aligned_.count(std::make_pair(i, ref.l))) todo.push_back(i);
         }
-        terms.push_back(it->second);
+        while (!todo.empty()) {
+            const Elem first = settled(todo[0]);
+            std::vector<int> same, rest;
+            for (int i : todo) (same_shape(settled(i), first) ? same : rest).push_back(i);
+            std::vector<Elem> src;
+            for (int i : same) src.push_back(settled(i));
+            Elem a = src.size() == 1 ? src[0] : pack(src), r = ref;
+            adjust_pair(a, r);
+            for (size_t g = 0; g < same.size(); ++g) ps_aligned_.emplace(std::make_pair(same[g], ref.l), part_of(a, g, first.batch));
+            todo.swap(rest);
+        }
+        std::vector<Elem> terms;
+        for (int i : idx) {
+            const Elem& si = settled(i);
+            terms.push_back(si.l == ref.l && si.scale == ref.scale ? si : ps_aligned_.at(std::make_pair(i, ref.l)));
+        }
+        std::vector<std::vector<double>> w(grp.second.size(), std::vector<double>(idx.size(), 0.0));
+        for (size_t g = 0; g < grp.second.size(); ++g) {
+            const std::vector<double>& c = *polys[grp.second[g]];
+            for (size_t t = 0; t < idx.size(); ++t)
+                if (idx[t] < (int)c.size() && !negligible(c[idx[t]])) w[g][t] = c[idx[t]];
+        }
+        const Elem all = weighted_sums(terms, w);
+        for (size_t g = 0; g < grp.second.size(); ++g) out[grp.second[g]] = part_of(all, g, ref.batch);
     }
-    return weighted_sum(terms, w);
+    return out;
 }
 
 // Products of independent pairs as ONE batched EvalMult per group of operands that share level, degree and scale (one tensor
@@ -113,13 +172,7 @@ std::vector<Elem> Scheme::mult_each(std::vector<Elem> a, std::vector<Elem> b, bo
             else if (each > 1) gb.push_back(b[0]);       // a batched multiplier is repeated; a single one is broadcast by EvalMult
         }
         const Elem prod = mult(pack(ga), gb.empty() ? b[0] : pack(gb));
-        const size_t words = (size_t)each * prod.words_each(P.N);
-        for (size_t g = 0; g < grp.size(); ++g) {
-            Elem& o = out[grp[g]];
-            o = prod;
-            o.off = prod.off + g * words;
-            o.batch = each;
-        }
+        for (size_t g = 0; g < grp.size(); ++g) out[grp[g]] = part_of(prod, g, each);
     }
     return out;
 }
@@ -203,11 +256,17 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
         return (int)nodes.size() - 1;
     };
     const int root = build(c, m);
-    for (Node& nd : nodes) {
-        if (nd.j != 0) continue;
-        const int d = poly_degree(nd.p);
-        nd.c0 = nd.p.empty() ? 0.0 : nd.p[0];
-        nd.val = inner_linear(T, nd.p, std::min(d, k - 1));
+    {
+        std::vector<size_t> leaves;
+        std::vector<const std::vector<double>*> polys;
+        for (size_t i = 0; i < nodes.size(); ++i)
+            if (nodes[i].j == 0) { leaves.push_back(i); polys.push_back(&nodes[i].p); }
+        const std::vector<Elem> vals = inner_linear_many(T, polys, k - 1);
+        for (size_t i = 0; i < leaves.size(); ++i) {
+            Node& nd = nodes[leaves[i]];
+            nd.c0 = nd.p.empty() ? 0.0 : nd.p[0];
+            nd.val = vals[i];
+        }
     }
     for (int h = 1; h <= m; ++h) {
         std::vector<int> with_q;                 // nodes of this height whose quotient is a ciphertext: (q + q0) T_g in one call
@@ -220,6 +279,8 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
             qs.push_back(negligible(q.c0) ? q.val : add_const(q.val, q.c0));
         }
         const std::vector<Elem> prods = mult_each(qs, {Gs[h - 1]}, false);
+        std::vector<size_t> both;                // nodes whose product and remainder are both ciphertexts: summed together below
+        std::vector<Elem> sum_a, sum_b;
         for (size_t i = 0; i < nodes.size(); ++i) {
             Node& nd = nodes[i];
             if (nd.j != h) continue;
@@ -230,9 +291,11 @@ Elem Scheme::cheby_ps(const Elem& x, const std::vector<double>& c_in) {
             if (at != with_q.end()) prod = prods[(size_t)(at - with_q.begin())];
             else if (!negligible(q.c0)) prod = mult_const(Gs[h - 1], q.c0);
             nd.c0 = r.c0;
-            if (prod.valid() && r.val.valid()) nd.val = add(prod, r.val);
+            if (prod.valid() && r.val.valid()) { both.push_back(i); sum_a.push_back(prod); sum_b.push_back(r.val); }
             else nd.val = prod.valid() ? prod : r.val;
         }
+        const std::vector<Elem> sums = add_each(sum_a, sum_b);
+        for (size_t g = 0; g < both.size(); ++g) nodes[both[g]].val = sums[g];
     }
     double c0 = nodes[root].c0;
     Elem res = nodes[root].val;

@@ -776,28 +776,40 @@ Elem Scheme::linear_wsum(const Elem& in_raw, const double* w, int n_out) {
 
 // sum_i w[i] * terms[i] for terms of identical level / degree 1 / scale (each possibly a batched operand): one kernel.
 // The result is one degree deeper, like EvalMult by a scalar.
-Elem Scheme::weighted_sum(const std::vector<Elem>& terms, const std::vector<double>& w) {
+Elem Scheme::weighted_sum(const std::vector<Elem>& terms, const std::vector<double>& w) { return weighted_sums(terms, {w}); }
+
+// n_out plaintext-weighted sums of the same aligned terms as ONE kernel: out[o] = sum_t w[o][t] terms[t].  The terms are read
+// where they lie (a table of pointers travels with the scalars), the result is one batched operand: combination o is elements
+// [o B, (o + 1) B) of it, B the batch of a term.
+Elem Scheme::weighted_sums(const std::vector<Elem>& terms, const std::vector<std::vector<double>>& w) {
     const Elem& f = terms.at(0);
-    const int n_in = (int)terms.size(), l = f.l, rows = 2 * l * f.batch;
-    const size_t each = (size_t)rows * P.N;
+    const int n_in = (int)terms.size(), n_out = (int)w.size(), l = f.l, rows = 2 * l * f.batch;
+    if (n_out < 1) throw std::invalid_argument("weighted_sums: no combinations");
     const double sf = P.sf[level_of(f)];
-    std::vector<u64> k((size_t)n_in * l * 2);
+    const size_t nk = (size_t)n_out * n_in * l * 2;
+    std::vector<u64> k(nk + (size_t)n_in);               // scalars with Shoup companions, then the pointer table
     for (int t = 0; t < n_in; ++t) {
-        if (terms[t].l != l || terms[t].deg != 1 || terms[t].scale != f.scale || terms[t].batch != f.batch) throw std::invalid_argument("weighted_sum: misaligned terms");
-        const i128 v = (i128)std::rint(w[t] * sf);
-        for (int i = 0; i < l; ++i) {
-            i128 r = v % (i128)P.q[i];
-            if (r < 0) r += P.q[i];
-            k[((size_t)t * l + i) * 2] = (u64)r; k[((size_t)t * l + i) * 2 + 1] = nt::shoup((u64)r, P.q[i]);
+        if (terms[t].ncomp != 2 || terms[t].l != l || terms[t].deg != 1 || terms[t].scale != f.scale || terms[t].batch != f.batch)
+            throw std::invalid_argument("weighted_sum: misaligned terms");
+        k[nk + (size_t)t] = (u64)(uintptr_t)terms[t].data();
+    }
+    for (int o = 0; o < n_out; ++o) {
+        if ((int)w[o].size() != n_in) throw std::invalid_argument("weighted_sums: one weight per term expected");
+        for (int t = 0; t < n_in; ++t) {
+            const i128 v = (i128)std::rint(w[o][t] * sf);
+            for (int i = 0; i < l; ++i) {
+                i128 r = v % (i128)P.q[i];
+                if (r < 0) r += P.q[i];
+                const size_t at = (((size_t)o * n_in + t) * l + i) * 2;
+                k[at] = (u64)r; k[at + 1] = nt::shoup((u64)r, P.q[i]);
+            }
         }
     }
     u64* kd = eng.alloc(k.size());
-    u64* in = eng.alloc(each * n_in);
-    for (int t = 0; t < n_in; ++t) eng.copy(in + (size_t)t * each, terms[t].data(), each);
     upload_small(kd, k.data(), k.size());
-    Elem r = make(2, l, 2, f.scale * sf, f.slots, f.batch);
-    launch_lincomb(eng.T, r.data(), in, kd, l, rows, n_in, 1, eng.stream);
-    eng.release(kd); eng.release(in);
+    Elem r = make(2, l, 2, f.scale * sf, f.slots, f.batch * n_out);
+    launch_lincomb(eng.T, r.data(), nullptr, kd, l, rows, n_in, n_out, eng.stream, reinterpret_cast<const u64* const*>(kd + nk));
+    eng.release(kd);
     return r;
 }
 

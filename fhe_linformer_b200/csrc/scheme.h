@@ -113,6 +113,7 @@ public:
     // of n_out ciphertexts one degree deeper.  The encrypted Linformer E / F projection is one such call.
     Elem linear_wsum(const Elem& in, const double* w, int n_out);
     Elem weighted_sum(const std::vector<Elem>& terms, const std::vector<double>& w);   // aligned terms, one kernel
+    Elem weighted_sums(const std::vector<Elem>& terms, const std::vector<std::vector<double>>& w);   // several combinations, one kernel
     Elem square(const Elem& a) { return mult(a, a); }
     Elem rotate(const Elem& a, int k);                // EvalRotate F.cpp:435,833,843
     Elem conjugate(const Elem& a);
@@ -184,8 +185,10 @@ private:
     Elem binary(const Elem& a, const Elem& b, bool subtract);
     // evaluation helpers
     Elem cheby_ps(const Elem& x, const std::vector<double>& c);
+    std::vector<Elem> add_each(const std::vector<Elem>& a, const std::vector<Elem>& b);   // independent sums, batched per shape
+    Elem part_of(const Elem& all, size_t g, int each) const;
     std::vector<Elem> mult_each(std::vector<Elem> a, std::vector<Elem> b, bool align);   // independent products as one batched EvalMult
-    Elem inner_linear(const std::vector<Elem>& T, const std::vector<double>& c, int upto);
+    std::vector<Elem> inner_linear_many(const std::vector<Elem>& T, const std::vector<const std::vector<double>*>& polys, int kmax);
     std::vector<Elem> ps_settled_;                          // inner_linear caches, valid during one cheby_ps evaluation
     std::map<std::pair<int, int>, Elem> ps_aligned_;
 
