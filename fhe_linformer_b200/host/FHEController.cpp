@@ -915,6 +915,7 @@ Ctxt FHEController::eval_exp(const Ctxt& c, int inputs_number) {
     for (auto& h : eight) h = res->handle();
     need(fl_mul_many(ctx_, eight, 8, &e), "EvalMultMany");
     res = wrap(e);
+    if (inputs_number <= 0) return res;
     return add(res, mask_plain(5, inputs_number, 0, -1, (int)res->GetLevel()));
 }
 

@@ -132,6 +132,8 @@ public:
 
     // ---- polynomial approximations of the activations (F.cpp:471-495, 1289-1336) ----------------------------------------
     Ctxt eval_exp(const Ctxt& c, int inputs_number);
+    // inputs_number <= 0: the bare ((Taylor_6)^8) without the "-1 outside the first inputs_number x inputs_number region" plaintext
+    // (packed attention keeps meaningful scores in every slot)
     Ctxt eval_inverse(const Ctxt& c, double min, double max);
     Ctxt eval_inverse_naive(const Ctxt& c, double min, double max);
     Ctxt eval_inverse_naive_2(const Ctxt& c, double min, double max, double mult);

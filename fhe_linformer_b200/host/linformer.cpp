@@ -95,6 +95,61 @@ Ctxt LinformerForward::attend_cls(const std::vector<Ctxt>& rows, const std::vect
     return fc_.matmulRE(weights, values, 128, 128)[0];                                   // M:215-216
 }
 
+// ---- packed mode: the same attention block, never leaving the wrapped-expanded layout --------------------------------------------
+// The 32 projected rows of X_E (X_F) enter ONE ciphertext, row t in column t (position masks, no rotation; columns 32..127 zero):
+//   K = X_E W_K, V = X_F W_V, q = W_Q x_0 / 64 and finally W_O are FHEController::packed_linear products (BSGS, 23 key switches each)
+//     instead of 32 + 32 + 1 + 1 rotate-and-sum ladders of 7 rotations;
+//   scores  = sum over the 128 features (stride-128 ladder) of q (.) K: score t in column t of every block, 0 in columns >= 32;
+//   exp     = the reference's polynomial, and -1 in the columns that hold no key (its eval_exp does the same for its layout);
+//   total   = stride-1 ladder over 32 columns: column t receives the sum over keys t..31 -- the SAME partial sums the reference's
+//             stride-128 ladder over its 32 blocks produces (M:201: block t sums blocks t..t+31, of which t..31 hold keys), so
+//             weight t = exp(s_t) / sum_{t' >= t} exp(s_t') exactly as there;
+//   context = stride-1 ladder of weights (.) V: the attention output of the CLS query in column 0 of every block.
+// Same polynomial for exp, same Chebyshev interpolant for 1/x on the same totals as M:197-205: the logits agree up to CKKS noise.
+// Returns row 0 after W_O, bias and residual (M:217-239) in the wrapped-expanded layout: column 0 is what "attended_row0" holds in
+// every column; the other columns are never read (wrap_rows_packed keeps column 0 of row 0).
+Ctxt LinformerForward::attend_cls_packed(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf) {
+    const int slots = fc_.num_slots;
+    auto expanded = [&](const std::vector<double>& v, double scale, int columns) {        // slot 128 j + t = v[j] for t < columns
+        std::vector<double> e((size_t)slots, 0.0);
+        for (int j = 0; j < 128; ++j)
+            for (int t = 0; t < columns; ++t) e[(size_t)128 * j + t] = v.at((size_t)j) * scale;
+        return e;
+    };
+    auto linear = [&](const Ctxt& x, const std::string& weight_file, const std::string& bias_file, bool transposed_file, double scale, int columns) {
+        std::vector<double> f;
+        auto weight = [&](int j, int i) {                                                 // coefficient of input feature j in output feature i
+            if (f.empty()) { f = utils::read_values_from_file(layer(weight_file)); if (f.size() < 128 * 128) throw std::runtime_error(weight_file + ": expected 128 x 128 values"); }
+            return transposed_file ? f[(size_t)128 * j + i] : f[(size_t)128 * i + j];
+        };
+        const Ctxt y = fc_.packed_linear(x, layer(weight_file) + (scale == 1.0 ? "" : "@*" + std::to_string(scale)), weight, scale);
+        return fc_.add(y, fc_.encode(expanded(utils::read_values_from_file(layer(bias_file)), scale, columns), (int)y->GetLevel() + 1, slots));
+    };
+    const Ctxt keys = linear(wrap_rows_packed(xe, 0), "selfAttn_WK_weight_T.txt", "selfAttn_WK_bias.txt", true, 1.0, 32);   // M:179-185
+    const Ctxt query = linear(rows[0], "selfAttn_WQ_weight_T.txt", "selfAttn_WQ_bias.txt", true, 1.0 / 64.0, 128);          // M:177-182, 1/64 of matmulScores folded in
+    checkpoint("packed_keys", keys);
+    checkpoint("packed_query", query);
+    Ctxt scores = fc_.rotsum(fc_.mult(query, keys), 128, 128);                            // M:196
+    checkpoint("packed_scores", scores);
+    scores = fc_.eval_exp(scores, 0);                                                     // M:197
+    std::vector<double> no_key((size_t)slots, 0.0);
+    for (int p = 0; p < slots; ++p)
+        if (p % 128 >= 32) no_key[(size_t)p] = -1.0;
+    scores = fc_.add(scores, fc_.encode(no_key, (int)scores->GetLevel(), slots));
+    checkpoint("packed_scores_exp", scores);
+    const Ctxt inverse = fc_.eval_inverse_naive(fc_.rotsum(scores, 32, 1), -1, 128);      // M:201-203
+    checkpoint("packed_scores_inverse", inverse);
+    scores = fc_.mult(scores, inverse);                                                   // M:205
+    checkpoint("packed_scores_normalised", scores);
+    const Ctxt values = linear(wrap_rows_packed(xf, 0), "selfAttn_WV_weight_T.txt", "selfAttn_WV_bias.txt", true, 1.0, 32);   // M:209-213
+    const Ctxt context = fc_.rotsum(fc_.mult(scores, values), 32, 1);                     // M:215-216
+    checkpoint("packed_attention_cls", context);
+    lap("Self-Attention");
+    const Ctxt out = fc_.add(linear(context, "selfAttn_WO_weight.txt", "selfAttn_WO_bias.txt", false, 1.0, 128), rows[0]);   // M:231-239
+    checkpoint("packed_attended_row0", out);
+    return out;
+}
+
 // ---- attention for every row (src/main_2.cpp:187-229, "M2:") ---------------------------------------------------------------
 // Queries go in two halves of at most 128; matmulScores(vector) packs query t's 32 scores at slots 128 j + t.
 std::vector<Ctxt> LinformerForward::attend_all(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf) {
@@ -133,13 +188,6 @@ std::vector<Ctxt> LinformerForward::self_output(const Ctxt& cls_context, const s
     for (size_t i = 1; i < rows.size(); ++i) out.push_back(zero->Clone());               // M:222-224
     const Ptxt wo = fc_.read_plain_input(layer("selfAttn_WO_weight.txt"), level);        // M:231
     const Ptxt bo = fc_.read_plain_expanded_input(layer("selfAttn_WO_bias.txt"), level + 1);   // M:232
-    if (packed_) {
-        // packed mode: W_O on the one row that carries attention output; the other rows go on as the fresh inputs they are
-        // (the reference adds W_O (x) Enc(0) to each of them, M:222-239: the same plaintext values)
-        std::vector<Ctxt> res(rows.begin(), rows.end());
-        res[0] = fc_.add(fc_.add(fc_.matmulCR({cls_context}, wo, nullptr)[0], bo), rows[0]);
-        return res;
-    }
     if (dead_work_) {
         out = fc_.matmulCR(out, wo, nullptr);                                            // M:235
     } else {
@@ -322,13 +370,16 @@ Ctxt LinformerForward::encoder() {
         const Ptxt bo = fc_.read_plain_expanded_input(layer("selfAttn_WO_bias.txt"), level + 1); // M2:240
         attended = fc_.matmulCR(context, wo, bo);                                                // M2:242
         for (size_t i = 0; i < attended.size(); ++i) attended[i] = fc_.add(attended[i], rows[i]); // M2:244-246
+    } else if (packed_) {
+        attended = rows;                                                                 // the other rows go on as the fresh inputs they are
+        attended[0] = attend_cls_packed(rows, xe, xf);
     } else {
         const Ctxt context = attend_cls(rows, xe, xf);
         checkpoint("attention_cls", context);
         lap("Self-Attention");
         attended = self_output(context, rows);
     }
-    checkpoint("attended_row0", attended[0]);
+    if (!packed_) checkpoint("attended_row0", attended[0]);                              // (packed: "packed_attended_row0" above)
     checkpoint("attended_row1", attended[1]);
     auto [half0, half1] = affine_and_refresh(attended, "affine1", true);
     checkpoint("affine1_refreshed_0", half0);

@@ -68,6 +68,7 @@ private:
     std::vector<Ctxt> load_expanded(const std::string& dir, const std::string& stem, int count);
 
     Ctxt attend_cls(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
+    Ctxt attend_cls_packed(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
     std::vector<Ctxt> self_output(const Ctxt& cls_context, const std::vector<Ctxt>& rows);
     std::pair<Ctxt, Ctxt> affine_and_refresh(const std::vector<Ctxt>& rows, const std::string& which, bool refresh);
     std::vector<Ctxt> feed_forward(const Ctxt& half0, const Ctxt& half1, int rows);

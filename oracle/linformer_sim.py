@@ -209,6 +209,28 @@ def sim_forward(model, sample, checkpoints=None, all_tokens=False):
     out[0] = out[0] + s.expanded(model["bO"])
     out = [o + r for o, r in zip(out, rows)]
     cp["attended_row0"], cp["attended_row1"] = out[0], out[1]
+    # what the packed mode (host/linformer.cpp attend_cls_packed) holds at its own checkpoints: the same numbers in the wrapped-expanded
+    # layout -- slot 128 j + t = entry j of projected row t, columns t >= 32 empty -- through the same ladders, so that the partial
+    # sums the 1/x interpolant sees (M:201: key t is normalised by the sum over keys t..31) are reproduced slot by slot
+    jj, tt = np.arange(s.n) // 128, np.arange(s.n) % 128
+    has_key = tt < 32
+    K = np.asarray(sample["XE"], np.float64)[:, :128] @ model["WK_T"] + model["bK"]
+    V = np.asarray(sample["XF"], np.float64)[:, :128] @ model["WV_T"] + model["bV"]
+    x0 = np.asarray(model["cls_token"], np.float64)[:128]
+    qv = (x0 @ model["WQ_T"] + model["bQ"]) / 64.0
+    cp["packed_keys"] = np.where(has_key, K[tt % 32, jj], 0.0)
+    cp["packed_query"] = qv[jj]
+    sc = s.rotsum(cp["packed_query"] * cp["packed_keys"], 128, 128)
+    cp["packed_scores"] = sc
+    ex = sum(c * sc ** i for i, c in enumerate([1, 1, 1 / 2., 1 / 6., 1 / 24., 1 / 120., 1 / 720.])) ** 8 + np.where(has_key, 0.0, -1.0)
+    cp["packed_scores_exp"] = ex
+    inv = s.eval_inverse_naive(s.rotsum(ex, 32, 1), -1, 128)
+    cp["packed_scores_inverse"] = inv
+    cp["packed_scores_normalised"] = ex * inv
+    vals = np.where(has_key, V[tt % 32, jj], 0.0)          # (columns without a key meet weight 0: what they hold does not matter)
+    ctx = s.rotsum(cp["packed_scores_normalised"] * vals, 32, 1)
+    cp["packed_attention_cls"] = ctx
+    cp["packed_attended_row0"] = (model["WO"] @ ctx.reshape(128, 128) + model["bO"][:128, None] + x0[:, None]).reshape(-1)
     return _sim_tail(s, cp, model, out, S, 1 / 50.)
 
 
