@@ -311,6 +311,58 @@ __global__ void __launch_bounds__(kThreads) bsgs_inner_kernel(u64* __restrict__ 
     }
 }
 
+// The same product for up to 16 baby steps with ONE polynomial per thread (a CTA is 128 coefficients x 2 polynomials, so the second
+// read of a plaintext word hits L1): half the registers of the kernel above at N1 = 16 (156 -> 2 warps per scheduler, and the
+// compiler cannot hoist its mask-predicated plaintext loads, so they ran one DRAM latency after the other: 0.6 TB/s).  Here the
+// 16 plaintext words of a giant step are fetched unconditionally up front (the plan allocates every (j, i) slot; an unused one is
+// loaded and ignored), so 16 independent loads are in flight per thread before the first multiply.
+constexpr int kBsgsWide = 16;
+__global__ void __launch_bounds__(kThreads, 2) bsgs_inner_wide_kernel(u64* __restrict__ W, const u64* __restrict__ pts, const u64* __restrict__ pc,
+                                                                      BsgsArgs a, DevTables T, int l, int B, size_t acc_bs, size_t pc_bs) {
+    const int b = blockIdx.x, t = blockIdx.z, ext = l + T.K;
+    const int pol = threadIdx.x >> 7;
+    const int x = blockIdx.y * (kThreads / 2) + (threadIdx.x & 127);
+    if (x >= T.N) return;
+    const int m = t < l ? t : T.L + (t - l);
+    const RedC rc = load_redc(T, m);
+    const size_t row = (size_t)t * T.N, ppoly = (size_t)ext * T.N, cpoly = (size_t)l * T.N;
+    Split30 u[kBsgsWide];
+#pragma unroll
+    for (int i = 0; i < kBsgsWide; ++i) {
+        u64 v = 0;
+        if (i < a.n1) {
+            if (i == 0) {
+                if (t < l) v = pc[(size_t)b * pc_bs + (size_t)pol * cpoly + row + x];
+            } else if (a.accb[i]) {
+                const uint32_t src = a.map[i][x];
+                v = a.accb[i][(size_t)b * acc_bs + (size_t)pol * ppoly + row + src];
+                if (pol == 0 && t < l) v = addmod(v, pc[(size_t)b * pc_bs + row + src], rc.q);
+            }
+        }
+        u[i] = split30(v);
+    }
+    for (int j = 0; j < a.n2; ++j) {
+        const uint32_t mask = a.mask[j];
+        const u64* pj = pts + ((size_t)j * a.n1 * ext + t) * T.N + x;
+        u64 w[kBsgsWide];
+#pragma unroll
+        for (int i = 0; i < kBsgsWide; ++i) w[i] = i < a.n1 ? __ldg(pj + (size_t)i * ppoly) : 0;
+        u64 r = 0;
+#pragma unroll
+        for (int i0 = 0; i0 < kBsgsWide; i0 += 8) {
+            Acc3 s{0, 0, 0};
+#pragma unroll
+            for (int i = i0; i < i0 + 8; ++i) {
+                Split30 ps = split30(w[i]);
+                if (!((mask >> i) & 1u)) ps = Split30{0, 0};
+                mac3(s, u[i], ps);
+            }
+            r = i0 ? addmod(r, reduce3(s, rc), rc.q) : reduce3(s, rc);
+        }
+        W[((size_t)j * B + b) * acc_bs + (size_t)pol * ppoly + row + x] = r;
+    }
+}
+
 // out[b][r][x] = sum_k src_k[b][r][map_k[x]]  (rows r of rpp limbs per polynomial, modulus by extended-basis index)   grid (N / 256, rows, B)
 __global__ void __launch_bounds__(kThreads) gather_multi_kernel(u64* __restrict__ out, GatherArgs g, DevTables T, int l, int rpp, size_t out_bs,
                                                                 size_t src_bs) {
@@ -606,8 +658,10 @@ void launch_bsgs_inner(const DevTables& t, u64* W, const u64* pts, const u64* pc
                        cudaStream_t s) {
     if (a.n1 < 1 || a.n1 > kBsgsMax || a.n2 < 1 || a.n2 > kBsgsMax) throw std::invalid_argument("linear transform: 1..16 baby and giant steps");
     const dim3 grid(B, cdiv(t.N, kThreads), l + t.K);
+    static const bool narrow16 = [] { const char* e = std::getenv("FLK_BSGS_NARROW16"); return e && e[0] == '1'; }();   // the former kernel, for comparison
     if (a.n1 <= 8) bsgs_inner_kernel<8><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
-    else bsgs_inner_kernel<16><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    else if (narrow16) bsgs_inner_kernel<16><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    else bsgs_inner_wide_kernel<<<dim3(B, cdiv(t.N, kThreads / 2), l + t.K), kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_gather_multi(const DevTables& t, u64* out, const GatherArgs& g, int l, int rows_per_poly, int rows, int batch, size_t out_bs, size_t src_bs,
