@@ -145,6 +145,27 @@ def test_activations(env):
     assert err(c, fc.invoke("relu", [enc(c, x)], reals=[2.0])[0], s.relu(x, 2.0)) < 1e-5
 
 
+@pytest.mark.parametrize("degree", [1, 2, 5, 13, 31, 32, 63, 119, 200, 300])
+def test_chebyshev_series_depth_and_values(env, degree):
+    """The level-synchronous Paterson-Stockmeyer evaluator (csrc/poly.cpp): values of random, odd-only and high-order-only series
+    against numpy, and the level budget -- ceil(log2(degree + 1)) multiplicative levels plus the pending rescale, whatever the
+    batching of independent products does internally (a short quotient chain must not be pushed to the level of its siblings)."""
+    fc, c, s, rng = env
+    x = rng.uniform(-1, 1, s.n)
+    ct = enc(c, x, level=3)
+    depth = math.ceil(math.log2(degree + 1))
+    for kind in ("dense", "odd", "top"):
+        coef = rng.uniform(-1, 1, degree + 1) / (degree + 1)
+        if kind == "odd": coef[0::2] = 0.0
+        if kind == "top": coef[1:degree] = 0.0                     # c0 and the highest term only
+        want = np.polynomial.chebyshev.chebval(x, coef)
+        series = coef.copy(); series[0] *= 2                        # EvalChebyshevSeries takes c0 doubled (c0/2 + sum c_i T_i)
+        got = c.eval_chebyshev(ct, series, -1, 1)
+        assert err(c, got, want) < 2e-6, (degree, kind)
+        used = got.level - ct.level + (1 if got.deg == 2 else 0)    # a pending rescale is a spent level
+        assert used <= depth + 1, (degree, kind, used, depth)       # + 1: the scalar coefficients of the baby polynomials
+
+
 def test_batched_bootstrap_chebyshev_and_ct_mult(env):
     """Batched operands through ct x ct multiplication, Chebyshev evaluation and bootstrapping equal the per-ciphertext results."""
     fc, c, s, rng = env
