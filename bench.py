@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--logN", type=int, default=16)
     ap.add_argument("--limbs", type=int, default=28, help="active Q limbs of the operands (28 = full chain)")
-    ap.add_argument("--batch", type=int, default=16, help="ciphertexts per step per GPU")
-    ap.add_argument("--group", type=int, default=8, help="ciphertexts sharing one key per batched call")
+    ap.add_argument("--batch", type=int, default=32, help="ciphertexts per step per GPU")
+    ap.add_argument("--group", type=int, default=32, help="ciphertexts sharing one key per batched call (the reference's row loops rotate S = 200 rows by one index)")
     ap.add_argument("--cpu-sample", type=int, default=20, help="rotations timed on the host for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the encrypted Linformer forward (extra `forward` key)")
