@@ -1,6 +1,7 @@
 // kernels.cu -- element-wise, automorphism, base-conversion, inner-product, ModDown and rescale kernels
 // (K2-K7 of SURVEY.md 2.1) for sm_100a.  All are HBM-streaming integer kernels: limb-major layout,
 // adjacent threads on adjacent coefficients, 128-bit accumulators reduced once.
+#include <atomic>
 #include <cstdlib>
 #include "kernels.cuh"
 #include "modarith.cuh"
@@ -311,24 +312,47 @@ __global__ void __launch_bounds__(kThreads) bsgs_inner_kernel(u64* __restrict__ 
     }
 }
 
-// The same product for up to 16 baby steps with ONE polynomial per thread (a CTA is 128 coefficients x 2 polynomials, so the second
-// read of a plaintext word hits L1): half the registers of the kernel above at N1 = 16 (156 -> 2 warps per scheduler, and the
-// compiler cannot hoist its mask-predicated plaintext loads, so they ran one DRAM latency after the other: 0.6 TB/s).  Here the
-// 16 plaintext words of a giant step are fetched unconditionally up front (the plan allocates every (j, i) slot; an unused one is
-// loaded and ignored), so 16 independent loads are in flight per thread before the first multiply.
-constexpr int kBsgsWide = 16;
-__global__ void __launch_bounds__(kThreads, 2) bsgs_inner_wide_kernel(u64* __restrict__ W, const u64* __restrict__ pts, const u64* __restrict__ pc,
-                                                                      BsgsArgs a, DevTables T, int l, int B, size_t acc_bs, size_t pc_bs) {
+// The same product as a TMA-fed pipeline (the kernel every transform runs on).  A CTA owns 128 coefficients of one extended limb of
+// one ciphertext, both polynomials (threads 0..127 / 128..255), so a plaintext word fetched once serves two multiplications.  The
+// plaintext rows of giant step j -- N1 diagonals x 128 coefficients, 1 KiB each, contiguous in HBM -- are brought into shared memory
+// by the TMA engine (cp.async.bulk, one 1-D copy per used diagonal, issued by one thread, completing on an mbarrier) kStages giant
+// steps ahead of their use, so no thread ever issues or waits for a plaintext load: the baby values stay in registers (one
+// polynomial per thread: 2 N1 registers), the multiplier runs while the next rows arrive.  The kernel above (loads issued by the
+// threads, 74 / 156 registers) ran at 0.6 TB/s for 16 baby steps and 1.3 TB/s for 8: latency-bound.
+template <int N1, int kStages>
+__global__ void __launch_bounds__(kThreads, 3) bsgs_inner_tma_kernel(u64* __restrict__ W, const u64* __restrict__ pts, const u64* __restrict__ pc,
+                                                                     BsgsArgs a, DevTables T, int l, int B, size_t acc_bs, size_t pc_bs) {
+    constexpr int kCols = kThreads / 2;                       // coefficients per CTA
+    extern __shared__ __align__(128) u64 bsgs_smem[];         // [kStages][N1][kCols] plaintext rows, then kStages mbarriers
+    u64(*rows)[N1][kCols] = reinterpret_cast<u64(*)[N1][kCols]>(bsgs_smem);
+    u64* full = bsgs_smem + (size_t)kStages * N1 * kCols;
     const int b = blockIdx.x, t = blockIdx.z, ext = l + T.K;
-    const int pol = threadIdx.x >> 7;
-    const int x = blockIdx.y * (kThreads / 2) + (threadIdx.x & 127);
-    if (x >= T.N) return;
+    const int pol = threadIdx.x / kCols, xl = threadIdx.x % kCols;
+    const int x0 = blockIdx.y * kCols, x = x0 + xl;
+    const size_t row = (size_t)t * T.N, ppoly = (size_t)ext * T.N, cpoly = (size_t)l * T.N;
+    auto fill = [&](int j) {                                  // thread 0: the used rows of giant step j into stage j % kStages
+        const int st = j % kStages;
+        const uint32_t mask = a.mask[j], bar = (uint32_t)__cvta_generic_to_shared(&full[st]);
+        const uint32_t bytes = (uint32_t)__popc(mask & ((1u << a.n1) - 1u)) * (uint32_t)(kCols * 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const u64* pj = pts + ((size_t)j * a.n1 * ext + t) * T.N + x0;
+        for (int i = 0; i < a.n1; ++i)
+            if ((mask >> i) & 1u)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(&rows[st][i][0])),
+                             "l"(pj + (size_t)i * ppoly), "r"((uint32_t)(kCols * 8)), "r"(bar)
+                             : "memory");
+    };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kStages; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&full[st])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int j = 0; j < kStages && j < a.n2; ++j) fill(j);
+    }
     const int m = t < l ? t : T.L + (t - l);
     const RedC rc = load_redc(T, m);
-    const size_t row = (size_t)t * T.N, ppoly = (size_t)ext * T.N, cpoly = (size_t)l * T.N;
-    Split30 u[kBsgsWide];
+    Split30 u[N1];
 #pragma unroll
-    for (int i = 0; i < kBsgsWide; ++i) {
+    for (int i = 0; i < N1; ++i) {
         u64 v = 0;
         if (i < a.n1) {
             if (i == 0) {
@@ -341,25 +365,25 @@ __global__ void __launch_bounds__(kThreads, 2) bsgs_inner_wide_kernel(u64* __res
         }
         u[i] = split30(v);
     }
+    __syncthreads();                                          // the barriers are initialised before anybody waits on them
     for (int j = 0; j < a.n2; ++j) {
-        const uint32_t mask = a.mask[j];
-        const u64* pj = pts + ((size_t)j * a.n1 * ext + t) * T.N + x;
-        u64 w[kBsgsWide];
-#pragma unroll
-        for (int i = 0; i < kBsgsWide; ++i) w[i] = i < a.n1 ? __ldg(pj + (size_t)i * ppoly) : 0;
+        const int st = j % kStages;
+        const uint32_t mask = a.mask[j], bar = (uint32_t)__cvta_generic_to_shared(&full[st]), parity = (uint32_t)(j / kStages) & 1u;
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+                     "r"(parity)
+                     : "memory");
         u64 r = 0;
 #pragma unroll
-        for (int i0 = 0; i0 < kBsgsWide; i0 += 8) {
+        for (int i0 = 0; i0 < N1; i0 += 8) {
             Acc3 s{0, 0, 0};
 #pragma unroll
-            for (int i = i0; i < i0 + 8; ++i) {
-                Split30 ps = split30(w[i]);
-                if (!((mask >> i) & 1u)) ps = Split30{0, 0};
-                mac3(s, u[i], ps);
-            }
+            for (int i = i0; i < i0 + 8; ++i)
+                if ((mask >> i) & 1u) mac3(s, u[i], split30(rows[st][i][xl]));      // warp-uniform branch; an unused row was not fetched
             r = i0 ? addmod(r, reduce3(s, rc), rc.q) : reduce3(s, rc);
         }
         W[((size_t)j * B + b) * acc_bs + (size_t)pol * ppoly + row + x] = r;
+        __syncthreads();                                      // everybody has read stage st: it may be refilled
+        if (threadIdx.x == 0 && j + kStages < a.n2) fill(j + kStages);
     }
 }
 
@@ -657,11 +681,25 @@ void launch_moddown_finish(const DevTables& t, const MdConst& md, const FinishAr
 void launch_bsgs_inner(const DevTables& t, u64* W, const u64* pts, const u64* pc, const BsgsArgs& a, int l, int B, size_t acc_bs, size_t pc_bs,
                        cudaStream_t s) {
     if (a.n1 < 1 || a.n1 > kBsgsMax || a.n2 < 1 || a.n2 > kBsgsMax) throw std::invalid_argument("linear transform: 1..16 baby and giant steps");
-    const dim3 grid(B, cdiv(t.N, kThreads), l + t.K);
-    static const bool narrow16 = [] { const char* e = std::getenv("FLK_BSGS_NARROW16"); return e && e[0] == '1'; }();   // the former kernel, for comparison
-    if (a.n1 <= 8) bsgs_inner_kernel<8><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
-    else if (narrow16) bsgs_inner_kernel<16><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
-    else bsgs_inner_wide_kernel<<<dim3(B, cdiv(t.N, kThreads / 2), l + t.K), kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    static const bool by_threads = [] { const char* e = std::getenv("FLK_BSGS_LOADS"); return e && e[0] == '1'; }();   // the former kernel, for comparison
+    if (by_threads || t.N % (kThreads / 2) != 0) {
+        const dim3 grid(B, cdiv(t.N, kThreads), l + t.K);
+        if (a.n1 <= 8) bsgs_inner_kernel<8><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+        else bsgs_inner_kernel<16><<<grid, kThreads, 0, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    } else {
+        const dim3 grid(B, t.N / (kThreads / 2), l + t.K);
+        constexpr size_t shm8 = (size_t)4 * 8 * (kThreads / 2) * 8 + 4 * 8, shm16 = (size_t)3 * 16 * (kThreads / 2) * 8 + 3 * 8;
+        static std::atomic<unsigned long long> configured{0};   // the attribute belongs to the device: one bit per device of this process
+        int dev = 0;
+        FLK_CUDA(cudaGetDevice(&dev));
+        if (!((configured.load() >> (dev & 63)) & 1ull)) {
+            FLK_CUDA(cudaFuncSetAttribute(bsgs_inner_tma_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm8));
+            FLK_CUDA(cudaFuncSetAttribute(bsgs_inner_tma_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm16));
+            configured.fetch_or(1ull << (dev & 63));
+        }
+        if (a.n1 <= 8) bsgs_inner_tma_kernel<8, 4><<<grid, kThreads, shm8, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+        else bsgs_inner_tma_kernel<16, 3><<<grid, kThreads, shm16, s>>>(W, pts, pc, a, t, l, B, acc_bs, pc_bs);
+    }
     FLK_CUDA(cudaGetLastError());
 }
 void launch_gather_multi(const DevTables& t, u64* out, const GatherArgs& g, int l, int rows_per_poly, int rows, int batch, size_t out_bs, size_t src_bs,

@@ -28,7 +28,8 @@ int main(int argc, char** argv) {
                      "--tokens DIR     folder with input_<i>.txt token embeddings (default <root>/tokens)\n--lean           skip operations whose results the circuit never reads\n"
                      "--encrypted-projection  compute the Linformer E/F projections on the server from the encrypted rows\n"
                      "--all-tokens     attention for every row (the circuit of the reference's main_2.cpp)\n"
-                     "--packed         feed-forward block on 128 rows per ciphertext through BSGS diagonal products (same logits, ~4x faster);\n"
+                     "--packed         every linear layer (attention and feed-forward) on 128 rows per ciphertext through BSGS diagonal products\n"
+                     "                 (same logits, ~6x faster; with --lean ~8x);\n"
                      "                 give it to --generate_keys as well so that the keys of the packed transforms are written\n"
                      "--resume         start from <root>/checkpoint/encodered.bin instead of running the encoder\n";
         return 0;
