@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--forward-in-flight", type=int, default=2, help="forwards in flight per GPU for the extra throughput-mode figure (1 = skip)")
     ap.add_argument("--forward-rows", type=int, default=200, help="S = rows of the forward sample (129..256); 200 = SURVEY.md Config 1")
     ap.add_argument("--samples", type=int, default=0, help="samples of the sample-parallel batch over ALL GPUs (BASELINE config 5 names 256); 0 = 8 per GPU")
+    ap.add_argument("--samples-per-call", type=int, default=4, help="samples per packed forward in the batched config-5 figure (forward.batch.packed_many)")
     ap.add_argument("--no-forward-configs", action="store_true", help="skip the BASELINE config 3 / 4 shapes (extra `forward.configs` block)")
     ap.add_argument("--no-forward-n16", action="store_true", help="skip the extra forward at the reference's commented-out ring N=2^16")
     ap.add_argument("--forward-logn", type=int, default=15, help="ring of the forward: 15 = the reference's parameters, 16 = its commented-out variant (sparse packing)")
@@ -639,33 +640,56 @@ def run_forward(a, local, rank, world, torch, dist):
             fc_t.forward(dirs, packed=True); fc_t.forward(dirs, packed=True)
             ctl.append(fc_t)
 
-        def run_batch(use_packed):
+        def run_batch(use_packed, group=1, lean=False, controllers=None):
+            # group > 1: `group` samples per call (flh_forward_many: every ciphertext of the forward carries one element per sample)
             q = queue.Queue()
-            for j in jobs:
-                q.put(j)
+            for k in range(0, len(jobs), group):
+                q.put(jobs[k:k + group])
             res = {}
+            failed = []
 
             def work(c):
+                try:
+                    work_(c)
+                except Exception as exc:      # a worker must not die silently: the timing would cover fewer samples
+                    failed.append(exc)
+
+            def work_(c):
                 while True:
                     try:
-                        i, d = q.get_nowait()
+                        part = q.get_nowait()
                     except queue.Empty:
                         return
-                    res[i] = c.forward(d, packed=True)[0] if use_packed else c.forward(d, dead_work=True)[0]
+                    if group > 1:
+                        z, _ = c.forward_many([d for _, d in part], dead_work=not lean, packed=True)
+                        for (i, _), row in zip(part, z):
+                            res[i] = row
+                    else:
+                        i, d = part[0]
+                        res[i] = c.forward(d, packed=True, dead_work=not lean)[0] if use_packed else c.forward(d, dead_work=True)[0]
 
             if world > 1:
                 dist.barrier()
-            th = [threading.Thread(target=work, args=(c,)) for c in ctl]
+            th = [threading.Thread(target=work, args=(c,)) for c in (controllers or ctl)]
             tb = time.perf_counter()
             for x in th: x.start()
             for x in th: x.join()
+            if failed:
+                raise failed[0]
             return time.perf_counter() - tb, res
 
+        n_ctl = len(ctl)
         batch_dt, got = run_batch(False)
         batch_packed_dt, got_packed = run_batch(True)
         batch_agree = float(max(np.abs(got[i] - got_packed[i]).max() for i in got)) if got else 0.0
         for c in ctl[1:]:
             c.close()
+        # several samples per call: one controller (a call already spreads every launch over its samples)
+        per_call = max(1, min(a.samples_per_call, len(jobs)))
+        run_batch(True, per_call, controllers=[fc]); run_batch(True, per_call, lean=True, controllers=[fc])            # warm-up of the batched shapes
+        batch_many_dt, got_many = run_batch(True, per_call, controllers=[fc])
+        batch_many_lean_dt, got_many_lean = run_batch(True, per_call, lean=True, controllers=[fc])
+        many_agree = float(max(max(np.abs(got[i] - got_many[i]).max(), np.abs(got[i] - got_many_lean[i]).max()) for i in got)) if got else 0.0
         fc.close()
         n16 = None
         if a.forward_logn == 15 and not a.no_forward_n16 and rank == 0:
@@ -680,7 +704,8 @@ def run_forward(a, local, rank, world, torch, dist):
     finally:
         os.dup2(saved, 1)
         os.close(devnull); os.close(saved)
-    t = torch.tensor([dt, lean, batch_dt, batch_packed_dt, packed["seconds_per_sample"], batch_agree], device="cuda", dtype=torch.float64)
+    t = torch.tensor([dt, lean, batch_dt, batch_packed_dt, packed["seconds_per_sample"], batch_agree, batch_many_dt, batch_many_lean_dt, many_agree],
+                     device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt, lean, batch_worst, batch_packed_worst = float(t[0].item()), float(t[1].item()), float(t[2].item()), float(t[3].item())
@@ -694,10 +719,15 @@ def run_forward(a, local, rank, world, torch, dist):
     gathered = shard.gather_logits(mat, device="cuda")
     classes = [int(np.argmax(row[:8])) for m_ in gathered for row in m_ if not np.isnan(row[0])]
     batch = {"samples": total, "samples_per_gpu": [len(shard.my_units(total, r, world)) for r in range(world)], "rows_S": a.forward_rows,
-             "in_flight_per_gpu": len(ctl), "seconds": batch_worst, "samples_per_s": total / batch_worst, "logits_gathered": len(classes),
+             "in_flight_per_gpu": n_ctl, "seconds": batch_worst, "samples_per_s": total / batch_worst, "logits_gathered": len(classes),
              "predicted_class_histogram": {str(c): classes.count(c) for c in sorted(set(classes))},
              "block_cache_GB_per_controller": cache_gb,
              "packed": {"seconds": batch_packed_worst, "samples_per_s": total / batch_packed_worst, "max_logit_difference_to_faithful": float(t[5].item())},
+             "packed_many": {"samples_per_call": per_call, "seconds": float(t[6].item()), "samples_per_s": total / float(t[6].item()),
+                             "lean_seconds": float(t[7].item()), "lean_samples_per_s": total / float(t[7].item()),
+                             "max_logit_difference_to_faithful": float(t[8].item()),
+                             "note": "flh_forward_many: several samples per packed forward, every ciphertext one element per sample (ciphertext-parallel over "
+                                     "samples inside each launch); lean = only what the logits read"},
              "note": "BASELINE config 5 (named size: 256 samples, --samples 256): samples sharded over the ranks (shard.my_units), resident "
                      "controllers in throughput mode, logits gathered on rank 0; samples/s = all samples / max-over-ranks wall time"}
     rot = sum(n for k, (n, _) in led.items() if k.startswith("rotate@"))

@@ -32,7 +32,7 @@ _SIGS = {
     "fl_lt_create": (ci, [vp, vp, ci, vp, vp, ci, ci, ci, C.POINTER(vp)]), "fl_lt_rotations": (ci, [vp, vp, vp, ci]),
     "fl_lt_shape": (ci, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
     "fl_lt_apply": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_lt_apply_plain": (ci, [vp, vp, vp, C.POINTER(vp)]), "fl_lt_free": (None, [vp]),
-    "fl_batch_pack": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_batch_slice": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_elem_batch": (ci, [vp]),
+    "fl_batch_pack": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_batch_slice": (ci, [vp, vp, ci, C.POINTER(vp)]), "fl_batch_range": (ci, [vp, vp, ci, ci, C.POINTER(vp)]), "fl_elem_batch": (ci, [vp]),
     "fl_elem_level": (ci, [vp]), "fl_elem_limbs": (ci, [vp]), "fl_elem_deg": (ci, [vp]), "fl_elem_slots": (ci, [vp]), "fl_elem_ncomp": (ci, [vp]),
     "fl_elem_scale": (dbl, [vp]), "fl_elem_clone": (ci, [vp, vp, C.POINTER(vp)]), "fl_elem_free": (None, [vp]),
     "fl_elem_export": (ci, [vp, vp, vp]), "fl_elem_import": (ci, [vp, vp, ci, ci, ci, dbl, ci, C.POINTER(vp)]),

@@ -346,6 +346,11 @@ int fl_batch_pack(fl_ctx* c, fl_elem* const* v, int n, fl_elem** out) {
     FL_TRY({ std::vector<Elem> e(n); for (int i = 0; i < n; ++i) e[i] = v[i]->e; *out = wrap(c->sch->pack(e)); })
 }
 int fl_batch_slice(fl_ctx* c, const fl_elem* a, int i, fl_elem** out) { FL_TRY(*out = wrap(c->sch->slice(a->e, i))) }
+int fl_batch_range(fl_ctx* c, const fl_elem* a, int first, int count, fl_elem** out) {
+    FL_TRY({
+        *out = wrap(c->sch->range(a->e, first, count));
+    })
+}
 int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out) { FL_TRY(*out = wrap(c->sch->clone(a->e))) }
 void fl_elem_free(fl_elem* a) { delete a; }
 int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host) {

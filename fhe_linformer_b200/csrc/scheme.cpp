@@ -153,6 +153,14 @@ Elem Scheme::slice(const Elem& a, int i) const {
     return e;
 }
 
+Elem Scheme::range(const Elem& a, int first, int count) const {
+    if (first < 0 || count < 1 || first + count > a.batch) throw std::out_of_range("batch range out of range");
+    Elem e = a;
+    e.off = a.off + (size_t)first * a.words_each(P.N);
+    e.batch = count;
+    return e;
+}
+
 Elem Scheme::pack(const std::vector<Elem>& v) {
     if (v.empty()) throw std::invalid_argument("pack: empty input");
     const Elem& f = v[0];

@@ -130,6 +130,7 @@ public:
     Elem clone(const Elem& a);                        // Ciphertext::Clone M:223
     Elem pack(const std::vector<Elem>& v);            // gather ciphertexts of identical level / scale into one batched operand
     Elem slice(const Elem& a, int i) const;           // zero-copy view of element i of a batched operand
+    Elem range(const Elem& a, int first, int count) const;   // ... of elements first .. first + count - 1
     int max_batch(int l) const;                       // batch size that keeps the key-switch workspace within budget
     Elem rescaled(const Elem& a);                     // ModReduceInternal
     void rescale_inplace(Elem& a);

@@ -37,6 +37,7 @@ def load_host_library():
     L.flh_generate.argtypes = [vp, ci, vp, ci, ci, ci]
     L.flh_load.argtypes = [vp, C.c_char_p, ci]
     L.flh_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
+    L.flh_forward_many.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), ci, ci, ci, ci, vp, C.POINTER(ci)]
     L.flh_forward.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, ci, ci, ci, vp, CHECKPOINT_FN, vp, C.c_char_p, ci, vp, C.POINTER(ci), C.POINTER(ci)]
     L.flh_invoke.argtypes = [vp, C.c_char_p, vp, ci, vp, ci, vp, ci, vp, ci, vp, ci, C.POINTER(ci)]
     _hlib = L
@@ -124,6 +125,17 @@ class FHEController:
                                      C.byref(nt), C.byref(toks)))
         stage = dict(zip(names.value.decode().split("\n"), secs[:nt.value].tolist()))
         return logits, stage, toks.value
+
+    def forward_many(self, dirs_list, token_limit=0, dead_work=False, classes=20, packed=True):
+        """The forward on several samples in one pass (flh_forward_many): every ciphertext carries one element per sample.
+        `dirs_list`: one {"weights", "input", "tokens"} per sample, same weights folder and same number of rows.  Returns
+        (logits[samples][classes], S)."""
+        n = len(dirs_list)
+        logits = np.zeros((n, classes)); toks = C.c_int(0)
+        ins = (C.c_char_p * n)(*[d["input"].encode() for d in dirs_list]); tks = (C.c_char_p * n)(*[d["tokens"].encode() for d in dirs_list])
+        self._ck(self.hl.flh_forward_many(self.h, dirs_list[0]["weights"].encode(), ins, tks, n, token_limit,
+                                          (1 if dead_work else 0) | (8 if packed else 0), classes, capi._ptr(logits), C.byref(toks)))
+        return logits, toks.value
 
     def invoke(self, method, cts=(), pts=(), ints=(), reals=(), out_cap=1024):
         """Call an FHEController method by name on C-ABI handles (layout tests)."""

@@ -522,6 +522,37 @@ vector<Ctxt> FHEController::read_expanded_inputs(const vector<string>& filenames
     }
     return out;
 }
+// The same for M samples at once: element t of the result is ONE batched ciphertext holding file t of every sample (sample-major
+// inside), so that a whole forward can run on M samples per call (every primitive below takes batched operands).
+vector<Ctxt> FHEController::read_expanded_inputs_many(const vector<vector<string>>& files_per_sample, double scale) {
+    const size_t M = files_per_sample.size();
+    if (M == 0) return {};
+    const size_t T = files_per_sample[0].size();
+    for (const auto& f : files_per_sample)
+        if (f.size() != T) throw std::invalid_argument("read_expanded_inputs_many: the samples differ in their number of rows");
+    if (M == 1) return read_expanded_inputs(files_per_sample[0], scale);
+    const size_t per_call = std::max<size_t>(1, (size_t)max_rows_per_batch / M);      // rows t per batched call
+    vector<Ctxt> out;
+    for (size_t first = 0; first < T; first += per_call) {
+        const size_t count = std::min(T, first + per_call) - first;
+        vector<double> slots(count * M * (size_t)num_slots);
+        for (size_t t = 0; t < count; ++t)
+            for (size_t m = 0; m < M; ++m) {
+                const vector<double> v = stretch(read_values_from_file(files_per_sample[m][first + t]), 128, 128, 128, scale);
+                std::copy(v.begin(), v.begin() + std::min(v.size(), (size_t)num_slots), slots.begin() + (t * M + m) * (size_t)num_slots);
+            }
+        fl_elem* pt = nullptr;
+        need(fl_encode_many(ctx_, slots.data(), (int)(count * M), num_slots, 0, num_slots, &pt), "MakeCKKSPackedPlaintext");
+        const fl_elem* one[1] = {pt};
+        fl_elem* ct = nullptr;
+        const int rc = fl_encrypt_many(ctx_, one, 1, &ct);
+        fl_elem_free(pt);
+        need(rc, "Encrypt");
+        const vector<Ctxt> part = unpack(wrap(ct), (int)M);
+        out.insert(out.end(), part.begin(), part.end());
+    }
+    return out;
+}
 Ptxt FHEController::read_plain_expanded_input(const string& filename, int level, double scale) {
     return encode(stretch(read_values_from_file(filename), 128, 128, 128, scale), level, num_slots);
 }
@@ -616,6 +647,21 @@ vector<Ctxt> FHEController::unpack(const Ctxt& packed) const {
     return out;
 }
 
+// groups of `group` consecutive elements of a batched operand, as views (group = 1: the single elements)
+vector<Ctxt> FHEController::unpack(const Ctxt& packed, int group) const {
+    const int n = fl_elem_batch(packed->handle());
+    if (group < 1 || n % group != 0) throw std::invalid_argument("unpack: the batch does not split into groups of that size");
+    if (group == 1) return unpack(packed);
+    if (n == group) return {packed};
+    vector<Ctxt> out((size_t)(n / group));
+    for (int i = 0; i < n / group; ++i) {
+        fl_elem* e = nullptr;
+        need(fl_batch_range(ctx_, packed->handle(), i * group, group, &e), "slice");
+        out[(size_t)i] = wrap(e);
+    }
+    return out;
+}
+
 vector<Ctxt> FHEController::per_row(const vector<Ctxt>& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const {
     vector<Ctxt> out(rows.size());
     if (!batch_rows) {
@@ -624,13 +670,15 @@ vector<Ctxt> FHEController::per_row(const vector<Ctxt>& rows, const std::functio
     }
     auto same = [](const Ctxt& a, const Ctxt& b) {
         return a->GetLevel() == b->GetLevel() && a->GetNoiseScaleDeg() == b->GetNoiseScaleDeg() && a->GetScalingFactor() == b->GetScalingFactor() &&
-               a->GetSlots() == b->GetSlots();
+               a->GetSlots() == b->GetSlots() && fl_elem_batch(a->handle()) == fl_elem_batch(b->handle());
     };
     size_t first = 0;
     while (first < rows.size()) {
+        // a row may itself be a batch (one element per sample, LinformerForward::add_sample): it comes back as the same batch
+        const int each = fl_elem_batch(rows[first]->handle());
         size_t last = first + 1;
-        while (last < rows.size() && last - first < (size_t)max_rows_per_batch && same(rows[first], rows[last])) ++last;
-        const vector<Ctxt> part = unpack(recipe(pack(vector<Ctxt>(rows.begin() + first, rows.begin() + last))));
+        while (last < rows.size() && (last - first + 1) * (size_t)each <= (size_t)std::max(max_rows_per_batch, each) && same(rows[first], rows[last])) ++last;
+        const vector<Ctxt> part = unpack(recipe(pack(vector<Ctxt>(rows.begin() + first, rows.begin() + last))), each);
         for (size_t i = 0; i < part.size(); ++i) out[first + i] = part[i];
         first = last;
     }

@@ -167,10 +167,13 @@ public:
     Ctxt ladder(const Ctxt& in, int slots, int stride);              // shared body of rotsum / rotsum_padded / repeat
     Ctxt pack(const Rows& rows) const;                               // rows of identical level / degree / scale -> one batched operand
     Rows unpack(const Ctxt& packed) const;                           // zero-copy views of a batched operand
+    Rows unpack(const Ctxt& packed, int group) const;                // ... in groups of `group` consecutive elements
     Rows per_row(const Rows& rows, const std::function<Ctxt(const Ctxt&)>& recipe) const;   // run a per-row recipe on batches
     Rows settle_rows(const Rows& rows) const;                        // pending FLEXIBLEAUTO rescales of many rows, as one batch
     Rows encrypt_many(const vector<Ptxt>& plaintexts);                // Encrypt of many plaintexts of one level as one batched call
     Rows read_expanded_inputs(const vector<string>& filenames, double scale = 1);   // read_expanded_input for a list of files, encrypted together
+    // file t of M samples as ONE batched ciphertext per t (a forward over M samples per call, LinformerForward::add_sample)
+    Rows read_expanded_inputs_many(const vector<vector<string>>& files_per_sample, double scale = 1);
     Ctxt shifted_sum(Rows items, int stride);                        // sum_i rot(items[i], stride * i) as a tree of batched rotations
     Rows all_shifts(const Ctxt& c, int count);                       // rot(c, t), t < count, by batched doubling
     // out[o] = sum_t weights[o][t] * rows[t] (+ bias[o]): the Linformer E / F projection on the row ciphertexts

@@ -124,6 +124,23 @@ int flh_forward(flh_controller* c, const char* weights_dir, const char* input_di
     });
 }
 
+int flh_forward_many(flh_controller* c, const char* weights_dir, const char* const* input_dirs, const char* const* tokens_dirs, int samples,
+                     int token_limit, int flags, int classes, double* logits, int* tokens) {
+    return guarded([&] {
+        if (samples < 1) throw std::invalid_argument("flh_forward_many: no samples");
+        flh::LinformerForward fwd(c->fc, {weights_dir, input_dirs[0], tokens_dirs[0]}, false);
+        fwd.set_token_limit(token_limit);
+        fwd.set_dead_work((flags & 1) != 0);
+        fwd.set_encrypted_projection((flags & 2) != 0);
+        fwd.set_all_token_attention((flags & 4) != 0);
+        fwd.set_packed((flags & 8) != 0);
+        for (int m = 1; m < samples; ++m) fwd.add_sample(input_dirs[m], tokens_dirs[m]);
+        const std::vector<std::vector<double>> z = fwd.run_many(classes);
+        for (int m = 0; m < samples; ++m) std::memcpy(logits + (size_t)m * classes, z[(size_t)m].data(), sizeof(double) * (size_t)classes);
+        if (tokens) *tokens = fwd.tokens();
+    });
+}
+
 int flh_invoke(flh_controller* c, const char* method, fl_elem* const* cts, int n_cts, fl_elem* const* pts, int n_pts, const int* ints, int n_ints,
                const double* reals, int n_reals, fl_elem** out, int out_cap, int* n_out) {
     return guarded([&] {

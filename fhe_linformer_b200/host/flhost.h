@@ -34,6 +34,11 @@ int flh_info(flh_controller* c, int* circuit_depth, int* num_slots);
 int flh_forward(flh_controller* c, const char* weights_dir, const char* input_dir, const char* tokens_dir, int token_limit, int dead_work,
                 int classes, double* logits, flh_checkpoint_fn sink, void* user, char* timing_names, int names_cap, double* timing_seconds,
                 int* n_timings, int* tokens);
+/* The same for `samples` samples in ONE pass (packed mode, flags bit 3): every ciphertext of the forward carries one element per
+   sample, so each kernel launch works on all of them (BASELINE config 5: a batch of samples, ciphertext-parallel).  The samples share
+   the weights folder and must have the same number of rows; logits is [samples][classes]. */
+int flh_forward_many(flh_controller* c, const char* weights_dir, const char* const* input_dirs, const char* const* tokens_dirs, int samples,
+                     int token_limit, int flags, int classes, double* logits, int* tokens);
 
 /* Generic method call for the layout tests: cts / pts are C-ABI handles (borrowed), results are new handles (owned by the caller).
  * method is the FHEController method name, ints / reals its scalar arguments in declaration order. */

@@ -49,6 +49,13 @@ std::vector<Ctxt> LinformerForward::load_expanded(const std::string& dir, const 
     return fc_.read_expanded_inputs(files);
 }
 
+std::vector<Ctxt> LinformerForward::load_expanded(const std::vector<std::string>& dirs, const std::string& stem, int count) {
+    std::vector<std::vector<std::string>> files(dirs.size());
+    for (size_t m = 0; m < dirs.size(); ++m)
+        for (int i = 0; i < count; ++i) files[m].push_back(dirs[m] + "/" + stem + std::to_string(i) + ".txt");
+    return fc_.read_expanded_inputs_many(files);
+}
+
 // ---- Linformer projection under encryption (F1): row i of X_E is sum_t E[i][t] rows[t] + E_b[i], still in the Expanded layout --
 std::vector<Ctxt> LinformerForward::project(const std::vector<Ctxt>& rows, const std::string& which) {
     const std::vector<double> flat = utils::read_values_from_file(layer("selfAttn_" + which + "_weight.txt"));
@@ -225,6 +232,7 @@ std::pair<Ctxt, Ctxt> LinformerForward::affine_and_refresh(const std::vector<Ctx
     if (first_half_only) return {fc_.bootstrap(w0), Ctxt()};
     w1 = affine(w1);                                                                     // M:316-317
     checkpoint(which + "_1", w1);
+    if (samples() > 1) return {fc_.bootstrap(w0), fc_.bootstrap(w1)};                    // each half is already a batch over the samples
     const std::vector<Ctxt> fresh = fc_.per_row({w0, w1}, [&](const Ctxt& c) { return fc_.bootstrap(c); });   // M:319-320, as one batch
     return {fresh[0], fresh[1]};
 }
@@ -267,12 +275,12 @@ std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, c
             for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b0[(size_t)128 * b + i] * gelu_scale;
         hidden.push_back(fc_.add(u, fc_.encode(bias, (int)u->GetLevel() + 1, slots)));   // product rescaled lazily: bias one level lower
     }
-    checkpoint("packed_hidden_block0", halves == 1 ? hidden[0] : fc_.unpack(hidden[0])[0]);
+    if (sink_) checkpoint("packed_hidden_block0", halves == 1 ? hidden[0] : fc_.unpack(hidden[0])[0]);
     // GELU (M:362) on all 2 x 4 hidden ciphertexts at once.  The reference refreshes every container right here (M:363) because its
     // unwrap / W2 / re-wrap chain still costs five levels; the packed chain needs two (W2, affine2), so the refresh moves behind
     // the second affine, where ONE ciphertext (the half that holds the CLS row) is left to bootstrap instead of eight.
     const Ctxt act = fc_.eval_gelu_function(fc_.pack(hidden), -1, 1, gelu_scale, 119);
-    const std::vector<Ctxt> parts = fc_.unpack(act);                                     // [block b][half h] -> index halves b + h
+    const std::vector<Ctxt> parts = fc_.unpack(act, samples());                          // [block b][half h] -> index halves b + h (one element per sample each)
     checkpoint("packed_gelu_block0", parts[0]);
     lap("Intermediate");
     Ctxt sum;
@@ -296,7 +304,7 @@ std::pair<Ctxt, Ctxt> LinformerForward::feed_forward_packed(const Ctxt& half0, c
         for (int t = 0; t < 128; ++t) bias[(size_t)128 * i + t] = b2.at((size_t)i) * (cls_column_scale ? (*cls_column_scale)[(size_t)t] : 1.0);
     sum = fc_.add(sum, fc_.encode(bias, (int)sum->GetLevel() + 1, slots));
     if (cls_column_scale) return {sum, Ctxt()};
-    const std::vector<Ctxt> out = fc_.unpack(sum);
+    const std::vector<Ctxt> out = fc_.unpack(sum, samples());
     return {out[0], out[1]};
 }
 
@@ -344,12 +352,30 @@ Ctxt LinformerForward::encoder() {
 
     std::vector<Ctxt> rows;
     rows.push_back(fc_.read_expanded_input(w("cls_token.txt")));                         // M:170
-    const std::vector<Ctxt> embedded = load_expanded(files_.tokens, "input_", found);    // M:171-173
-    rows.insert(rows.end(), embedded.begin(), embedded.end());
     std::vector<Ctxt> xe, xf;
-    if (!encrypted_projection_) {
-        xe = load_expanded(files_.input, "XE_", 32);                                     // M:159-162
-        xf = load_expanded(files_.input, "XF_", 32);                                     // M:164-167
+    if (more_.empty()) {
+        const std::vector<Ctxt> embedded = load_expanded(files_.tokens, "input_", found);    // M:171-173
+        rows.insert(rows.end(), embedded.begin(), embedded.end());
+        if (!encrypted_projection_) {
+            xe = load_expanded(files_.input, "XE_", 32);                                 // M:159-162
+            xf = load_expanded(files_.input, "XF_", 32);                                 // M:164-167
+        }
+    } else {
+        // several samples per call: row t of every sample in one batched ciphertext (the CLS row is a model weight: one for all)
+        if (!packed_ || all_tokens_ || encrypted_projection_ || sink_)
+            throw std::invalid_argument("several samples per call: packed mode only (no all-token attention, no encrypted projection, no checkpoints)");
+        std::vector<std::string> token_dirs{files_.tokens}, input_dirs{files_.input};
+        for (const auto& s : more_) { input_dirs.push_back(s.first); token_dirs.push_back(s.second); }
+        for (const std::string& d : token_dirs) {
+            int n = 0;
+            for (const auto& entry : fs::directory_iterator(d))
+                if (entry.path().filename().string().rfind("input_", 0) == 0) ++n;
+            if (std::min(n, token_limit_ > 0 ? token_limit_ : n) != found) throw std::invalid_argument("several samples per call: the samples differ in their number of rows");
+        }
+        const std::vector<Ctxt> embedded = load_expanded(token_dirs, "input_", found);
+        rows.insert(rows.end(), embedded.begin(), embedded.end());
+        xe = load_expanded(input_dirs, "XE_", 32);
+        xf = load_expanded(input_dirs, "XF_", 32);
     }
     lap("Encrypt");
     if (encrypted_projection_) {
@@ -467,7 +493,19 @@ std::vector<double> LinformerForward::logits(const Ctxt& classified, int classes
     return out;
 }
 
+std::vector<std::vector<double>> LinformerForward::logits_many(const Ctxt& classified, int classes) {
+    std::vector<std::vector<double>> out;
+    for (const Ctxt& c : fc_.unpack(classified)) out.push_back(logits(c, classes));
+    return out;
+}
+
+std::vector<std::vector<double>> LinformerForward::run_many(int classes) {
+    times_.clear();
+    return logits_many(classifier(pooler(encoder())), classes);
+}
+
 std::vector<double> LinformerForward::run(int classes) {
+    if (samples() > 1) throw std::invalid_argument("run(): several samples were added, call run_many()");
     times_.clear();
     return logits(classifier(pooler(encoder())), classes);
 }

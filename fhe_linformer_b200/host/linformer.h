@@ -47,12 +47,19 @@ public:
     // row, and the unwrap / container / re-wrap round trips between them (F.cpp:1086-1205) disappear: ~1 k rotations per forward
     // instead of ~21 k at S = 200.  Needs FHEController::generate_packed_keys().
     void set_packed(bool on) { packed_ = on; }
+    // One more sample (its XE_/XF_ folder and its token folder; same weights, same number of rows) evaluated by the SAME calls:
+    // every ciphertext of the forward then carries one element per sample (BASELINE config 5: a batch of samples,
+    // ciphertext-parallel).  Packed mode only; the results come from run_many() / logits_many().
+    void add_sample(const std::string& input_dir, const std::string& tokens_dir) { more_.push_back({input_dir, tokens_dir}); }
+    int samples() const { return 1 + (int)more_.size(); }
 
     Ctxt encoder();                       // main.cpp:145-425
     Ctxt pooler(const Ctxt& encoded);     // main.cpp:427-451
     Ctxt classifier(const Ctxt& pooled);  // main.cpp:453-475
     std::vector<double> logits(const Ctxt& classified, int classes = 20);   // main.cpp:115-123: slot 128 i holds class i
     std::vector<double> run(int classes = 20);                               // the three stages + decrypt
+    std::vector<std::vector<double>> logits_many(const Ctxt& classified, int classes = 20);   // one vector per sample
+    std::vector<std::vector<double>> run_many(int classes = 20);
     static int argmax_softmax(const std::vector<double>& logits, std::vector<double>* prob = nullptr);   // main.cpp:125-142
 
     const std::vector<StageTime>& timings() const { return times_; }
@@ -66,6 +73,7 @@ private:
     void checkpoint(const std::string& name, const Ctxt& c);
     void lap(const std::string& name);
     std::vector<Ctxt> load_expanded(const std::string& dir, const std::string& stem, int count);
+    std::vector<Ctxt> load_expanded(const std::vector<std::string>& dirs, const std::string& stem, int count);
 
     Ctxt attend_cls(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
     Ctxt attend_cls_packed(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
@@ -83,6 +91,7 @@ private:
     bool encrypted_projection_ = false;
     bool all_tokens_ = false;
     bool packed_ = false;
+    std::vector<std::pair<std::string, std::string>> more_;   // (input folder, token folder) of the samples after the first
     std::vector<Ctxt> attend_all(const std::vector<Ctxt>& rows, const std::vector<Ctxt>& xe, const std::vector<Ctxt>& xf);
     std::vector<Ctxt> project(const std::vector<Ctxt>& rows, const std::string& which);
     int tokens_ = 0;

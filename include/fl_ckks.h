@@ -207,6 +207,7 @@ int fl_elem_clone(fl_ctx* c, const fl_elem* a, fl_elem** out);
  * independent iterations of the reference's `for (i < rows.size())` loops (F.cpp:872-1120) share kernel launches. */
 int fl_batch_pack(fl_ctx* c, fl_elem* const* v, int n, fl_elem** out);
 int fl_batch_slice(fl_ctx* c, const fl_elem* a, int i, fl_elem** out);   /* zero-copy view of element i */
+int fl_batch_range(fl_ctx* c, const fl_elem* a, int first, int count, fl_elem** out);   /* zero-copy view of elements first .. first + count - 1 */
 int fl_elem_batch(const fl_elem* a);
 void fl_elem_free(fl_elem* a);
 int fl_elem_export(fl_ctx* c, const fl_elem* a, uint64_t* host /* ncomp * limbs * N */);

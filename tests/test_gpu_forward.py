@@ -96,6 +96,32 @@ def test_packed_mode_matches_slot_simulator(setup):
     bare.close()
 
 
+def test_several_samples_per_call(setup, tmp_path):
+    """flh_forward_many (BASELINE config 5, ciphertext-parallel over samples): three different samples through ONE packed forward,
+    every ciphertext carrying one element per sample -- each sample's logits equal its own slot simulation (<= 1e-3, same class)
+    and the single-sample packed run."""
+    from fhe_linformer_b200 import synth
+    from oracle import linformer_sim as ls
+    fc, model, sample, dirs, root = setup
+    fc.set_option("packed_keys", 1)
+    samples = [sample] + [synth.make_sample(model, 128, seed=777 + i) for i in range(2)]
+    dirs_list = [dirs]
+    for i, sm in enumerate(samples[1:]):
+        d = {"weights": dirs["weights"], "input": str(tmp_path / ("input%d" % i)), "tokens": str(tmp_path / ("tokens%d" % i))}
+        synth.write_sample_files(d["input"], d["tokens"], sm)
+        dirs_list.append(d)
+    for lean in (False, True):
+        got, S = fc.forward_many(dirs_list, dead_work=not lean, packed=True)
+        assert S == 129 and got.shape == (3, 20)
+        for sm, z in zip(samples, got):
+            ref = ls.sim_forward(model, sm)
+            assert np.abs(z - ref).max() < LOGIT_TOL and int(np.argmax(z)) == int(np.argmax(ref))
+    single, _, _ = fc.forward(dirs_list[1], packed=True, dead_work=False)
+    assert np.abs(single - got[1]).max() < 4e-4
+    with pytest.raises(RuntimeError, match="packed mode only"):
+        fc.forward_many(dirs_list, packed=False)
+
+
 def test_encrypted_projection_variant(setup):
     """X_E / X_F computed on the server from the encrypted rows (fl_linear_wsum) instead of uploaded by the client."""
     from oracle import linformer_sim as ls
