@@ -500,17 +500,6 @@ __global__ void __launch_bounds__(kThreads) rescale_conv_kernel(u64* __restrict_
     tq[((size_t)p * (l - 1) + i) * T.N + j] = v;
 }
 
-__global__ void __launch_bounds__(kThreads) rescale_finish_kernel(u64* __restrict__ out, const u64* __restrict__ in, const u64* __restrict__ tq,
-                                                                  DevTables T, RsConst rs, int l) {
-    const int p = blockIdx.z, i = blockIdx.y;
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= T.N) return;
-    const u64 q = T.q[i];
-    const size_t oi = ((size_t)p * l + i) * T.N + j, oo = ((size_t)p * (l - 1) + i) * T.N + j;
-    const u64 w = rs.qlinv[(size_t)(l - 1) * T.L + i], ws = rs.qlinv_sh[(size_t)(l - 1) * T.L + i];
-    out[oo] = mul_shoup(submod(in[oi], tq[oo], q), w, ws, q);
-}
-
 __global__ void __launch_bounds__(kThreads) mod_switch_kernel(u64* __restrict__ out, const u64* __restrict__ x, DevTables T, int src_mod, LimbSel sel) {
     const int p = blockIdx.z, i = blockIdx.y;
     const int j = blockIdx.x * kThreads + threadIdx.x;
@@ -715,10 +704,6 @@ void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, i
 }
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {
     rescale_conv_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(tq, xlast, t, l);
-    FLK_CUDA(cudaGetLastError());
-}
-void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s) {
-    rescale_finish_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(out, in, tq, t, rs, l);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_mod_switch(const DevTables& t, u64* out, const u64* x, int src_mod, const LimbSel& sel, int polys, cudaStream_t s) {

@@ -129,8 +129,7 @@ struct RsConst {
 };
 // tq[p][i][j] = centred switch of xlast[p][j] (coefficient form of limb l-1) to modulus q_i, i < l-1
 void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s);
-// out[p][i] = (in[p][i] - tq[p][i]) * q_{l-1}^-1 ; in has l limbs per poly, out has l-1
-void launch_rescale_finish(const DevTables& t, const RsConst& rs, u64* out, const u64* in, const u64* tq, int l, int polys, cudaStream_t s);
+// (out[p][i] = (in[p][i] - NTT(tq[p][i])) * q_{l-1}^-1 is the ModDown finish with P = q_{l-1}: launch_ntt_finish)
 
 // ModRaise / modulus switch: out[p][i][j] = centred(x[p][j] mod q_src) mod q_{sel.m[i]}   (x in coefficient form)
 void launch_mod_switch(const DevTables& t, u64* out, const u64* x, int src_mod, const LimbSel& sel, int polys, cudaStream_t s);

@@ -19,6 +19,7 @@
 // for moduli below 2^56 (every Q limb) 65q < 2^64, so the forward transform carries NO conditional subtraction
 // until one Barrett-style reduction at the very end; the 60-bit P limbs keep values below 8q.  The inverse keeps
 // values below 4q with one conditional subtraction per butterfly.  Per butterfly: 9 IMAD-class + 9 IADD3-class SASS.
+#include <atomic>
 #include <cstdlib>
 
 #include "device_ctx.h"
@@ -398,9 +399,12 @@ void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, con
     const dim3 grid(1u << kRadix1Log, f.polys * f.l, batch);
     switch (S2) {
 #define FLK_CASE(X) case X: { constexpr size_t shm = (size_t)((1 << X) + (1 << X) / 8 + 2 * (1 << X) + 2) * 8;                                                      \
-                              static bool cfg = false;                                                                                                     \
-                              if (!cfg) { FLK_CUDA(cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));       \
-                                          cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); cfg = true; } \
+                              static std::atomic<unsigned long long> cfg{0};   /* the attribute belongs to the device: one bit per device */             \
+                              int dev = 0; FLK_CUDA(cudaGetDevice(&dev));                                                                                  \
+                              if (!((cfg.load() >> (dev & 63)) & 1ull)) {                                                                                  \
+                                  FLK_CUDA(cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));       \
+                                  cudaFuncSetAttribute(ntt_chunk_finish_kernel<X>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+                                  cfg.fetch_or(1ull << (dev & 63)); }                                                                                      \
                               ntt_chunk_finish_kernel<X><<<grid, Sched<X>::NT, shm, s>>>(tq, t, tq_bs, f); } break;
         FLK_CASE(6) FLK_CASE(7) FLK_CASE(8) FLK_CASE(9) FLK_CASE(10) FLK_CASE(11) FLK_CASE(12)
 #undef FLK_CASE
