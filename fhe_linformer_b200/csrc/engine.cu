@@ -253,18 +253,18 @@ const KsLevel& Engine::ks_level(int l) {
 void Engine::rescale(u64* out, const u64* in, int l, int polys) {
     if (l < 2) throw std::invalid_argument("rescale: no limb left to drop");
     const int N = P.N;
-    // Five launches, each polynomial a batch element: the inverse transform reads the last limb where it lies, and the
+    // Four launches, each polynomial a batch element: the inverse transform reads the last limb where it lies, and the
     // (x_i - switched) q_last^-1 epilogue rides on the last pass of the forward transform (the ModDown finish with P = q_last).
     u64* xlast = alloc((size_t)polys * N);
     LimbSel s1; s1.push(l - 1, 0);
     launch_intt(T, xlast, s1, polys, (size_t)N, nullptr, nullptr, stream, in + (size_t)(l - 1) * N, (size_t)l * N);
     u64* tq = alloc((size_t)polys * (l - 1) * N);
-    launch_rescale_conv(T, tq, xlast, l, polys, stream);
     FinishArgs fa{};
     fa.out = out; fa.out_bs = (size_t)(l - 1) * N;
     fa.acc = in; fa.acc_ps = 0; fa.acc_bs = (size_t)l * N;
     fa.tq = tq; fa.tq_bs = (size_t)(l - 1) * N;
     NttFinish f{fa, nullptr, rs_.qlinv + (size_t)(l - 1) * P.L, rs_.qlinv_sh + (size_t)(l - 1) * P.L, l - 1, 1};
+    f.switch_src = xlast; f.switch_mod = l - 1;           // the centred switch of the dropped limb happens in the first pass's loads
     launch_ntt_finish(T, tq, polys, (size_t)(l - 1) * N, f, stream);
     release(xlast); release(tq);
     if (ledger_on) ledger.add("rescale", l, (32.0 * l - 16.0) * N, polys / 2 > 0 ? polys / 2 : 1);

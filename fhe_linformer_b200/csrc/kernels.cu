@@ -488,18 +488,7 @@ __global__ void __launch_bounds__(kThreads) lincomb_kernel(u64* __restrict__ out
         if (o0 + o < n_out) out[(size_t)(o0 + o) * ct + poly_off] = acc[o];
 }
 
-// ---------------- rescale ----------------
-__global__ void __launch_bounds__(kThreads) rescale_conv_kernel(u64* __restrict__ tq, const u64* __restrict__ xlast, DevTables T, int l) {
-    const int p = blockIdx.z, i = blockIdx.y;
-    const int j = blockIdx.x * kThreads + threadIdx.x;
-    if (j >= T.N) return;
-    const u64 ql = T.q[l - 1], half = ql >> 1, q = T.q[i], ml = T.mu_lo[i], mh = T.mu_hi[i];
-    const u64 x = xlast[(size_t)p * T.N + j];
-    u64 v = barrett128(U128{x, 0}, q, ml, mh);
-    if (x > half) v = submod(v, barrett128(U128{ql, 0}, q, ml, mh), q);
-    tq[((size_t)p * (l - 1) + i) * T.N + j] = v;
-}
-
+// ---------------- modulus switch of one coefficient-form limb (ModRaise of the bootstrap; the rescale does its switch inside ntt.cu) ----------------
 __global__ void __launch_bounds__(kThreads) mod_switch_kernel(u64* __restrict__ out, const u64* __restrict__ x, DevTables T, int src_mod, LimbSel sel) {
     const int p = blockIdx.z, i = blockIdx.y;
     const int j = blockIdx.x * kThreads + threadIdx.x;
@@ -700,10 +689,6 @@ void launch_lincomb(const DevTables& t, u64* out, const u64* in, const u64* k, i
                     const u64* const* in_ptrs) {
     lincomb_kernel<<<dim3(cdiv(t.N, kThreads), rows, (n_out + kOt - 1) / kOt), kThreads, 0, s>>>(out, in, in_ptrs, reinterpret_cast<const ulonglong2*>(k),
                                                                                                t, l, rows, n_in, n_out);
-    FLK_CUDA(cudaGetLastError());
-}
-void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s) {
-    rescale_conv_kernel<<<dim3(cdiv(t.N, kThreads), l - 1, polys), kThreads, 0, s>>>(tq, xlast, t, l);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_mod_switch(const DevTables& t, u64* out, const u64* x, int src_mod, const LimbSel& sel, int polys, cudaStream_t s) {

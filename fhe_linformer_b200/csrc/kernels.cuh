@@ -113,6 +113,10 @@ struct NttFinish {
     const u64* pinv;          // [L] P^-1 mod q_i and Shoup companions
     const u64* pinv_sh;
     int l, polys;
+    // rescale: the operand of the transform is ONE coefficient-form polynomial per batch element modulo limb switch_mod
+    // ([batch][N] at switch_src), switched to each limb's modulus by the first pass on load (tq is then written, not read, by that pass)
+    const u64* switch_src = nullptr;
+    int switch_mod = -1;
 };
 void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, const NttFinish& f, cudaStream_t s);
 
@@ -127,8 +131,7 @@ struct RsConst {
     const u64* qlinv;     // [L][L]: q_r^-1 mod q_i
     const u64* qlinv_sh;
 };
-// tq[p][i][j] = centred switch of xlast[p][j] (coefficient form of limb l-1) to modulus q_i, i < l-1
-void launch_rescale_conv(const DevTables& t, u64* tq, const u64* xlast, int l, int polys, cudaStream_t s);
+// (the centred switch of the dropped limb to every other modulus happens in the first pass of launch_ntt_finish: NttFinish::switch_src)
 // (out[p][i] = (in[p][i] - NTT(tq[p][i])) * q_{l-1}^-1 is the ModDown finish with P = q_{l-1}: launch_ntt_finish)
 
 // ModRaise / modulus switch: out[p][i][j] = centred(x[p][j] mod q_src) mod q_{sel.m[i]}   (x in coefficient form)

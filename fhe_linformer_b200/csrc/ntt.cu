@@ -98,7 +98,8 @@ constexpr int R1 = 1 << kRadix1Log;
 
 template <bool FWD>
 __global__ void __launch_bounds__(256, 3) ntt_column_kernel(u64* __restrict__ data, DevTables T, LimbSel sel, size_t batch_stride,
-                                                         const u64* __restrict__ post, const u64* __restrict__ post_sh) {
+                                                         const u64* __restrict__ post, const u64* __restrict__ post_sh,
+                                                         const u64* __restrict__ xsrc = nullptr, int xsrc_mod = -1) {
     // the 15 twiddles of these four stages are the same for every column of a limb: one copy per CTA in shared memory
     // (broadcast reads) instead of 60 registers per thread
     __shared__ ulonglong2 stw[R1];
@@ -111,8 +112,23 @@ __global__ void __launch_bounds__(256, 3) ntt_column_kernel(u64* __restrict__ da
     u64* a = data + (size_t)blockIdx.z * batch_stride + (size_t)sel.pos[limb] * T.N + c;
     const u64 q = T.q[m], nq = 0 - q, q4 = q << 2;
     u64 e[R1];
+    if (FWD && xsrc) {
+        // forward transform of a polynomial given in coefficient form modulo ANOTHER limb (rescale: the dropped limb): the centred
+        // switch to this limb's modulus happens on load, so the switched copy is never written to or read from HBM
+        const u64 qs = T.q[xsrc_mod], half = qs >> 1, ml = T.mu_lo[m], mh = T.mu_hi[m];
+        const u64 qs_here = barrett128(U128{qs, 0}, q, ml, mh);
+        const u64* x = xsrc + (size_t)blockIdx.z * T.N + c;
 #pragma unroll
-    for (int k = 0; k < R1; ++k) e[k] = a[(size_t)k * cols];
+        for (int k = 0; k < R1; ++k) {
+            const u64 v0 = x[(size_t)k * cols];
+            u64 v = barrett128(U128{v0, 0}, q, ml, mh);
+            if (v0 > half) v = submod(v, qs_here, q);
+            e[k] = v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R1; ++k) e[k] = a[(size_t)k * cols];
+    }
     if (FWD) {
         if (is_wide(q)) ct_block<kRadix1Log, true>(e, stw, nq, q4); else ct_block<kRadix1Log, false>(e, stw, nq, q4);
 #pragma unroll
@@ -374,10 +390,10 @@ void launch_chunk(const DevTables& t, u64* data, const LimbSel& sel, int batch, 
 
 template <bool FWD>
 void launch_column(const DevTables& t, u64* data, const LimbSel& sel, int batch, size_t bs, const u64* post, const u64* post_sh,
-                   cudaStream_t s) {
+                   cudaStream_t s, const u64* xsrc = nullptr, int xsrc_mod = -1) {
     const int cols = t.N >> kRadix1Log, threads = cols < 256 ? cols : 256;
     dim3 grid((cols + threads - 1) / threads, sel.n, batch);
-    ntt_column_kernel<FWD><<<grid, threads, 0, s>>>(data, t, sel, bs, post, post_sh);
+    ntt_column_kernel<FWD><<<grid, threads, 0, s>>>(data, t, sel, bs, post, post_sh, xsrc, xsrc_mod);
 }
 
 
@@ -394,7 +410,7 @@ void launch_ntt_finish(const DevTables& t, u64* tq, int batch, size_t tq_bs, con
     if (batch == 0) return;
     LimbSel sq;
     for (int i = 0; i < f.polys * f.l; ++i) sq.push(i % f.l, i);
-    launch_column<true>(t, tq, sq, batch, tq_bs, nullptr, nullptr, s);
+    launch_column<true>(t, tq, sq, batch, tq_bs, nullptr, nullptr, s, f.switch_src, f.switch_mod);
     const int S2 = t.logN - kRadix1Log;
     const dim3 grid(1u << kRadix1Log, f.polys * f.l, batch);
     switch (S2) {
