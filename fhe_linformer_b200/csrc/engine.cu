@@ -278,6 +278,25 @@ void Engine::ntt_l2(u64* data, const LimbSel& sel, int batch, size_t bs) {
     for (int b0 = 0; b0 < batch; b0 += sub) launch_ntt(T, data + (size_t)b0 * bs, sel, std::min(sub, batch - b0), bs, stream);
 }
 
+// ModUp of INTT'd, pre-scaled digits: base conversion to the limbs outside each digit, then the forward transform of those limbs.
+// (Folding the conversion into the loads of the transform's first pass -- VERDICT r01 item 2(ii) -- was built and measured in round 2:
+// bit-exact, but 2 464 instead of 3 981 rotations/s.  A column-pass thread owns 16 coefficients of ONE target limb, so every one of
+// the l + K - alpha targets of a digit re-reads the digit's alpha source limbs through L2, 28 times the loads of the conversion
+// kernel, which keeps the sources of two coefficients in registers across all targets.  DESIGN.md section 4.)
+void Engine::modup_ntt(const KsLevel& ks, u64* up, const u64* dco, int B, size_t up_bs, size_t dco_bs) {
+    const int l = ks.l, ext = l + P.K;
+    LimbSel su;
+    for (int d = 0; d < ks.beta; ++d) {
+        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
+        for (int t = 0; t < ext; ++t) {
+            if (t >= lo && t < hi) continue;
+            su.push(P.mod_index_ext(l, t), d * ext + t);
+        }
+    }
+    launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
+    ntt_l2(up, su, B, up_bs);
+}
+
 // Hybrid key switch of a batch of polynomials with one evaluation key (HYBRID KeySwitch of EvalRotate / EvalMult, A.6):
 //   INTT digits (pre-scaled) -> ModUp base conversion -> NTT -> inner product with the key over Q_l u P -> INTT of the P part
 //   -> ModDown conversion -> NTT -> (acc - conv) P^-1 + addends, optionally permuted by the automorphism of g.
@@ -293,16 +312,7 @@ void Engine::keyswitch(const KsBatch& io, const u64* evk, uint32_t g) {
     launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream, io.c, io.c_bs);   // reads c1 in place: no gather copy
     // 2. ModUp: basis-extend every digit to the limbs outside it, back to evaluation form
     u64* up = alloc(up_bs * B);
-    launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
-    LimbSel su;
-    for (int d = 0; d < beta; ++d) {
-        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
-        for (int t = 0; t < ext; ++t) {
-            if (t >= lo && t < hi) continue;
-            su.push(P.mod_index_ext(l, t), d * ext + t);
-        }
-    }
-    ntt_l2(up, su, B, up_bs);
+    modup_ntt(ks, up, dco, B, up_bs, dco_bs);
     // 3. inner product with the evaluation key over Q_l u P
     u64* acc = alloc(acc_bs * B);
     launch_inner_product(T, ks, acc, up, io.c, evk, B, acc_bs, up_bs, io.c_bs, stream);
@@ -401,16 +411,7 @@ void Engine::rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs
     u64* dco = alloc(dco_bs * B);
     launch_intt(T, dco, sel_range(0, l), B, dco_bs, ks.post, ks.post_sh, stream, c1, cs);
     u64* up = alloc(up_bs * B);
-    launch_modup_conv(T, ks, up, dco, B, up_bs, dco_bs, stream);
-    LimbSel su;
-    for (int d = 0; d < beta; ++d) {
-        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
-        for (int t = 0; t < ext; ++t) {
-            if (t >= lo && t < hi) continue;
-            su.push(P.mod_index_ext(l, t), d * ext + t);
-        }
-    }
-    launch_ntt(T, up, su, B, up_bs, stream);
+    modup_ntt(ks, up, dco, B, up_bs, dco_bs);
     u64* acc = alloc(acc_bs * B);
     launch_inner_product_multi(T, ks, acc, up, c1, evks, maps, nk, B, acc_bs, up_bs, cs, stream);
     u64* s0 = alloc(dco_bs * B);
@@ -440,16 +441,7 @@ void Engine::modup_batch(u64* up, const u64* c, size_t c_bs, int Bn, int l) {
     const size_t dco_bs = (size_t)l * N, up_bs = (size_t)beta * ext * N;
     u64* dco = alloc(dco_bs * Bn);
     launch_intt(T, dco, sel_range(0, l), Bn, dco_bs, ks.post, ks.post_sh, stream, c, c_bs);
-    launch_modup_conv(T, ks, up, dco, Bn, up_bs, dco_bs, stream);
-    LimbSel su;
-    for (int d = 0; d < beta; ++d) {
-        const int lo = d * ks.alpha, hi = std::min(lo + ks.alpha, l);
-        for (int t = 0; t < ext; ++t) {
-            if (t >= lo && t < hi) continue;
-            su.push(P.mod_index_ext(l, t), d * ext + t);
-        }
-    }
-    launch_ntt(T, up, su, Bn, up_bs, stream);
+    modup_ntt(ks, up, dco, Bn, up_bs, dco_bs);
     release(dco);
 }
 

@@ -81,6 +81,7 @@ public:
     // out[b] = plan(ct[b]) for B ciphertexts stored back to back: one ModUp for all baby rotations, plaintext products in the
     // extended basis, one ModDown per giant step, giant rotations summed before a single final ModDown
     void linear_transform(u64* out, const u64* ct, int B, const LtPlan& plan);
+    void modup_ntt(const KsLevel& ks, u64* up, const u64* dco, int B, size_t up_bs, size_t dco_bs);   // base conversion + NTT of all digits
     // out[b] = (self ? ct[b] : 0) + sum_k rotate(ct[b], g_k): the rotations share one ModUp and one ModDown (hoisting); nk <= kHoistMax
     void rotate_sum_batch(u64* out, const u64* ct, int l, const uint32_t* gs, const u64* const* evks, int nk, int B, bool self);
     // the same with HOST operands: uploads, key switches and downloads of successive chunks overlap on three streams
