@@ -29,8 +29,9 @@ int flh_info(flh_controller* c, int* circuit_depth, int* num_slots);
 
 /* encoder1 -> pooler -> classifier -> decrypt (main.cpp:105-123).  timings: up to *n_timings (name, seconds) pairs. */
 /* dead_work bit 0: issue the operations main.cpp never reads; bit 1: evaluate the E / F projection under encryption (F1);
- * bit 2: the all-token attention circuit of main_2.cpp (F4); bit 3: packed mode -- the FFN on 128 rows per ciphertext through
- * BSGS diagonal matrix products (LinformerForward::set_packed) */
+ * bit 2: the all-token attention circuit of main_2.cpp (F4); bit 3: packed mode -- every linear layer (attention and FFN) on 128
+ * rows per ciphertext through BSGS diagonal matrix products (LinformerForward::set_packed); with bit 0 clear only the
+ * operations the logits read are evaluated (2 bootstraps per forward) */
 int flh_forward(flh_controller* c, const char* weights_dir, const char* input_dir, const char* tokens_dir, int token_limit, int dead_work,
                 int classes, double* logits, flh_checkpoint_fn sink, void* user, char* timing_names, int names_cap, double* timing_seconds,
                 int* n_timings, int* tokens);

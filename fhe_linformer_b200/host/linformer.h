@@ -41,11 +41,13 @@ public:
     // up to 128 queries packed by matmulScores(vector)), 1/x fitted on [-1, 190000], W_O bias on every row, tanh scale 1/18,
     // plaintext class mask -- SURVEY.md F4
     void set_all_token_attention(bool on) { all_tokens_ = on; }
-    // true: packed mode (BASELINE north star: BSGS diagonal ct x pt matmul behind the FFN linears).  Same network, same weights,
-    // same logits up to CKKS noise; the rows stay in the wrapped-expanded layout (128 rows per ciphertext) from the first affine
-    // to the second, each 128 x 128 weight block is ONE FHEController::packed_linear per half instead of a (x) + 7-step ladder per
-    // row, and the unwrap / container / re-wrap round trips between them (F.cpp:1086-1205) disappear: ~1 k rotations per forward
-    // instead of ~21 k at S = 200.  Needs FHEController::generate_packed_keys().
+    // true: packed mode (BASELINE north star: BSGS diagonal ct x pt matmul behind the linear layers).  Same network, same weights,
+    // same logits up to CKKS noise; the 32 projected rows of the attention block and the S rows from the first affine to the
+    // second stay in the wrapped-expanded layout (128 rows per ciphertext), each 128 x 128 weight block (W_K, W_V, W_Q, W_O, the
+    // eight FFN blocks) is ONE FHEController::packed_linear instead of a (x) + 7-step ladder per row, and the unwrap / container /
+    // re-wrap round trips between them (F.cpp:1086-1205) disappear: ~0.8 k rotations per forward instead of ~21 k at S = 200.
+    // Together with set_dead_work(false) only what the logits read is evaluated (first half of the rows, CLS column after W2).
+    // Needs FHEController::generate_packed_keys().
     void set_packed(bool on) { packed_ = on; }
     // One more sample (its XE_/XF_ folder and its token folder; same weights, same number of rows) evaluated by the SAME calls:
     // every ciphertext of the forward then carries one element per sample (BASELINE config 5: a batch of samples,
