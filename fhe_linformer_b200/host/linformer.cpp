@@ -348,6 +348,7 @@ Ctxt LinformerForward::encoder() {
         if (entry.path().filename().string().rfind("input_", 0) == 0) ++found;
     if (token_limit_ > 0 && found > token_limit_) found = token_limit_;
     tokens_ = found + 1;
+    if (packed_ && all_tokens_) throw std::invalid_argument("packed mode evaluates the CLS-query attention of main.cpp; the all-token circuit has no packed form");
     if (verbose_) std::cout << tokens_ << " inputs found!" << std::endl << std::endl;
 
     std::vector<Ctxt> rows;
