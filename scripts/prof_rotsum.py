@@ -21,6 +21,10 @@ rotsum = lambda x: c._out(c.lib.fl_rotsum, x.h, 7, 128)
 c.lib.fl_rotsum.restype = C.c_int
 c.lib.fl_rotsum.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 r = rotsum(b); c.sync()
+rt = C.CDLL("libcudart.so")
+rt.cudaProfilerStart()          # under ncu --profile-from-start off: exactly one ladder
+r = rotsum(b); c.sync()
+rt.cudaProfilerStop()
 t0 = time.time()
 for _ in range(reps):
     r = rotsum(b)
