@@ -18,6 +18,7 @@ _SIGS = {
     "fl_keys_save": (ci, [vp, C.c_char_p]), "fl_keys_load": (ci, [vp, C.c_char_p]),
     "fl_encode": (ci, [vp, vp, vp, ci, ci, ci, C.POINTER(vp)]),
     "fl_encode_many": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(vp)]),
+    "fl_encrypt_values_many": (ci, [vp, vp, ci, ci, ci, ci, C.POINTER(vp)]),
     "fl_encrypt": (ci, [vp, vp, C.POINTER(vp)]), "fl_encrypt_seeded": (ci, [vp, vp, u64, C.POINTER(vp)]),
     "fl_encrypt_many": (ci, [vp, vp, ci, C.POINTER(vp)]),
     "fl_decrypt": (ci, [vp, vp, vp, vp, ci]), "fl_decode": (ci, [vp, vp, vp, vp, ci]),
@@ -151,6 +152,12 @@ class CKKS(Engine):
         if m.ndim != 2: raise ValueError("encode_many: a 2-D array of real rows expected")
         slots = slots or self.N // 2
         return self._out(self.lib.fl_encode_many, _ptr(m), m.shape[0], m.shape[1], level, slots)
+
+    def encrypt_values_many(self, rows, level=0, slots=None):
+        """Encode + encrypt several real vectors in one pass (fl_encrypt_values_many); returns the list of ciphertexts."""
+        m = np.ascontiguousarray(np.asarray(rows, np.float64))
+        if m.ndim != 2: raise ValueError("encrypt_values_many: a 2-D array of real rows expected")
+        return self.unpack(self._out(self.lib.fl_encrypt_values_many, _ptr(m), m.shape[0], m.shape[1], level, slots or self.N // 2))
 
     def encrypt(self, x, level=0, slots=None, seed=None):
         p = x if isinstance(x, Elem) else self.encode(x, level, slots)

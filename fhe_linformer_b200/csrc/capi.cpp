@@ -250,6 +250,9 @@ int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, i
 int fl_encode_many(fl_ctx* c, const double* re, int count, int n, int level, int slots, fl_pt** out) {
     FL_TRY(*out = wrap(c->sch->encode_many_real(re, count, n, level, slots)))
 }
+int fl_encrypt_values_many(fl_ctx* c, const double* re, int count, int n, int level, int slots, fl_ct** out) {
+    FL_TRY(*out = wrap(c->sch->encrypt_values_many(re, count, n, level, slots)))
+}
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out) { FL_TRY(*out = wrap(c->sch->encrypt(p->e))) }
 int fl_encrypt_many(fl_ctx* c, const fl_pt* const* pts, int n, fl_ct** out) {
     FL_TRY({

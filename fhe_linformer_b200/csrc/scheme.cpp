@@ -549,6 +549,48 @@ Elem Scheme::encrypt_many(const std::vector<const Elem*>& pts) {
     return ct;
 }
 
+// Encode and encrypt B real vectors in one pass: the encoded message stays in coefficient form until the error e0 has been added to
+// it, so message and error share ONE forward transform (three per ciphertext -- v, e0 + m, e1 -- instead of four), and v lives in the
+// c1 slot of the result, so both components are finished in place (no staging buffer, no strided copies).  Same distribution as
+// Encrypt(pk, MakeCKKSPackedPlaintext(values)); used for the S + 64 input rows of a forward.
+Elem Scheme::encrypt_values_many(const double* vals, int B, int n, int level, int slots) {
+    if (!pk_) throw std::runtime_error("Encrypt: no public key");
+    if (level < 0 || level >= P.L) throw std::invalid_argument("encode: level out of range");
+    if (B < 1) throw std::invalid_argument("Encrypt (batched): no vectors");
+    const int Nh = P.N / 2, l = P.L - level, N = P.N;
+    if (slots < 1 || slots > Nh || (slots & (slots - 1))) throw std::invalid_argument("encode: slots must be a power of two <= N/2");
+    if (n < 0 || n > slots) throw std::invalid_argument("encode (batched): more values than slots");
+    DevFft& f = dev_fft(slots);
+    const size_t each = (size_t)slots, pl = (size_t)l * N, pkl = (size_t)P.L * N, cs = 2 * pl;
+    const LimbSel sel = sel_range(0, l);
+    double* d = (double*)eng.alloc(2 * each * B);
+    FLK_CUDA(cudaMemsetAsync(d, 0, 2 * each * B * sizeof(double), eng.stream));
+    FLK_CUDA(cudaMemcpy2DAsync(d, each * sizeof(double), vals, (size_t)n * sizeof(double), (size_t)n * sizeof(double), B, cudaMemcpyHostToDevice, eng.stream));
+    u64* m = eng.alloc(pl * B);                                   // message, then message + e0, coefficient form -> evaluation form
+    launch_encode(eng.T, m, d, d + each * B, slots, P.sf[level], l, f.rot, f.cre, f.cim, eng.stream, 0, B);
+    eng.release((u64*)d);
+    u64* e = eng.alloc(pl * B);
+    auto sample = [&](u64* dst, int kind, size_t stride) {
+        launch_sample_limbs_csprng(eng.T, dst, rng_keys_[(int)Use::Encrypt], rng_stream_, kind, sel, eng.stream, B, stride);
+        rng_stream_ += (u64)B;
+    };
+    sample(e, 1, pl);
+    launch_ew(eng.T, EwOp::Add, m, m, e, sel, 1, B, pl, pl, 0, eng.stream);
+    eng.ntt(m, sel, B, pl);
+    Elem ct = make(2, l, 1, P.sf[level], slots, B);
+    u64* c0 = ct.data(); u64* c1 = c0 + pl;
+    sample(c1, 0, cs);                                            // v, in the c1 slot of every ciphertext
+    eng.ntt(c1, sel, B, cs);
+    launch_ew(eng.T, EwOp::Mul, c0, c1, pk_, sel, 1, B, cs, 0, 0, eng.stream);            // c0 = pk0 v
+    launch_ew(eng.T, EwOp::Add, c0, c0, m, sel, 1, B, cs, pl, 0, eng.stream);             //      + e0 + m
+    launch_ew(eng.T, EwOp::Mul, c1, c1, pk_ + pkl, sel, 1, B, cs, 0, 0, eng.stream);      // c1 = pk1 v
+    sample(e, 1, pl);
+    eng.ntt(e, sel, B, pl);
+    launch_ew(eng.T, EwOp::Add, c1, c1, e, sel, 1, B, cs, pl, 0, eng.stream);             //      + e1
+    eng.release(m); eng.release(e);
+    return ct;
+}
+
 Elem Scheme::encrypt_with(const Elem& pt, bool seeded, u64 seed) {
     if (!pk_) throw std::runtime_error("Encrypt: no public key");
     if (pt.ncomp != 1) throw std::invalid_argument("Encrypt: plaintext expected");

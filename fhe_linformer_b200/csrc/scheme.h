@@ -92,6 +92,7 @@ public:
 
     // ---- encode / encrypt / decrypt (MakeCKKSPackedPlaintext F.cpp:353, Encrypt :380, Decrypt :389) ----
     Elem encode(const cplx* vals, int n, int level, int slots, int deg = 1);
+    Elem encrypt_values_many(const double* vals, int B, int n, int level, int slots);   // encode + encrypt, one batched ciphertext
     Elem encode_many_real(const double* vals, int B, int n, int level, int slots);   // one batched plaintext
     Elem encode_real(const double* vals, int n, int level, int slots);
     Elem encode_at(const cplx* vals, int n, int l, double scale, int slots, int deg);   // explicit limb count / scale

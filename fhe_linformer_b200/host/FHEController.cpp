@@ -501,7 +501,7 @@ vector<Ctxt> FHEController::read_expanded_inputs(const vector<string>& filenames
         for (const string& f : filenames) pts.push_back(read_plain_expanded_input(f, 0, scale));
         return encrypt_many(pts);
     }
-    // all rows of a chunk as one batched plaintext (one upload, one encoding) and one batched encryption
+    // all rows of a chunk in one pass: one upload, one batched encoding + encryption (fl_encrypt_values_many)
     vector<Ctxt> out;
     for (size_t first = 0; first < filenames.size(); first += (size_t)max_rows_per_batch) {
         const size_t last = std::min(filenames.size(), first + (size_t)max_rows_per_batch), count = last - first;
@@ -510,13 +510,8 @@ vector<Ctxt> FHEController::read_expanded_inputs(const vector<string>& filenames
             const vector<double> v = stretch(read_values_from_file(filenames[first + i]), 128, 128, 128, scale);
             std::copy(v.begin(), v.begin() + std::min(v.size(), (size_t)num_slots), slots.begin() + i * (size_t)num_slots);
         }
-        fl_elem* pt = nullptr;
-        need(fl_encode_many(ctx_, slots.data(), (int)count, num_slots, 0, num_slots, &pt), "MakeCKKSPackedPlaintext");
-        const fl_elem* one[1] = {pt};
         fl_elem* ct = nullptr;
-        const int rc = fl_encrypt_many(ctx_, one, 1, &ct);
-        fl_elem_free(pt);
-        need(rc, "Encrypt");
+        need(fl_encrypt_values_many(ctx_, slots.data(), (int)count, num_slots, 0, num_slots, &ct), "Encrypt");
         const vector<Ctxt> part = unpack(wrap(ct));
         out.insert(out.end(), part.begin(), part.end());
     }
@@ -541,13 +536,8 @@ vector<Ctxt> FHEController::read_expanded_inputs_many(const vector<vector<string
                 const vector<double> v = stretch(read_values_from_file(files_per_sample[m][first + t]), 128, 128, 128, scale);
                 std::copy(v.begin(), v.begin() + std::min(v.size(), (size_t)num_slots), slots.begin() + (t * M + m) * (size_t)num_slots);
             }
-        fl_elem* pt = nullptr;
-        need(fl_encode_many(ctx_, slots.data(), (int)(count * M), num_slots, 0, num_slots, &pt), "MakeCKKSPackedPlaintext");
-        const fl_elem* one[1] = {pt};
         fl_elem* ct = nullptr;
-        const int rc = fl_encrypt_many(ctx_, one, 1, &ct);
-        fl_elem_free(pt);
-        need(rc, "Encrypt");
+        need(fl_encrypt_values_many(ctx_, slots.data(), (int)(count * M), num_slots, 0, num_slots, &ct), "Encrypt");
         const vector<Ctxt> part = unpack(wrap(ct), (int)M);
         out.insert(out.end(), part.begin(), part.end());
     }

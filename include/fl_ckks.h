@@ -136,6 +136,9 @@ int fl_encode(fl_ctx* c, const double* re, const double* im, int n, int level, i
 /* `count` real vectors (n values each, row-major in re) -> ONE batched plaintext in one upload and five launches; element i is
    bit-identical to fl_encode(re + i n, NULL, n, ...).  The read_*_input loops of a forward (F.cpp:628-649 per file) go through it. */
 int fl_encode_many(fl_ctx* c, const double* re, int count, int n, int level, int slots, fl_pt** out);
+/* MakeCKKSPackedPlaintext + Encrypt of `count` real vectors in one pass (F.cpp:628-649 per input file): ONE batched ciphertext;
+   message and error e0 share a forward transform, three transforms per ciphertext instead of four */
+int fl_encrypt_values_many(fl_ctx* c, const double* re, int count, int n, int level, int slots, fl_ct** out);
 int fl_encrypt(fl_ctx* c, const fl_pt* p, fl_ct** out);                         /* Encrypt F.cpp:380 */
 /* the same for n plaintexts of one level in a dozen launches: *out is ONE batched operand (fl_batch_slice gives ciphertext i).
    n = 1 with a batched plaintext (fl_encode_many) encrypts every element of it. */

@@ -209,6 +209,13 @@ def test_batched_encryption(ctx):
         assert (pt.export() == c.encode(r, level=2).export()).all()
     for r, ct in zip(rows, c.encrypt_many(many)):
         assert np.abs(c.decrypt(ct)[: n // 2] - r).max() < 1e-7 and np.abs(c.decrypt(ct)[n // 2:]).max() < 1e-7
+    # fl_encrypt_values_many: encode + encrypt in one pass (message and e0 share a transform); same decryptions, own randomness
+    direct = c.encrypt_values_many(rows, level=2)
+    assert len(direct) == 5
+    for r, ct in zip(rows, direct):
+        assert ct.level == 2 and np.abs(c.decrypt(ct)[: n // 2] - r).max() < 1e-7 and np.abs(c.decrypt(ct)[n // 2:]).max() < 1e-7
+    twice = c.encrypt_values_many(np.stack([rows[0], rows[0]]), level=0)
+    assert (twice[0].export() != twice[1].export()).mean() > 0.99
     got = c.encrypt_many(parts[1:4])                                            # slices of a batched plaintext: the contiguous path
     for r, ct in zip(rows[1:4], got):
         assert np.abs(c.decrypt(ct)[: n // 2] - r).max() < 1e-7
