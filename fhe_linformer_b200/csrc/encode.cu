@@ -46,8 +46,9 @@ __global__ void __launch_bounds__(kThreads) sample_limbs_kernel(u64* __restrict_
 }
 // the same two samplers from ChaCha20 key stream: coefficient j takes block j of stream `nonce`; the thread draws the small integer
 // once and writes its residue into every limb (one key-stream block per coefficient, not per limb)
+// accumulate: dst <- dst + sample (mod q) instead of dst <- sample (an error polynomial added to a message in coefficient form)
 __global__ void __launch_bounds__(kThreads) sample_limbs_csprng_kernel(u64* __restrict__ dst, ChaChaKey key, u64 nonce, int kind, DevTables T,
-                                                                       LimbSel sel, size_t batch_stride) {
+                                                                       LimbSel sel, size_t batch_stride, int accumulate) {
     const int j = blockIdx.x * kThreads + threadIdx.x;
     if (j >= T.N) return;
     dst += (size_t)blockIdx.z * batch_stride;      // polynomial z of a batch is stream nonce + z
@@ -56,7 +57,9 @@ __global__ void __launch_bounds__(kThreads) sample_limbs_csprng_kernel(u64* __re
     const int v = kind == 0 ? ternary_of(chacha_u64(blk, 0)) : gauss_of(chacha_u64(blk, 0), chacha_u64(blk, 1) & 1);
     for (int limb = 0; limb < sel.n; ++limb) {
         const u64 q = T.q[sel.m[limb]];
-        dst[(size_t)sel.pos[limb] * T.N + j] = v >= 0 ? (u64)v : q - (u64)(-v);
+        const u64 r = v >= 0 ? (u64)v : q - (u64)(-v);
+        u64* p = dst + (size_t)sel.pos[limb] * T.N + j;
+        *p = accumulate ? addmod(*p, r, q) : r;
     }
 }
 
@@ -177,8 +180,8 @@ void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const 
     FLK_CUDA(cudaGetLastError());
 }
 void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s, int batch,
-                                size_t batch_stride) {
-    sample_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), 1, batch), kThreads, 0, s>>>(dst, key, nonce, kind, t, sel, batch_stride);
+                                size_t batch_stride, bool accumulate) {
+    sample_limbs_csprng_kernel<<<dim3(cdiv(t.N, kThreads), 1, batch), kThreads, 0, s>>>(dst, key, nonce, kind, t, sel, batch_stride, accumulate ? 1 : 0);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s) {

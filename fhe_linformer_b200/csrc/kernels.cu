@@ -33,6 +33,19 @@ __global__ void __launch_bounds__(kThreads) ew_kernel(u64* __restrict__ out, con
     *reinterpret_cast<ulonglong2*>(out + blockIdx.y * a_bs + e) = z;
 }
 
+__global__ void __launch_bounds__(kThreads) ew_muladd_kernel(u64* __restrict__ out, const u64* __restrict__ a, const u64* __restrict__ b,
+                                                             const u64* __restrict__ c, DevTables T, LimbSel sel, size_t a_bs, size_t b_bs, size_t c_bs) {
+    const size_t per_poly = (size_t)sel.n * T.N;
+    const size_t e = ((size_t)blockIdx.x * kThreads + threadIdx.x) * 2;
+    if (e >= per_poly) return;
+    const int m = sel.m[(int)(e >> T.logN)];
+    const u64 q = T.q[m], ml = T.mu_lo[m], mh = T.mu_hi[m];
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(a + blockIdx.y * a_bs + e);
+    const ulonglong2 y = *reinterpret_cast<const ulonglong2*>(b + blockIdx.y * b_bs + e);
+    const ulonglong2 z = *reinterpret_cast<const ulonglong2*>(c + blockIdx.y * c_bs + e);
+    *reinterpret_cast<ulonglong2*>(out + blockIdx.y * a_bs + e) = make_ulonglong2(addmod(mulmod(x.x, y.x, q, ml, mh), z.x, q), addmod(mulmod(x.y, y.y, q, ml, mh), z.y, q));
+}
+
 __global__ void __launch_bounds__(kThreads) mul_scalar_kernel(u64* __restrict__ out, const u64* __restrict__ a, DevTables T, LimbSel sel,
                                                               ScalarSet sc, int polys) {
     const size_t per_poly = (size_t)sel.n * T.N;
@@ -559,6 +572,11 @@ void launch_ew(const DevTables& t, EwOp op, u64* out, const u64* a, const u64* b
         case EwOp::Sub: ew_kernel<1><<<grid, kThreads, 0, s>>>(out, a, b, t, sel, polys, a_bs, b_bs, b_ps); break;
         case EwOp::Mul: ew_kernel<2><<<grid, kThreads, 0, s>>>(out, a, b, t, sel, polys, a_bs, b_bs, b_ps); break;
     }
+    FLK_CUDA(cudaGetLastError());
+}
+void launch_ew_muladd(const DevTables& t, u64* out, const u64* a, const u64* b, const u64* c, const LimbSel& sel, int batch, size_t a_bs, size_t b_bs,
+                      size_t c_bs, cudaStream_t s) {
+    ew_muladd_kernel<<<dim3(cdiv((size_t)sel.n * t.N / 2, kThreads), batch), kThreads, 0, s>>>(out, a, b, c, t, sel, a_bs, b_bs, c_bs);
     FLK_CUDA(cudaGetLastError());
 }
 void launch_mul_scalar(const DevTables& t, u64* out, const u64* a, const ScalarSet& sc, const LimbSel& sel, int polys, cudaStream_t s) {

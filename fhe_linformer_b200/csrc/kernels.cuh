@@ -10,6 +10,9 @@ enum class EwOp : int { Add = 0, Sub = 1, Mul = 2 };
 // (ct x pt).  Buffers are [batch][polys][l][N]; limb i of every polynomial uses modulus sel.m[i].
 void launch_ew(const DevTables& t, EwOp op, u64* out, const u64* a, const u64* b, const LimbSel& sel, int polys, int batch,
                size_t a_batch_stride, size_t b_batch_stride, size_t b_poly_stride, cudaStream_t s);
+// out = a * b + c, limb-wise (one polynomial per batch element; out and a share a_batch_stride; b is broadcast when its stride is 0)
+void launch_ew_muladd(const DevTables& t, u64* out, const u64* a, const u64* b, const u64* c, const LimbSel& sel, int batch, size_t a_batch_stride,
+                      size_t b_batch_stride, size_t c_batch_stride, cudaStream_t s);
 
 struct ScalarSet {   // per-limb multiplier with Shoup companion
     u64 c[64];
@@ -155,7 +158,7 @@ void launch_uniform_limbs(const DevTables& t, u64* dst, const u64* seeds, const 
 struct ChaChaKey;
 // (batch polynomials batch_stride words apart: polynomial z is stream nonce + z)
 void launch_sample_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, int kind, const LimbSel& sel, cudaStream_t s, int batch = 1,
-                                size_t batch_stride = 0);
+                                size_t batch_stride = 0, bool accumulate = false);
 void launch_uniform_limbs_csprng(const DevTables& t, u64* dst, const ChaChaKey& key, u64 nonce, const LimbSel& sel, cudaStream_t s);
 // special inverse FFT of (re, im)[slots] in place, then coefficient form of round(scale * values) in l limbs (not yet NTT'd);
 // kext > 0 appends the residues modulo the first kext special limbs (plaintexts in the extended basis Q_l u P)

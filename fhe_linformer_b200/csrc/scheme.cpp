@@ -569,25 +569,22 @@ Elem Scheme::encrypt_values_many(const double* vals, int B, int n, int level, in
     u64* m = eng.alloc(pl * B);                                   // message, then message + e0, coefficient form -> evaluation form
     launch_encode(eng.T, m, d, d + each * B, slots, P.sf[level], l, f.rot, f.cre, f.cim, eng.stream, 0, B);
     eng.release((u64*)d);
-    u64* e = eng.alloc(pl * B);
-    auto sample = [&](u64* dst, int kind, size_t stride) {
-        launch_sample_limbs_csprng(eng.T, dst, rng_keys_[(int)Use::Encrypt], rng_stream_, kind, sel, eng.stream, B, stride);
+    auto sample = [&](u64* dst, int kind, size_t stride, bool accumulate) {
+        launch_sample_limbs_csprng(eng.T, dst, rng_keys_[(int)Use::Encrypt], rng_stream_, kind, sel, eng.stream, B, stride, accumulate);
         rng_stream_ += (u64)B;
     };
-    sample(e, 1, pl);
-    launch_ew(eng.T, EwOp::Add, m, m, e, sel, 1, B, pl, pl, 0, eng.stream);
+    sample(m, 1, pl, true);                                       // m + e0, still in coefficient form
     eng.ntt(m, sel, B, pl);
     Elem ct = make(2, l, 1, P.sf[level], slots, B);
     u64* c0 = ct.data(); u64* c1 = c0 + pl;
-    sample(c1, 0, cs);                                            // v, in the c1 slot of every ciphertext
+    sample(c1, 0, cs, false);                                     // v, in the c1 slot of every ciphertext
     eng.ntt(c1, sel, B, cs);
-    launch_ew(eng.T, EwOp::Mul, c0, c1, pk_, sel, 1, B, cs, 0, 0, eng.stream);            // c0 = pk0 v
-    launch_ew(eng.T, EwOp::Add, c0, c0, m, sel, 1, B, cs, pl, 0, eng.stream);             //      + e0 + m
-    launch_ew(eng.T, EwOp::Mul, c1, c1, pk_ + pkl, sel, 1, B, cs, 0, 0, eng.stream);      // c1 = pk1 v
-    sample(e, 1, pl);
+    launch_ew_muladd(eng.T, c0, c1, pk_, m, sel, B, cs, 0, pl, eng.stream);               // c0 = pk0 v + (e0 + m)
+    u64* e = m;                                                   // (the message buffer is free again)
+    sample(e, 1, pl, false);
     eng.ntt(e, sel, B, pl);
-    launch_ew(eng.T, EwOp::Add, c1, c1, e, sel, 1, B, cs, pl, 0, eng.stream);             //      + e1
-    eng.release(m); eng.release(e);
+    launch_ew_muladd(eng.T, c1, c1, pk_ + pkl, e, sel, B, cs, 0, pl, eng.stream);         // c1 = pk1 v + e1
+    eng.release(m);
     return ct;
 }
 
