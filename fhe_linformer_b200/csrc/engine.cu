@@ -486,13 +486,16 @@ void Engine::linear_transform(u64* out, const u64* ct, int B, const LtPlan& p) {
         u64* up = alloc(up_bs * B);
         modup_batch(up, c1, cs, B, l);
         accb = alloc(acc_bs * B * (size_t)(n1 - 1));
+        IpJobs babies{};                                       // every baby rotation's key product in one launch (the operand is shared)
         for (int i = 1; i < n1; ++i) {
             if (!((used >> i) & 1u)) continue;
             u64* dst = accb + (size_t)(i - 1) * B * acc_bs;
-            launch_inner_product(T, ks, dst, up, c1, p.baby_evk[i], B, acc_bs, up_bs, cs, stream);
+            babies.acc[babies.n] = dst; babies.up[babies.n] = up; babies.c[babies.n] = c1; babies.evk[babies.n] = p.baby_evk[i];
+            ++babies.n;
             a.accb[i] = dst; a.map[i] = automorph_map(p.baby_g[i]);
             ++nb;
         }
+        if (babies.n) launch_inner_product_jobs(T, ks, babies, B, acc_bs, up_bs, cs, stream);
         release(up);
     }
     u64* W = alloc(acc_bs * B * (size_t)n2);
@@ -517,13 +520,16 @@ void Engine::linear_transform(u64* out, const u64* ct, int B, const LtPlan& p) {
         u64* acc2 = alloc(acc_bs * B * (size_t)r);
         GatherArgs gz{}, g0{};
         gz.n = g0.n = r;
+        IpJobs giants{};                                       // one launch for all giant steps (each has its own operand and key)
         for (int j = 0; j < r; ++j) {
             const u64* wj = w + (size_t)j * B * cs;
-            launch_inner_product(T, ks, acc2 + (size_t)j * B * acc_bs, up2 + (size_t)j * B * up_bs, wj + (size_t)l * N, p.giant_evk[j], B, acc_bs, up_bs, cs,
-                                 stream);
+            giants.acc[giants.n] = acc2 + (size_t)j * B * acc_bs; giants.up[giants.n] = up2 + (size_t)j * B * up_bs;
+            giants.c[giants.n] = wj + (size_t)l * N; giants.evk[giants.n] = p.giant_evk[j];
+            ++giants.n;
             gz.src[j] = acc2 + (size_t)j * B * acc_bs; g0.src[j] = wj;
             gz.map[j] = g0.map[j] = automorph_map(p.giant_g[j]);
         }
+        launch_inner_product_jobs(T, ks, giants, B, acc_bs, up_bs, cs, stream);
         release(up2);
         u64* Z = alloc(acc_bs * B);
         launch_gather_multi(T, Z, gz, l, ext, 2 * ext, B, acc_bs, acc_bs, stream);

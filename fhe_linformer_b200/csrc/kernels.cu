@@ -147,12 +147,18 @@ __global__ void __launch_bounds__(kThreads) modup_conv_kernel(u64* __restrict__ 
 // is used IPB times.  The digit loop is unrolled (BETA is a template parameter) so all loads of a thread are in flight together.
 constexpr int kIpb = 8;
 template <int BETA>
-__global__ void __launch_bounds__(kThreads) inner_product_kernel(u64* __restrict__ acc, const u64* __restrict__ up, const u64* __restrict__ c_eval,
-                                                                 const u64* __restrict__ evk, DevTables T, KsLevel ks, int batch, size_t acc_bs,
-                                                                 size_t up_bs, size_t c_bs, int t_first) {
-    // grid (coefficients, batch groups, limbs): CTAs are issued x, then y, then z, so all batch groups of one limb run back to back
-    // and that limb's key words (2 beta x N, streamed from HBM once) are served from L2 to every group after the first
-    const int t = t_first + blockIdx.z, l = ks.l, ext = l + T.K, b0 = blockIdx.y * kIpb;
+__global__ void __launch_bounds__(kThreads) inner_product_kernel(IpJobs jobs, DevTables T, KsLevel ks, int batch, size_t acc_bs, size_t up_bs, size_t c_bs,
+                                                                 int t_first) {
+    // grid (coefficients, jobs x batch groups, limbs): CTAs are issued x, then y, then z, so all batch groups of one limb run back to
+    // back and that limb's key words (2 beta x N, streamed from HBM once) are served from L2 to every group after the first.  Several
+    // jobs (operand, key, output) share one launch -- the baby steps of a BSGS transform multiply ONE extended operand by up to 15 keys:
+    // with the job index fastest in y, that operand's limb is read from HBM once and from L2 by the other keys.
+    const int job = blockIdx.y % jobs.n;
+    u64* __restrict__ acc = jobs.acc[job];
+    const u64* __restrict__ up = jobs.up[job];
+    const u64* __restrict__ c_eval = jobs.c[job];
+    const u64* __restrict__ evk = jobs.evk[job];
+    const int t = t_first + blockIdx.z, l = ks.l, ext = l + T.K, b0 = (blockIdx.y / jobs.n) * kIpb;
     const int j = (blockIdx.x * kThreads + threadIdx.x) * 2;
     if (j >= T.N) return;
     const int m = t < l ? t : T.L + (t - l);
@@ -614,11 +620,18 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
 }
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange rg) {
+    IpJobs one{};
+    one.n = 1; one.acc[0] = acc; one.up[0] = up; one.c[0] = c_eval; one.evk[0] = evk;
+    launch_inner_product_jobs(t, ks, one, batch, acc_bs, up_bs, c_bs, s, rg);
+}
+void launch_inner_product_jobs(const DevTables& t, const KsLevel& ks, const IpJobs& jobs, int batch, size_t acc_bs, size_t up_bs, size_t c_bs,
+                               cudaStream_t s, LimbRange rg) {
+    if (jobs.n < 1 || jobs.n > kIpJobsMax) throw std::invalid_argument("key inner product: 1..16 jobs per launch");
     if (rg.count < 0) rg = LimbRange{0, ks.l + t.K};
     if (rg.count == 0) return;
-    const dim3 grid(cdiv(t.N / 2, kThreads), (batch + kIpb - 1) / kIpb, rg.count);
+    const dim3 grid(cdiv(t.N / 2, kThreads), jobs.n * ((batch + kIpb - 1) / kIpb), rg.count);
     switch (ks.beta) {
-#define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(acc, up, c_eval, evk, t, ks, batch, acc_bs, up_bs, c_bs, rg.first); break;
+#define FLK_CASE(X) case X: inner_product_kernel<X><<<grid, kThreads, 0, s>>>(jobs, t, ks, batch, acc_bs, up_bs, c_bs, rg.first); break;
         FLK_CASE(1) FLK_CASE(2) FLK_CASE(3) FLK_CASE(4) FLK_CASE(5) FLK_CASE(6) FLK_CASE(7) FLK_CASE(8)
 #undef FLK_CASE
         default: throw std::invalid_argument("more than 8 key-switch digits is not supported");

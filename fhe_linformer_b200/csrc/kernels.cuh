@@ -62,6 +62,18 @@ void launch_modup_conv(const DevTables& t, const KsLevel& ks, u64* up, const u64
 // acc[b][{0,1}][t] = sum_d U_d[t] * evk_{b,a}[d][mod(t)];  U_d[t] = c_eval[b][t] inside digit d else up[b][d][t]
 void launch_inner_product(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* evk, int batch,
                           size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s, LimbRange targets = kAllLimbs);
+// Several (operand, key, output) jobs of identical shape in ONE launch: the baby steps of a BSGS transform (one operand, up to 15
+// keys: the operand's limb is fetched from HBM once) and its giant steps (one operand per key).
+constexpr int kIpJobsMax = 16;
+struct IpJobs {
+    u64* acc[kIpJobsMax];
+    const u64* up[kIpJobsMax];
+    const u64* c[kIpJobsMax];
+    const u64* evk[kIpJobsMax];
+    int n;
+};
+void launch_inner_product_jobs(const DevTables& t, const KsLevel& ks, const IpJobs& jobs, int batch, size_t acc_bs, size_t up_bs, size_t c_bs,
+                               cudaStream_t s, LimbRange limbs = kAllLimbs);
 // hoisted multi-rotation: acc[b][{0,1}][t][j] = sum_k (sum_d U_d[b][t] evk_k[d][mod(t)])[map_k[j]], nk <= kHoistMax keys with their gather maps
 void launch_inner_product_multi(const DevTables& t, const KsLevel& ks, u64* acc, const u64* up, const u64* c_eval, const u64* const* evks,
                                 const uint32_t* const* maps, int nk, int batch, size_t acc_bs, size_t up_bs, size_t c_bs, cudaStream_t s);
