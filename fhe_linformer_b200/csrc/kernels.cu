@@ -224,7 +224,12 @@ __global__ void __launch_bounds__(kThreads, KPR_MAX > 1 ? 4 : 1) inner_product_m
     // The carry-free accumulators take 8 products before they must be reduced, so the digit products of KPR = 8 / BETA keys
     // (gathered at different source positions, but summed into the same output) share one reduction -- the reduction costs
     // more instructions than a key's products.
-    constexpr int KPR = (BETA >= 8 ? 1 : 8 / BETA) < KPR_MAX ? (BETA >= 8 ? 1 : 8 / BETA) : KPR_MAX;
+    constexpr int KPR_WIDE = (BETA >= 8 ? 1 : 8 / BETA) < KPR_MAX ? (BETA >= 8 ? 1 : 8 / BETA) : KPR_MAX;
+    // Below 2^56 (every Q limb) the halves of a residue are 30 + 26 bits: the low accumulator still takes 2^60 per product, so 15
+    // products fit it together with the fold of the high one (15 2^60 + 4q < 2^64), the other two stay far below their bounds --
+    // 15 / BETA keys share a reduction there instead of 8 / BETA (the reductions were 39 % of this kernel's instructions).
+    constexpr int KPR_NARROW = KPR_MAX == 1 ? 1 : (BETA >= 15 ? 1 : 15 / BETA);
+    const int KPR = (rc.q >> 56) != 0 ? KPR_WIDE : KPR_NARROW;
     u64 r0[IPB], r1[IPB];
     Acc3 s0[IPB], s1[IPB];
 #pragma unroll
